@@ -1,0 +1,744 @@
+// engine.cu -- host side of libagp.so: context, stream-ordered workspace, the fused "fit"
+// (Gram -> blocked right-looking Cholesky with bordered forward solve -> backward solve -> logpdf),
+// prediction, sampling, and the extern "C" ABI declared in include/agp.h.
+//
+// Data layout in HBM: the factor lives in ONE column-major buffer of
+// (n_pad + 128) x n_pad elements, n_pad = N rounded up to 128 with identity padding.  The Gram kernel
+// writes the lower triangle directly into it, the Cholesky runs in place (A = L L', L = U'), and the
+// extra 128-row "border" tile holds delta' = (Y - m)' so that the panel TRSM + trailing update
+// perform the forward substitution v = L^-1 delta for free (up to 128 right-hand sides).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "agp.h"
+#include "kernels.h"
+
+#define TILE AGP_TILE
+
+struct agp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  agp_config cfg{};
+  std::string err;
+  int64_t info = 0;
+  int memspace = AGP_MEM_HOST;
+  double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaEvent_t ev[8]{};
+  std::vector<cudaEvent_t> prof_ev;  // pairs around every trailing-update launch
+  int prof_used = 0;
+  int profile = 1;
+  int rank = 0, nranks = 1, grid_p = 1, grid_q = 1;
+  void* nccl = nullptr;
+};
+
+struct agp_post {
+  agp_ctx* ctx = nullptr;
+  int dtype = AGP_F64;
+  int64_t n = 0, n_pad = 0, lda = 0;
+  int D = 0;
+  void* L = nullptr;      // (n_pad+TILE) x n_pad
+  void* Dinv = nullptr;   // nblk x TILE x TILE
+  void* Xt = nullptr;     // n_pad x D transformed points
+  void* alpha = nullptr;  // n_pad
+  void* ard = nullptr;    // D (device) or null
+  agp_kernel k{};
+  int mean_kind = 0;
+  double mean_c = 0.0;
+  double logdet = 0.0;
+};
+
+struct agp_vfe_post {
+  agp_ctx* ctx = nullptr;
+  int dtype = AGP_F32;
+  int64_t m = 0, m_pad = 0, lda = 0;
+  int D = 0;
+  void* U = nullptr;      // factor of Kzz + jitter   (m_pad+TILE) x m_pad
+  void* Udinv = nullptr;
+  void* Lam = nullptr;    // factor of A A' + I
+  void* Ldinv = nullptr;
+  void* Zt = nullptr;     // m_pad x D
+  void* m_e = nullptr;    // m_pad
+  void* ard = nullptr;
+  agp_kernel k{};
+  int mean_kind = 0;
+  double mean_c = 0.0;
+};
+
+namespace {
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      char _b[512];                                                                       \
+      snprintf(_b, sizeof(_b), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      ctx->err = _b;                                                                      \
+      return AGP_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+struct Scratch {  // stream-ordered allocations freed together
+  agp_ctx* ctx;
+  std::vector<void*> ptrs;
+  explicit Scratch(agp_ctx* c) : ctx(c) {}
+  ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, ctx->stream); }
+  cudaError_t alloc(void** p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+    if (e == cudaSuccess) ptrs.push_back(*p);
+    return e;
+  }
+  void release(void* p) {  // ownership moves out
+    for (auto& q : ptrs) if (q == p) { q = ptrs.back(); ptrs.pop_back(); return; }
+  }
+};
+
+template <typename T>
+int upload(agp_ctx* ctx, Scratch& sc, const void* src, size_t count, bool always_host, T** out) {
+  if (!src || count == 0) { *out = nullptr; return AGP_OK; }
+  if (!always_host && ctx->memspace == AGP_MEM_DEVICE) { *out = (T*)src; return AGP_OK; }
+  void* d = nullptr;
+  CK(sc.alloc(&d, count * sizeof(T)));
+  CK(cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  *out = (T*)d;
+  return AGP_OK;
+}
+
+template <typename T>
+int download(agp_ctx* ctx, void* dst, const T* src, size_t count, bool always_host) {
+  if (!dst || count == 0) return AGP_OK;
+  cudaMemcpyKind kind = (!always_host && ctx->memspace == AGP_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  CK(cudaMemcpyAsync(dst, src, count * sizeof(T), kind, ctx->stream));
+  return AGP_OK;
+}
+
+int check_kernel(agp_ctx* ctx, const agp_kernel* k, int D) {
+  if (!k) { ctx->err = "kernel spec is NULL"; return AGP_ERR_INVALID; }
+  if (k->family < AGP_SE || k->family > AGP_LINEAR) { ctx->err = "unsupported kernel family"; return AGP_ERR_UNSUPPORTED; }
+  if (k->transform < AGP_T_NONE || k->transform > AGP_T_ARD) { ctx->err = "unsupported transform"; return AGP_ERR_UNSUPPORTED; }
+  if (k->transform == AGP_T_ARD && !k->ard) { ctx->err = "ARD transform without weights"; return AGP_ERR_INVALID; }
+  if (D <= 0) { ctx->err = "D must be positive"; return AGP_ERR_DIM_MISMATCH; }
+  return AGP_OK;
+}
+
+void prof_begin(agp_ctx* ctx) { ctx->prof_used = 0; }
+cudaEvent_t prof_event(agp_ctx* ctx) {
+  if (ctx->prof_used == (int)ctx->prof_ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    ctx->prof_ev.push_back(e);
+  }
+  return ctx->prof_ev[ctx->prof_used++];
+}
+double prof_total_ms(agp_ctx* ctx) {
+  double t = 0;
+  for (int i = 0; i + 1 < ctx->prof_used; i += 2) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->prof_ev[i], ctx->prof_ev[i + 1]) == cudaSuccess) t += ms;
+  }
+  return t;
+}
+
+// ---- blocked right-looking Cholesky, in place, lower; rows include the border tile -------------
+template <typename T>
+void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t rows_total, T* Dinv,
+                      double* logdet_part, int* info) {
+  cudaStream_t s = ctx->stream;
+  const int nblk = (int)(n_pad / TILE);
+  for (int k = 0; k < nblk; ++k) {
+    T* Akk = L + (int64_t)k * TILE + (int64_t)k * TILE * lda;
+    launch_potrf_diag<T>(Akk, lda, Dinv + (int64_t)k * TILE * TILE, logdet_part, k, info, s);
+    const int64_t rows_below = rows_total - (int64_t)(k + 1) * TILE;
+    if (rows_below <= 0) continue;
+    T* A21 = Akk + TILE;
+    GemmArgs t{};  // A21 <- A21 * inv(L11)'
+    t.A = A21; t.lda = lda; t.a_kmajor = 0;
+    t.B = Dinv + (int64_t)k * TILE * TILE; t.ldb = TILE; t.b_kmajor = 0;
+    t.C = A21; t.ldc = lda; t.M = rows_below; t.N = TILE; t.K = TILE;
+    launch_gemm<T>(t, s);
+    const int64_t cols_trail = n_pad - (int64_t)(k + 1) * TILE;
+    if (cols_trail <= 0) continue;
+    GemmArgs u{};  // A22 -= A21 A21'   (lower tiles only)
+    u.A = A21; u.lda = lda; u.a_kmajor = 0;
+    u.B = A21; u.ldb = lda; u.b_kmajor = 0;
+    u.C = A21 + (int64_t)TILE * lda; u.ldc = lda;
+    u.M = rows_below; u.N = cols_trail; u.K = TILE; u.alpha_neg = 1; u.beta_one = 1; u.lower_only = 1;
+    if (ctx->profile) cudaEventRecord(prof_event(ctx), s);
+    launch_gemm<T>(u, s);
+    if (ctx->profile) cudaEventRecord(prof_event(ctx), s);
+  }
+}
+
+// V <- L^-1 V for a n_pad x ncols block of right-hand sides (ncols multiple of 4), in place
+template <typename T>
+void forward_subst_multi(agp_ctx* ctx, const T* L, int64_t lda, const T* Dinv, int64_t n_pad, T* B, int64_t ldb,
+                         int64_t ncols) {
+  cudaStream_t s = ctx->stream;
+  const int nblk = (int)(n_pad / TILE);
+  for (int k = 0; k < nblk; ++k) {
+    T* Bk = B + (int64_t)k * TILE;
+    GemmArgs a{};
+    a.A = Dinv + (int64_t)k * TILE * TILE; a.lda = TILE; a.a_kmajor = 0;
+    a.B = Bk; a.ldb = ldb; a.b_kmajor = 1;
+    a.C = Bk; a.ldc = ldb; a.M = TILE; a.N = ncols; a.K = TILE;
+    launch_gemm<T>(a, s);
+    const int64_t rows_below = n_pad - (int64_t)(k + 1) * TILE;
+    if (rows_below <= 0) continue;
+    GemmArgs u{};
+    u.A = L + (int64_t)(k + 1) * TILE + (int64_t)k * TILE * lda; u.lda = lda; u.a_kmajor = 0;
+    u.B = Bk; u.ldb = ldb; u.b_kmajor = 1;
+    u.C = Bk + TILE; u.ldc = ldb; u.M = rows_below; u.N = ncols; u.K = TILE; u.alpha_neg = 1; u.beta_one = 1;
+    launch_gemm<T>(u, s);
+  }
+}
+
+template <typename T>
+void fill_gram_params(GramParams& gp, const agp_kernel* k, int symmetric, int lower_only, int64_t va, int64_t vb,
+                      const agp_noise* noise, const T* noise_v_dev) {
+  gp.family = k->family;
+  gp.variance = k->variance;
+  gp.linear_c = k->linear_c;
+  gp.symmetric = symmetric;
+  gp.lower_only = lower_only;
+  gp.valid_a = va;
+  gp.valid_b = vb;
+  gp.noise_kind = noise ? noise->kind : -1;
+  gp.noise_s = noise ? noise->s : 0.0;
+  gp.noise_v = noise_v_dev;
+}
+
+// transformed, padded, point-major copy of a point set on the device
+template <typename T>
+int prep_points(agp_ctx* ctx, Scratch& sc, const agp_kernel* k, const T* ard_dev, int layout, const void* X,
+                int64_t n, int64_t n_pad, int D, T** Xt_out, bool keep) {
+  T* Xd = nullptr;
+  int rc = upload<T>(ctx, sc, X, (size_t)n * D, false, &Xd);
+  if (rc) return rc;
+  void* xt = nullptr;
+  CK(cudaMallocAsync(&xt, (size_t)(n_pad > 0 ? n_pad : 1) * D * sizeof(T), ctx->stream));
+  if (!keep) sc.ptrs.push_back(xt);
+  launch_prep_points<T>(Xd, layout, n, n_pad, D, k->transform, k->scale, ard_dev, (T*)xt, ctx->stream);
+  *Xt_out = (T*)xt;
+  return AGP_OK;
+}
+
+template <typename T>
+int fit_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_noise* noise, int layout,
+             const void* X, int64_t N, int D, const void* Y, int S, void* logpdf_out, void* alpha_out,
+             agp_post** post_out, T** L_keep /*optional raw factor out for rand*/, int64_t* lda_out,
+             Scratch* outer_sc) {
+  int rc = check_kernel(ctx, k, D);
+  if (rc) return rc;
+  if (N <= 0) { ctx->err = "N must be positive"; return AGP_ERR_DIM_MISMATCH; }
+  if (S < 0 || S > TILE) { ctx->err = "number of right-hand sides must be in [0,128]"; return AGP_ERR_UNSUPPORTED; }
+  if (S > 0 && !Y) { ctx->err = "Y is NULL"; return AGP_ERR_INVALID; }
+  static const agp_mean zero_mean{0, 0.0, nullptr};
+  static const agp_noise default_noise{0, 1e-18, nullptr};  // default_sigma^2, finite_gp_projection.jl:17
+  if (!mean) mean = &zero_mean;
+  if (!noise) noise = &default_noise;
+  if (mean->kind == 2 && !mean->v) { ctx->err = "mean vector is NULL"; return AGP_ERR_INVALID; }
+  if (noise->kind == 1 && !noise->v) { ctx->err = "noise vector is NULL"; return AGP_ERR_INVALID; }
+
+  cudaStream_t s = ctx->stream;
+  CK(cudaSetDevice(ctx->device));
+  Scratch sc(ctx);
+  const int64_t n_pad = round_up(N, TILE), lda = n_pad + TILE;
+  const int nblk = (int)(n_pad / TILE);
+  prof_begin(ctx);
+  CK(cudaEventRecord(ctx->ev[0], s));
+
+  // ---- H2D
+  T *ard_d = nullptr, *mean_d = nullptr, *noise_d = nullptr, *Yd = nullptr, *Xt = nullptr;
+  if (k->transform == AGP_T_ARD) { rc = upload<T>(ctx, sc, k->ard, D, true, &ard_d); if (rc) return rc; }
+  if (mean->kind == 2) { rc = upload<T>(ctx, sc, mean->v, N, true, &mean_d); if (rc) return rc; }
+  if (noise->kind == 1) { rc = upload<T>(ctx, sc, noise->v, N, true, &noise_d); if (rc) return rc; }
+  if (S > 0) { rc = upload<T>(ctx, sc, Y, (size_t)N * S, false, &Yd); if (rc) return rc; }
+  const bool keep = (post_out != nullptr);
+  rc = prep_points<T>(ctx, sc, k, ard_d, layout, X, N, n_pad, D, &Xt, keep);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev[1], s));
+
+  // ---- buffers
+  void *Lv = nullptr, *Dinvv = nullptr, *alphav = nullptr;
+  CK(cudaMallocAsync(&Lv, (size_t)lda * n_pad * sizeof(T), s));
+  CK(cudaMallocAsync(&Dinvv, (size_t)nblk * TILE * TILE * sizeof(T), s));
+  CK(cudaMallocAsync(&alphav, (size_t)n_pad * sizeof(T), s));
+  T* L = (T*)Lv; T* Dinv = (T*)Dinvv; T* alpha = (T*)alphav;
+  agp_post* post = nullptr;
+  if (keep) {
+    post = new agp_post();
+    post->ctx = ctx; post->dtype = sizeof(T) == 8 ? AGP_F64 : AGP_F32;
+    post->n = N; post->n_pad = n_pad; post->lda = lda; post->D = D;
+    post->L = Lv; post->Dinv = Dinvv; post->Xt = Xt; post->alpha = alphav;
+    post->k = *k; post->k.ard = nullptr;
+    post->mean_kind = mean->kind == 2 ? 0 : mean->kind; post->mean_c = mean->c;
+    if (ard_d) { sc.release(ard_d); post->ard = ard_d; }
+  } else if (L_keep) {
+    outer_sc->ptrs.push_back(Lv); sc.ptrs.push_back(Dinvv); sc.ptrs.push_back(alphav);
+  } else {
+    sc.ptrs.push_back(Lv); sc.ptrs.push_back(Dinvv); sc.ptrs.push_back(alphav);
+  }
+  double* dscal = nullptr;  // [0..nblk) logdet parts, [nblk..nblk+TILE) sqmahal, [+1] logdet
+  void* tmp = nullptr;
+  CK(sc.alloc(&tmp, (size_t)(nblk + TILE + 2) * sizeof(double)));
+  dscal = (double*)tmp;
+  int* dinfo = nullptr;
+  CK(sc.alloc(&tmp, sizeof(int)));
+  dinfo = (int*)tmp;
+  CK(cudaMemsetAsync(dinfo, 0, sizeof(int), s));
+  T* rwork = nullptr;
+  CK(sc.alloc(&tmp, (size_t)(S > 0 ? S : 1) * n_pad * sizeof(T)));
+  rwork = (T*)tmp;
+  T* lp_d = nullptr;
+  CK(sc.alloc(&tmp, (size_t)TILE * sizeof(T)));
+  lp_d = (T*)tmp;
+
+  // ---- Gram (+ noise) straight into the factor buffer, border rows = delta'
+  GramParams gp{};
+  fill_gram_params<T>(gp, k, 1, 1, N, N, noise, noise_d);
+  launch_gram<T>(Xt, Xt, n_pad, n_pad, D, L, lda, gp, s);
+  launch_border_init<T>(L, lda, N, n_pad, Yd, N, S, mean->kind, mean->c, mean_d, s);
+  CK(cudaEventRecord(ctx->ev[2], s));
+
+  // ---- Cholesky (forward substitution of delta rides along in the border tile)
+  cholesky_inplace<T>(ctx, L, lda, n_pad, lda, Dinv, dscal, dinfo);
+  CK(cudaEventRecord(ctx->ev[3], s));
+
+  // ---- sqmahal, alpha = L^-T v, logpdf
+  if (S > 0) {
+    launch_extract_v<T>(L, lda, n_pad, S, rwork, dscal + nblk, s);
+    if (alpha_out || keep) {
+      for (int kb = nblk - 1; kb >= 0; --kb) launch_bwd_step<T>(L, lda, Dinv, kb, rwork, s);
+      CK(cudaMemcpyAsync(alpha, rwork, (size_t)n_pad * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  launch_finalize_logpdf<T>(dscal, nblk, dscal + nblk, S, N, lp_d, dscal + nblk + TILE, s);
+  CK(cudaEventRecord(ctx->ev[4], s));
+
+  // ---- D2H
+  int h_info = 0;
+  double h_logdet = 0.0;
+  CK(cudaMemcpyAsync(&h_info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h_logdet, dscal + nblk + TILE, sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (S > 0 && logpdf_out) CK(cudaMemcpyAsync(logpdf_out, lp_d, (size_t)S * sizeof(T), cudaMemcpyDeviceToHost, s));
+  if (S > 0 && alpha_out) { rc = download<T>(ctx, alpha_out, alpha, (size_t)N, false); if (rc) return rc; }
+  CK(cudaEventRecord(ctx->ev[5], s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+
+  float ms = 0;
+  auto el = [&](int a, int b) { cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]); return (double)ms; };
+  ctx->timings[0] = el(0, 5); ctx->timings[1] = el(0, 1); ctx->timings[2] = el(1, 2); ctx->timings[3] = el(2, 3);
+  ctx->timings[4] = el(3, 4); ctx->timings[5] = el(4, 5); ctx->timings[6] = 0.0;
+  ctx->timings[7] = ctx->profile ? prof_total_ms(ctx) : 0.0;
+
+  if (h_info != 0) {
+    ctx->info = h_info;
+    char b[128];
+    snprintf(b, sizeof(b), "matrix is not positive definite; Cholesky failed at pivot %d", h_info);
+    ctx->err = b;
+    if (post) { agp_post_free(post); }
+    return AGP_ERR_NOT_POSDEF;
+  }
+  if (post) { post->logdet = h_logdet; *post_out = post; }
+  if (L_keep) { *L_keep = L; *lda_out = lda; }
+  return AGP_OK;
+}
+
+template <typename T>
+int post_cross(agp_post* p, Scratch& sc, int layout, const void* Xs, int64_t M, int64_t m_pad, T** Xst, T** B) {
+  agp_ctx* ctx = p->ctx;
+  int rc = prep_points<T>(ctx, sc, &p->k, (const T*)p->ard, layout, Xs, M, m_pad, p->D, Xst, false);
+  if (rc) return rc;
+  void* b = nullptr;
+  CK(sc.alloc(&b, (size_t)p->n_pad * m_pad * sizeof(T)));
+  *B = (T*)b;
+  GramParams gp{};
+  fill_gram_params<T>(gp, &p->k, 0, 0, p->n, M, nullptr, nullptr);
+  launch_gram<T>((const T*)p->Xt, *Xst, p->n_pad, m_pad, p->D, *B, p->n_pad, gp, ctx->stream);
+  return AGP_OK;
+}
+
+template <typename T>
+int post_mean_var_impl(agp_post* p, int layout, const void* Xs, int64_t M, const agp_mean* mean_s,
+                       const agp_noise* noise_s, void* mean_out, void* var_out) {
+  agp_ctx* ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  CK(cudaSetDevice(ctx->device));
+  if (M <= 0) return AGP_OK;
+  CK(cudaEventRecord(ctx->ev[0], s));
+  // chunk the test points so that the N x Mc cross-Gram stays <= ~4 GB
+  int64_t cap = (int64_t)(4.0e9 / ((double)p->n_pad * sizeof(T)));
+  cap = cap / TILE * TILE;
+  if (cap < TILE) cap = TILE;
+  agp_mean mz{p->mean_kind, p->mean_c, nullptr};
+  if (!mean_s) mean_s = &mz;
+  for (int64_t c0 = 0; c0 < M; c0 += cap) {
+    const int64_t mc = (M - c0 < cap) ? (M - c0) : cap;
+    const int64_t m_pad = round_up(mc, TILE);
+    Scratch sc(ctx);
+    const char* xs_c = (const char*)Xs;
+    const void* xs_chunk = nullptr;
+    std::vector<char> stage;
+    if (layout == AGP_POINT_MAJOR) {
+      xs_chunk = xs_c + (size_t)c0 * p->D * sizeof(T);
+    } else {
+      if (c0 == 0 && mc == M) xs_chunk = Xs;
+      else { ctx->err = "feature-major test sets larger than one chunk are unsupported"; return AGP_ERR_UNSUPPORTED; }
+    }
+    T *Xst = nullptr, *B = nullptr;
+    int rc = post_cross<T>(p, sc, layout, xs_chunk, mc, m_pad, &Xst, &B);
+    if (rc) return rc;
+    T *mean_d = nullptr, *noise_d = nullptr;
+    if (mean_s->kind == 2) { rc = upload<T>(ctx, sc, (const T*)mean_s->v + c0, mc, true, &mean_d); if (rc) return rc; }
+    if (noise_s && noise_s->kind == 1) { rc = upload<T>(ctx, sc, (const T*)noise_s->v + c0, mc, true, &noise_d); if (rc) return rc; }
+    void* tmp = nullptr;
+    CK(sc.alloc(&tmp, (size_t)m_pad * 3 * sizeof(T)));
+    T* mu = (T*)tmp; T* var = mu + m_pad; T* kd = var + m_pad;
+    launch_kdiag<T>(Xst, mc, p->D, p->k.family, p->k.variance, p->k.linear_c, kd, s);
+    launch_gemv_t<T>(B, p->n_pad, p->n_pad, mc, (const T*)p->alpha, mean_s->kind, mean_s->c, mean_d, mu, s);
+    if (var_out) {
+      forward_subst_multi<T>(ctx, (const T*)p->L, p->lda, (const T*)p->Dinv, p->n_pad, B, p->n_pad, m_pad);
+      launch_colsumsq_var<T>(B, p->n_pad, p->n_pad, mc, kd, noise_s ? noise_s->kind : -1, noise_s ? noise_s->s : 0.0,
+                             noise_d, var, s);
+    }
+    if (mean_out) { rc = download<T>(ctx, (T*)mean_out + c0, mu, mc, false); if (rc) return rc; }
+    if (var_out) { rc = download<T>(ctx, (T*)var_out + c0, var, mc, false); if (rc) return rc; }
+    CK(cudaStreamSynchronize(s));
+  }
+  CK(cudaEventRecord(ctx->ev[1], s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+  ctx->timings[6] = ms;
+  ctx->timings[0] = ms;
+  return AGP_OK;
+}
+
+template <typename T>
+int post_mean_cov_impl(agp_post* p, int layout, const void* Xs, int64_t M, const agp_mean* mean_s, void* mean_out,
+                       void* cov_out) {
+  agp_ctx* ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  CK(cudaSetDevice(ctx->device));
+  if (M <= 0) return AGP_OK;
+  const int64_t m_pad = round_up(M, TILE);
+  Scratch sc(ctx);
+  T *Xst = nullptr, *B = nullptr;
+  int rc = post_cross<T>(p, sc, layout, Xs, M, m_pad, &Xst, &B);
+  if (rc) return rc;
+  agp_mean mz{p->mean_kind, p->mean_c, nullptr};
+  if (!mean_s) mean_s = &mz;
+  T* mean_d = nullptr;
+  if (mean_s->kind == 2) { rc = upload<T>(ctx, sc, mean_s->v, M, true, &mean_d); if (rc) return rc; }
+  void* tmp = nullptr;
+  CK(sc.alloc(&tmp, (size_t)m_pad * sizeof(T)));
+  T* mu = (T*)tmp;
+  launch_gemv_t<T>(B, p->n_pad, p->n_pad, M, (const T*)p->alpha, mean_s->kind, mean_s->c, mean_d, mu, s);
+  if (mean_out) { rc = download<T>(ctx, mean_out, mu, M, false); if (rc) return rc; }
+  if (cov_out) {
+    forward_subst_multi<T>(ctx, (const T*)p->L, p->lda, (const T*)p->Dinv, p->n_pad, B, p->n_pad, m_pad);
+    CK(sc.alloc(&tmp, (size_t)m_pad * m_pad * sizeof(T) * 2));
+    T* C = (T*)tmp; T* Kss = C + m_pad * m_pad;
+    GemmArgs g{};  // C = V' V
+    g.A = B; g.lda = p->n_pad; g.a_kmajor = 1;
+    g.B = B; g.ldb = p->n_pad; g.b_kmajor = 1;
+    g.C = C; g.ldc = m_pad; g.M = m_pad; g.N = m_pad; g.K = p->n_pad;
+    launch_gemm<T>(g, s);
+    GramParams gp{};
+    fill_gram_params<T>(gp, &p->k, 1, 0, M, M, nullptr, nullptr);
+    launch_gram<T>(Xst, Xst, m_pad, m_pad, p->D, Kss, m_pad, gp, s);
+    launch_cov_finish<T>(C, m_pad, Kss, m_pad, s);
+    cudaMemcpyKind kind = ctx->memspace == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    CK(cudaMemcpy2DAsync(cov_out, (size_t)M * sizeof(T), C, (size_t)m_pad * sizeof(T), (size_t)M * sizeof(T), (size_t)M, kind, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  return AGP_OK;
+}
+
+template <typename T>
+int post_solve_lower_impl(agp_post* p, const void* Bh, int64_t nrhs, void* V_out) {
+  agp_ctx* ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  CK(cudaSetDevice(ctx->device));
+  if (nrhs <= 0) return AGP_OK;
+  const int64_t c_pad = round_up(nrhs, 4);
+  Scratch sc(ctx);
+  void* tmp = nullptr;
+  CK(sc.alloc(&tmp, (size_t)p->n_pad * c_pad * sizeof(T)));
+  T* B = (T*)tmp;
+  CK(cudaMemsetAsync(B, 0, (size_t)p->n_pad * c_pad * sizeof(T), s));
+  cudaMemcpyKind kin = ctx->memspace == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  CK(cudaMemcpy2DAsync(B, (size_t)p->n_pad * sizeof(T), Bh, (size_t)p->n * sizeof(T), (size_t)p->n * sizeof(T), (size_t)nrhs, kin, s));
+  forward_subst_multi<T>(ctx, (const T*)p->L, p->lda, (const T*)p->Dinv, p->n_pad, B, p->n_pad, c_pad);
+  cudaMemcpyKind kout = ctx->memspace == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  CK(cudaMemcpy2DAsync(V_out, (size_t)p->n * sizeof(T), B, (size_t)p->n_pad * sizeof(T), (size_t)p->n * sizeof(T), (size_t)nrhs, kout, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  return AGP_OK;
+}
+
+template <typename T>
+int post_export_impl(agp_post* p, void* U_out) {
+  agp_ctx* ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->memspace == AGP_MEM_DEVICE) {
+    launch_export_upper<T>((const T*)p->L, p->lda, p->n, (T*)U_out, p->n, s);
+  } else {
+    Scratch sc(ctx);
+    void* tmp = nullptr;
+    CK(sc.alloc(&tmp, (size_t)p->n * p->n * sizeof(T)));
+    launch_export_upper<T>((const T*)p->L, p->lda, p->n, (T*)tmp, p->n, s);
+    CK(cudaMemcpyAsync(U_out, tmp, (size_t)p->n * p->n * sizeof(T), cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  return AGP_OK;
+}
+
+template <typename T>
+int rand_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_noise* noise, int layout,
+              const void* X, int64_t N, int D, const void* Z, int S, void* out) {
+  if (S <= 0) return AGP_OK;
+  if (!Z || !out) { ctx->err = "Z/out is NULL"; return AGP_ERR_INVALID; }
+  Scratch outer(ctx);
+  T* L = nullptr;
+  int64_t lda = 0;
+  int rc = fit_impl<T>(ctx, k, mean, noise, layout, X, N, D, nullptr, 0, nullptr, nullptr, nullptr, &L, &lda, &outer);
+  if (rc) return rc;
+  cudaStream_t s = ctx->stream;
+  const int64_t n_pad = round_up(N, TILE), s_pad = round_up(S, 4);
+  void* tmp = nullptr;
+  CK(outer.alloc(&tmp, (size_t)n_pad * s_pad * sizeof(T) * 2));
+  T* Zd = (T*)tmp; T* Od = Zd + n_pad * s_pad;
+  CK(cudaMemsetAsync(Zd, 0, (size_t)n_pad * s_pad * sizeof(T), s));
+  cudaMemcpyKind kin = ctx->memspace == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  CK(cudaMemcpy2DAsync(Zd, (size_t)n_pad * sizeof(T), Z, (size_t)N * sizeof(T), (size_t)N * sizeof(T), (size_t)S, kin, s));
+  GemmArgs g{};  // out = L * Z (TRMM, lower)
+  g.A = L; g.lda = lda; g.a_kmajor = 0;
+  g.B = Zd; g.ldb = n_pad; g.b_kmajor = 1;
+  g.C = Od; g.ldc = n_pad; g.M = n_pad; g.N = s_pad; g.K = n_pad; g.trmm_lower = 1;
+  launch_gemm<T>(g, s);
+  static const agp_mean zero_mean{0, 0.0, nullptr};
+  if (!mean) mean = &zero_mean;
+  T* mean_d = nullptr;
+  if (mean->kind == 2) { rc = upload<T>(ctx, outer, mean->v, N, true, &mean_d); if (rc) return rc; }
+  launch_add_mean_cols<T>(Od, n_pad, N, S, mean->kind, mean->c, mean_d, s);
+  cudaMemcpyKind kout = ctx->memspace == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  CK(cudaMemcpy2DAsync(out, (size_t)N * sizeof(T), Od, (size_t)n_pad * sizeof(T), (size_t)N * sizeof(T), (size_t)S, kout, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  return AGP_OK;
+}
+
+template <typename T>
+int gram_impl(agp_ctx* ctx, const agp_kernel* k, int layout, const void* X, int64_t N, int D, const void* Z,
+              int64_t M, const agp_noise* noise, void* K_out) {
+  int rc = check_kernel(ctx, k, D);
+  if (rc) return rc;
+  if (N <= 0 || (Z && M <= 0)) { ctx->err = "empty input"; return AGP_ERR_DIM_MISMATCH; }
+  cudaStream_t s = ctx->stream;
+  CK(cudaSetDevice(ctx->device));
+  Scratch sc(ctx);
+  const int64_t n_pad = round_up(N, 64);
+  const int64_t cols = Z ? M : N, c_pad = round_up(cols, 64);
+  T *ard_d = nullptr, *noise_d = nullptr, *Xt = nullptr, *Zt = nullptr;
+  if (k->transform == AGP_T_ARD) { rc = upload<T>(ctx, sc, k->ard, D, true, &ard_d); if (rc) return rc; }
+  if (noise && noise->kind == 1) { rc = upload<T>(ctx, sc, noise->v, N, true, &noise_d); if (rc) return rc; }
+  rc = prep_points<T>(ctx, sc, k, ard_d, layout, X, N, n_pad, D, &Xt, false);
+  if (rc) return rc;
+  if (Z) { rc = prep_points<T>(ctx, sc, k, ard_d, layout, Z, M, c_pad, D, &Zt, false); if (rc) return rc; }
+  void* tmp = nullptr;
+  CK(sc.alloc(&tmp, (size_t)n_pad * c_pad * sizeof(T)));
+  GramParams gp{};
+  fill_gram_params<T>(gp, k, Z ? 0 : 1, 0, N, cols, Z ? nullptr : noise, noise_d);
+  launch_gram<T>(Xt, Z ? Zt : Xt, n_pad, c_pad, D, (T*)tmp, n_pad, gp, s);
+  cudaMemcpyKind kout = ctx->memspace == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  CK(cudaMemcpy2DAsync(K_out, (size_t)N * sizeof(T), tmp, (size_t)n_pad * sizeof(T), (size_t)N * sizeof(T), (size_t)cols, kout, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  return AGP_OK;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// extern "C" ABI
+// ------------------------------------------------------------------------------------------------
+#define DISPATCH(dtype, call_f32, call_f64)                                   \
+  ((dtype) == AGP_F32 ? (call_f32) : ((dtype) == AGP_F64 ? (call_f64) : (int)AGP_ERR_UNSUPPORTED))
+
+extern "C" {
+
+const char* agp_version(void) { return "agp-blackwell 0.1 (sm_100a)"; }
+
+int32_t agp_init(agp_ctx** out, int32_t device, const agp_config* cfg) {
+  if (!out) return AGP_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return AGP_ERR_CUDA;  // no CPU fallback, by design
+  if (device < 0 || device >= ndev) return AGP_ERR_INVALID;
+  agp_ctx* ctx = new agp_ctx();
+  ctx->device = device;
+  if (cfg) ctx->cfg = *cfg;
+  ctx->cfg.tile_nb = TILE;
+  ctx->cfg.fp64_mode = env_int("AGP_FP64_MODE", ctx->cfg.fp64_mode);
+  ctx->cfg.fp32_mode = env_int("AGP_FP32_MODE", ctx->cfg.fp32_mode);
+  ctx->cfg.lookahead = env_int("AGP_LOOKAHEAD", ctx->cfg.lookahead);
+  ctx->cfg.use_graph = env_int("AGP_GRAPH", ctx->cfg.use_graph);
+  ctx->profile = env_int("AGP_PROFILE", 1);
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
+  for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;  // keep freed blocks: repeated fits of the same size never hit the OS
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = ctx;
+  return AGP_OK;
+}
+
+int32_t agp_destroy(agp_ctx* ctx) {
+  if (!ctx) return AGP_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
+  for (auto e : ctx->prof_ev) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return AGP_OK;
+}
+
+const char* agp_last_error(const agp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+int64_t agp_last_info(const agp_ctx* ctx) { return ctx ? ctx->info : 0; }
+int32_t agp_set_memspace(agp_ctx* ctx, int32_t m) {
+  if (!ctx || (m != AGP_MEM_HOST && m != AGP_MEM_DEVICE)) return AGP_ERR_INVALID;
+  ctx->memspace = m;
+  return AGP_OK;
+}
+int32_t agp_last_timings(const agp_ctx* ctx, double* out, int32_t n) {
+  if (!ctx || !out) return 0;
+  int c = n < 8 ? n : 8;
+  for (int i = 0; i < c; ++i) out[i] = ctx->timings[i];
+  return c;
+}
+int64_t agp_launch_count(const agp_ctx*) { return agp_kernel_launches(); }
+
+int32_t agp_gram(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, int32_t layout, const void* X, int64_t N,
+                 int32_t D, const void* Z, int64_t M, const agp_noise* noise, void* K_out) {
+  if (!ctx) return AGP_ERR_INVALID;
+  return DISPATCH(dtype, gram_impl<float>(ctx, k, layout, X, N, D, Z, M, noise, K_out),
+                  gram_impl<double>(ctx, k, layout, X, N, D, Z, M, noise, K_out));
+}
+
+int32_t agp_fit(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, const agp_mean* mean, const agp_noise* noise,
+                int32_t layout, const void* X, int64_t N, int32_t D, const void* Y, int32_t S, void* logpdf_out,
+                void* alpha_out, agp_post** post_out) {
+  if (!ctx) return AGP_ERR_INVALID;
+  if (post_out) *post_out = nullptr;
+  return DISPATCH(dtype,
+                  fit_impl<float>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out, post_out, nullptr, nullptr, nullptr),
+                  fit_impl<double>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out, post_out, nullptr, nullptr, nullptr));
+}
+
+int32_t agp_post_mean_var(agp_post* p, int32_t layout, const void* Xs, int64_t M, const agp_mean* mean_s,
+                          const agp_noise* noise_s, void* mean_out, void* var_out) {
+  if (!p) return AGP_ERR_INVALID;
+  return DISPATCH(p->dtype, post_mean_var_impl<float>(p, layout, Xs, M, mean_s, noise_s, mean_out, var_out),
+                  post_mean_var_impl<double>(p, layout, Xs, M, mean_s, noise_s, mean_out, var_out));
+}
+
+int32_t agp_post_mean_cov(agp_post* p, int32_t layout, const void* Xs, int64_t M, const agp_mean* mean_s,
+                          void* mean_out, void* cov_out) {
+  if (!p) return AGP_ERR_INVALID;
+  return DISPATCH(p->dtype, post_mean_cov_impl<float>(p, layout, Xs, M, mean_s, mean_out, cov_out),
+                  post_mean_cov_impl<double>(p, layout, Xs, M, mean_s, mean_out, cov_out));
+}
+
+int32_t agp_post_solve_lower(agp_post* p, const void* B, int64_t nrhs, void* V_out) {
+  if (!p || !B || !V_out) return AGP_ERR_INVALID;
+  return DISPATCH(p->dtype, post_solve_lower_impl<float>(p, B, nrhs, V_out), post_solve_lower_impl<double>(p, B, nrhs, V_out));
+}
+
+int32_t agp_post_factor_export(agp_post* p, void* U_out) {
+  if (!p || !U_out) return AGP_ERR_INVALID;
+  return DISPATCH(p->dtype, post_export_impl<float>(p, U_out), post_export_impl<double>(p, U_out));
+}
+
+int32_t agp_post_logdet(agp_post* p, double* out) {
+  if (!p || !out) return AGP_ERR_INVALID;
+  *out = p->logdet;
+  return AGP_OK;
+}
+int64_t agp_post_n(const agp_post* p) { return p ? p->n : 0; }
+
+int32_t agp_post_free(agp_post* p) {
+  if (!p) return AGP_OK;
+  cudaSetDevice(p->ctx->device);
+  cudaStream_t s = p->ctx->stream;
+  if (p->L) cudaFreeAsync(p->L, s);
+  if (p->Dinv) cudaFreeAsync(p->Dinv, s);
+  if (p->Xt) cudaFreeAsync(p->Xt, s);
+  if (p->alpha) cudaFreeAsync(p->alpha, s);
+  if (p->ard) cudaFreeAsync(p->ard, s);
+  delete p;
+  return AGP_OK;
+}
+
+int32_t agp_rand(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, const agp_mean* mean, const agp_noise* noise,
+                 int32_t layout, const void* X, int64_t N, int32_t D, const void* Z, int32_t S, void* out) {
+  if (!ctx) return AGP_ERR_INVALID;
+  return DISPATCH(dtype, rand_impl<float>(ctx, k, mean, noise, layout, X, N, D, Z, S, out),
+                  rand_impl<double>(ctx, k, mean, noise, layout, X, N, D, Z, S, out));
+}
+
+int32_t agp_bc_owner(int32_t ti, int32_t tj, int32_t P, int32_t Q) { return (ti % P) * Q + (tj % Q); }
+int64_t agp_bc_local_tiles(int32_t nt, int32_t rank, int32_t P, int32_t Q) {
+  int64_t c = 0;
+  for (int i = 0; i < nt; ++i)
+    for (int j = 0; j <= i; ++j)
+      if (agp_bc_owner(i, j, P, Q) == rank) ++c;
+  return c;
+}
+
+// ---- not yet implemented in this build (tracked in DESIGN.md "status") ---------------------------
+int32_t agp_nccl_unique_id(void*) { return AGP_ERR_UNSUPPORTED; }
+int32_t agp_init_dist(agp_ctx** ctx, int32_t, int32_t, int32_t, int32_t, int32_t, const void*, const agp_config*) {
+  if (ctx) *ctx = nullptr;
+  return AGP_ERR_UNSUPPORTED;
+}
+int32_t agp_post_extend(agp_post* p, int32_t, const void*, int64_t, const void*, const agp_mean*, const agp_noise*, void*) {
+  if (p) p->ctx->err = "agp_post_extend: not implemented yet";
+  return AGP_ERR_UNSUPPORTED;
+}
+int32_t agp_vfe_elbo(agp_ctx* ctx, int32_t, const agp_kernel*, const agp_mean*, const agp_noise*, int32_t, const void*,
+                     int64_t, int32_t, const void*, int64_t, const agp_noise*, const void*, void*, void*) {
+  if (ctx) ctx->err = "agp_vfe_elbo: not implemented yet";
+  return AGP_ERR_UNSUPPORTED;
+}
+int32_t agp_vfe_fit(agp_ctx* ctx, int32_t, const agp_kernel*, const agp_mean*, const agp_noise*, int32_t, const void*,
+                    int64_t, int32_t, const void*, int64_t, const agp_noise*, const void*, agp_vfe_post** out) {
+  if (out) *out = nullptr;
+  if (ctx) ctx->err = "agp_vfe_fit: not implemented yet";
+  return AGP_ERR_UNSUPPORTED;
+}
+int32_t agp_vfe_mean_var(agp_vfe_post*, int32_t, const void*, int64_t, void*, void*) { return AGP_ERR_UNSUPPORTED; }
+int32_t agp_vfe_post_free(agp_vfe_post* p) { delete p; return AGP_OK; }
+
+}  // extern "C"

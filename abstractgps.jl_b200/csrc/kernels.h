@@ -1,0 +1,92 @@
+// kernels.h -- launch-level interface between the engine (engine.cu) and the sm_100a kernels.
+// All matrices are column-major.  TILE = 128 is the factorisation tile edge: every matrix the
+// Cholesky touches is padded to a multiple of TILE (identity padding), so kernels on that path
+// see no ragged edges; the generic GEMM still bounds-checks for the prediction path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define AGP_TILE 128
+
+struct GramParams {
+  int family;        // AGP_SE ...
+  double variance;   // sigma_f^2
+  double linear_c;
+  int symmetric;     // 1: Xb == Xa, exact-zero self distance, optional noise on the diagonal
+  int lower_only;    // 1: skip 64x64 tiles strictly above the diagonal
+  int64_t valid_a;   // rows >= valid_a are padding
+  int64_t valid_b;   // cols >= valid_b are padding
+  int noise_kind;    // -1 none, 0 scalar, 1 vector
+  double noise_s;
+  const void* noise_v;  // device, T
+};
+
+// op(A) is M x K, op(B) is K x N, C is M x N (ldc).  C = beta*C + alpha*op(A)op(B), alpha in {+1,-1}.
+struct GemmArgs {
+  const void* A; int64_t lda; int a_kmajor;  // 0: A(m,k) at A[m + k*lda]   1: A(m,k) at A[k + m*lda]
+  const void* B; int64_t ldb; int b_kmajor;  // 0: B(k,n) at B[n + k*ldb]   1: B(k,n) at B[k + n*ldb]
+  void* C; int64_t ldc;
+  int64_t M, N, K;
+  int alpha_neg;     // 1 -> alpha = -1 else +1
+  int beta_one;      // 1 -> beta = 1 else 0
+  int lower_only;    // 1 -> skip tiles with tile_n > tile_m (SYRK on a diagonal-anchored C)
+  int trmm_lower;    // 1 -> A is lower triangular M x K anchored at (0,0): limit k <= row tile end
+};
+
+template <typename T> void launch_prep_points(const T* X, int layout, int64_t n, int64_t n_pad, int D,
+                                              int transform, double scale, const T* ard, T* Xt,
+                                              cudaStream_t s);
+template <typename T> void launch_gram(const T* Xa, const T* Xb, int64_t na_pad, int64_t nb_pad, int D,
+                                       T* K, int64_t ldk, const GramParams& p, cudaStream_t s);
+template <typename T> void launch_kdiag(const T* Xt, int64_t n, int D, int family, double variance,
+                                        double linear_c, T* out, cudaStream_t s);
+// border rows: E[s, j] = Y[j + s*ldy] - mean_j  (j < n, s < S), 0 elsewhere; E is TILE x n_pad at
+// rows [n_pad, n_pad+TILE) of the factor matrix (leading dimension lda).
+template <typename T> void launch_border_init(T* A, int64_t lda, int64_t n, int64_t n_pad, const T* Y,
+                                              int64_t ldy, int S, int mean_kind, double mean_c,
+                                              const T* mean_v, cudaStream_t s);
+// diagonal block factorisation + inverse: A (TILE x TILE at Ablk, lda) -> L in place (upper zeroed),
+// Dinv = inv(L) (TILE x TILE col-major, lower), logdet_part[blk] = sum log L_jj, info (first bad pivot, 1-based).
+template <typename T> void launch_potrf_diag(T* Ablk, int64_t lda, T* Dinv, double* logdet_part, int blk,
+                                             int* info, cudaStream_t s);
+template <typename T> void launch_gemm(const GemmArgs& g, cudaStream_t s);
+// v extraction from the border rows + sqmahal: r[s*n_pad + j] = E[s, j], sq[s] = sum_j E[s,j]^2
+template <typename T> void launch_extract_v(const T* A, int64_t lda, int64_t n_pad, int S, T* r, double* sq,
+                                            cudaStream_t s);
+// one step of the blocked backward substitution L' alpha = r (in place in r), block k
+template <typename T> void launch_bwd_step(const T* A, int64_t lda, const T* Dinv, int k, T* r,
+                                           cudaStream_t s);
+// one step of the blocked forward substitution L v = r (in place), block k (used by extend / vfe)
+template <typename T> void launch_fwd_step(const T* A, int64_t lda, const T* Dinv, int k, int nblk, T* r,
+                                           cudaStream_t s);
+template <typename T> void launch_finalize_logpdf(const double* logdet_part, int nblk, const double* sq, int S,
+                                                  int64_t n, T* out, double* logdet_out, cudaStream_t s);
+// mu[j] = mean_j + sum_i B[i + j*ldb] * alpha[i]
+template <typename T> void launch_gemv_t(const T* B, int64_t ldb, int64_t n, int64_t m, const T* alpha,
+                                         int mean_kind, double mean_c, const T* mean_v, T* mu, cudaStream_t s);
+// var[j] = kdiag[j] - sum_i V[i + j*ldv]^2 (+ noise)
+template <typename T> void launch_colsumsq_var(const T* V, int64_t ldv, int64_t n, int64_t m, const T* kdiag,
+                                               int noise_kind, double noise_s, const T* noise_v, T* var,
+                                               cudaStream_t s);
+// out[i + j*ldo] = (i<=j) ? L[j + i*lda] : 0     (U = L')
+template <typename T> void launch_export_upper(const T* A, int64_t lda, int64_t n, T* U, int64_t ldo,
+                                               cudaStream_t s);
+template <typename T> void launch_add_mean_cols(T* out, int64_t ldo, int64_t n, int S, int mean_kind,
+                                                double mean_c, const T* mean_v, cudaStream_t s);
+// C[i + j*ldc] = Kss[i + j*ldc] - C[...]  and symmetrise (mean_and_cov epilogue)
+template <typename T> void launch_cov_finish(T* C, int64_t ldc, const T* Kss, int64_t m, cudaStream_t s);
+template <typename T> void launch_fill(T* p, int64_t n, double v, cudaStream_t s);
+template <typename T> void launch_copy2d(const T* src, int64_t lds, T* dst, int64_t ldd, int64_t rows,
+                                         int64_t cols, cudaStream_t s);
+// generic small helpers for VFE
+template <typename T> void launch_scale_cols(T* B, int64_t ldb, int64_t rows, int64_t cols, const T* colscale,
+                                             cudaStream_t s);  // B[:,j] *= colscale[j]
+template <typename T> void launch_add_diag(T* A, int64_t lda, int64_t n, double v, cudaStream_t s);
+template <typename T> void launch_sumsq(const T* p, int64_t n, double* out, cudaStream_t s);  // out += sum p^2
+template <typename T> void launch_vfe_prep(const T* y, int64_t n, int mean_kind, double mean_c, const T* mean_v,
+                                           int noise_kind, double noise_s, const T* noise_v, const T* kdiag,
+                                           T* delta, T* inv_sqrt_noise, double* scal /*[0]=logdet_sy [1]=sum d^2 [2]=tr*/,
+                                           cudaStream_t s);
+
+int64_t agp_kernel_launches();
+void agp_count_launch();  // global counter (all kernels above bump it)

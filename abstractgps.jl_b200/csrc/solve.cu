@@ -1,0 +1,421 @@
+// solve.cu -- K6/K7/K8: blocked triangular solves with one right-hand side, reductions (sqmahal,
+// logdet, column sums of squares), predictive-mean GEMV and small element-wise helpers.
+// Replaces `C \ delta` (/root/reference/src/exact_gpr_posterior.jl:33), tr_At_A / diag_At_A
+// (/root/reference/src/util/common_covmat_ops.jl:64-67), `C_xcond_x' * alpha`
+// (/root/reference/src/exact_gpr_posterior.jl:87) and the logpdf assembly
+// (/root/reference/src/finite_gp_projection.jl:309-310).  All HBM-bound: one coalesced pass over
+// the data, warp-shuffle reductions, fp64 accumulation of every scalar.
+#include "kernels.h"
+#include "agp.h"
+
+namespace {
+constexpr int TB = AGP_TILE;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__global__ void border_init_kernel(T* __restrict__ A, int64_t lda, int64_t n, int64_t n_pad, const T* __restrict__ Y,
+                                   int64_t ldy, int S, int mean_kind, T mean_c, const T* __restrict__ mean_v) {
+  // one thread per (s, j), s fastest: each column's TILE border entries are contiguous in memory.
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n_pad * TB) return;
+  const int s = (int)(idx & (TB - 1));
+  const int64_t j = idx >> 7;
+  T v = 0;
+  if (s < S && j < n) {
+    T m = (mean_kind == 0) ? (T)0 : (mean_kind == 1 ? mean_c : mean_v[j]);
+    v = Y[j + (int64_t)s * ldy] - m;
+  }
+  A[(n_pad + s) + j * lda] = v;
+}
+
+template <typename T>
+__global__ void extract_v_kernel(const T* __restrict__ A, int64_t lda, int64_t n_pad, int S, T* __restrict__ r,
+                                 double* __restrict__ sq) {
+  // block s handles border row s
+  const int s = blockIdx.x;
+  double acc = 0.0;
+  for (int64_t j = threadIdx.x; j < n_pad; j += blockDim.x) {
+    T v = A[(n_pad + s) + j * lda];
+    r[(int64_t)s * n_pad + j] = v;
+    acc += (double)v * (double)v;
+  }
+  __shared__ double red[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    sq[s] = t;
+  }
+}
+
+// backward step k: every CTA b <= k recomputes alpha_k = Dinv_k' r_k (128x128 mat-vec out of L2);
+// CTA b == k stores it, CTA b < k applies r_b -= L[k-block rows, b-block cols]' alpha_k.
+template <typename T>
+__global__ void __launch_bounds__(256) bwd_step_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ Dinv,
+                                                       int k, T* __restrict__ r) {
+  __shared__ T rk[TB];
+  __shared__ T ak[TB];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < TB) rk[tid] = r[(int64_t)k * TB + tid];
+  __syncthreads();
+  const T* Dk = Dinv + (int64_t)k * TB * TB;
+  // alpha_k[i] = sum_j Dinv(j, i) r_k[j]  (column i of Dinv, contiguous in j)
+  for (int i = warp; i < TB; i += 8) {
+    double acc = 0.0;
+    for (int j = lane; j < TB; j += 32) acc += (double)Dk[j + i * TB] * (double)rk[j];
+    acc = warp_sum(acc);
+    if (lane == 0) ak[i] = (T)acc;
+  }
+  __syncthreads();
+  if (b == k) {
+    if (tid < TB) r[(int64_t)k * TB + tid] = ak[tid];
+    return;
+  }
+  const T* Lkb = A + (int64_t)k * TB + (int64_t)b * TB * lda;  // tile (k, b)
+  for (int c = warp; c < TB; c += 8) {
+    double acc = 0.0;
+    for (int i = lane; i < TB; i += 32) acc += (double)Lkb[i + (int64_t)c * lda] * (double)ak[i];
+    acc = warp_sum(acc);
+    if (lane == 0) r[(int64_t)b * TB + c] -= (T)acc;
+  }
+}
+
+// forward step k: v_k = Dinv_k r_k ; r_b -= L[b-block rows, k-block cols] v_k for b > k.
+// thread (row i, half h) accumulates half of the 128-term dot product; rows are consecutive across
+// threads so every global read is coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256) fwd_step_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ Dinv,
+                                                       int k, T* __restrict__ r) {
+  __shared__ T rk[TB];
+  __shared__ T vk[TB];
+  __shared__ double part[2][TB];
+  const int b = k + blockIdx.x;
+  const int tid = threadIdx.x;
+  const int i = tid & (TB - 1), h = tid >> 7;
+  if (tid < TB) rk[tid] = r[(int64_t)k * TB + tid];
+  __syncthreads();
+  const T* Dk = Dinv + (int64_t)k * TB * TB;
+  {
+    double acc = 0.0;
+    const int j0 = h * (TB / 2);
+    for (int j = j0; j < j0 + TB / 2; ++j) acc = fma((double)Dk[i + j * TB], (double)rk[j], acc);
+    part[h][i] = acc;
+  }
+  __syncthreads();
+  if (tid < TB) vk[tid] = (T)(part[0][tid] + part[1][tid]);
+  __syncthreads();
+  if (b == k) {
+    if (tid < TB) r[(int64_t)k * TB + tid] = vk[tid];
+    return;
+  }
+  const T* Lbk = A + (int64_t)b * TB + (int64_t)k * TB * lda;  // tile (b, k)
+  {
+    double acc = 0.0;
+    const int j0 = h * (TB / 2);
+    for (int j = j0; j < j0 + TB / 2; ++j) acc = fma((double)Lbk[i + (int64_t)j * lda], (double)vk[j], acc);
+    part[h][i] = acc;
+  }
+  __syncthreads();
+  if (tid < TB) r[(int64_t)b * TB + tid] -= (T)(part[0][tid] + part[1][tid]);
+}
+
+template <typename T>
+__global__ void finalize_logpdf_kernel(const double* __restrict__ logdet_part, int nblk, const double* __restrict__ sq,
+                                       int S, int64_t n, T* __restrict__ out, double* __restrict__ logdet_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double ld = 0.0;
+    for (int b = 0; b < nblk; ++b) ld += logdet_part[b];
+    ld *= 2.0;
+    if (logdet_out) *logdet_out = ld;
+    const double log2pi = 1.8378770664093454835606594728112;
+    for (int s = 0; s < S; ++s) out[s] = (T)(-0.5 * ((double)n * log2pi + ld + sq[s]));
+  }
+}
+
+template <typename T>
+__global__ void gemv_t_kernel(const T* __restrict__ B, int64_t ldb, int64_t n, int64_t m, const T* __restrict__ alpha,
+                              int mean_kind, T mean_c, const T* __restrict__ mean_v, T* __restrict__ mu) {
+  const int64_t j = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= m) return;
+  double acc = 0.0;
+  const T* col = B + j * ldb;
+  for (int64_t i = lane; i < n; i += 32) acc += (double)col[i] * (double)alpha[i];
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    T mj = (mean_kind == 0) ? (T)0 : (mean_kind == 1 ? mean_c : mean_v[j]);
+    mu[j] = mj + (T)acc;
+  }
+}
+
+template <typename T>
+__global__ void colsumsq_var_kernel(const T* __restrict__ V, int64_t ldv, int64_t n, int64_t m, const T* __restrict__ kdiag,
+                                    int noise_kind, T noise_s, const T* __restrict__ noise_v, T* __restrict__ var) {
+  const int64_t j = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= m) return;
+  double acc = 0.0;
+  const T* col = V + j * ldv;
+  for (int64_t i = lane; i < n; i += 32) { double v = (double)col[i]; acc += v * v; }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    T v = kdiag[j] - (T)acc;
+    if (noise_kind == 0) v += noise_s;
+    else if (noise_kind == 1) v += noise_v[j];
+    var[j] = v;
+  }
+}
+
+template <typename T>
+__global__ void export_upper_kernel(const T* __restrict__ A, int64_t lda, int64_t n, T* __restrict__ U, int64_t ldo) {
+  // 32x32 smem transpose: U(i,j) = L(j,i) for i <= j
+  __shared__ T tile[32][33];
+  const int64_t bi = blockIdx.x * 32, bj = blockIdx.y * 32;  // output block rows bi.., cols bj..
+  // read L(bj + y, bi + x) coalesced along rows of L (first index)
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int64_t lr = bj + threadIdx.x, lc = bi + y;  // L(lr, lc)
+    T v = 0;
+    if (lr < n && lc < n && lr >= lc) v = A[lr + lc * lda];
+    tile[y][threadIdx.x] = v;  // tile[lc-bi][lr-bj]
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += 8) {
+    int64_t ui = bi + threadIdx.x, uj = bj + y;  // U(ui, uj) = L(uj, ui) = tile[ui-bi][uj-bj]
+    if (ui < n && uj < n) U[ui + uj * ldo] = tile[threadIdx.x][y];
+  }
+}
+
+template <typename T>
+__global__ void add_mean_cols_kernel(T* __restrict__ out, int64_t ldo, int64_t n, int S, int mean_kind, T mean_c,
+                                     const T* __restrict__ mean_v) {
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * S) return;
+  int64_t s = idx / n, i = idx - s * n;
+  T m = (mean_kind == 0) ? (T)0 : (mean_kind == 1 ? mean_c : mean_v[i]);
+  out[i + s * ldo] += m;
+}
+
+template <typename T>
+__global__ void cov_finish_kernel(T* __restrict__ C, int64_t ldc, const T* __restrict__ Kss, int64_t m) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t j = blockIdx.y;
+  if (i >= m || j >= m) return;
+  C[i + j * ldc] = Kss[i + j * ldc] - C[i + j * ldc];
+}
+
+template <typename T>
+__global__ void fill_kernel(T* p, int64_t n, T v) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+template <typename T>
+__global__ void copy2d_kernel(const T* __restrict__ src, int64_t lds, T* __restrict__ dst, int64_t ldd, int64_t rows,
+                              int64_t cols) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t j = blockIdx.y;
+  if (i < rows && j < cols) dst[i + j * ldd] = src[i + j * lds];
+}
+
+template <typename T>
+__global__ void scale_cols_kernel(T* __restrict__ B, int64_t ldb, int64_t rows, int64_t cols, const T* __restrict__ cs) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t j = blockIdx.y;
+  if (i < rows && j < cols) B[i + j * ldb] *= cs[j];
+}
+
+template <typename T>
+__global__ void add_diag_kernel(T* A, int64_t lda, int64_t n, T v) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) A[i + i * lda] += v;
+}
+
+template <typename T>
+__global__ void sumsq_kernel(const T* __restrict__ p, int64_t n, double* out) {
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = (double)p[i];
+    acc += v * v;
+  }
+  acc = warp_sum(acc);
+  __shared__ double red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    atomicAdd(out, t);
+  }
+}
+
+// VFE prep (/root/reference/src/sparse_approximations.jl:296-300,307-313): delta = (y-m)/sqrt(s2),
+// inv_sqrt_noise, logdet(Sigma_y), sum delta^2, tr(Cf Sigma_y^-1)
+template <typename T>
+__global__ void vfe_prep_kernel(const T* __restrict__ y, int64_t n, int mean_kind, T mean_c, const T* __restrict__ mean_v,
+                                int noise_kind, T noise_s, const T* __restrict__ noise_v, const T* __restrict__ kdiag,
+                                T* __restrict__ delta, T* __restrict__ isn, double* __restrict__ scal) {
+  double a0 = 0, a1 = 0, a2 = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    T s2 = (noise_kind == 0) ? noise_s : noise_v[i];
+    T m = (mean_kind == 0) ? (T)0 : (mean_kind == 1 ? mean_c : mean_v[i]);
+    T is = (T)1 / (T)sqrt((double)s2);
+    T d = (y[i] - m) * is;
+    delta[i] = d;
+    isn[i] = is;
+    a0 += log((double)s2);
+    a1 += (double)d * (double)d;
+    a2 += (double)kdiag[i] / (double)s2;
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(scal + 0, a0); atomicAdd(scal + 1, a1); atomicAdd(scal + 2, a2); }
+}
+}  // namespace
+
+template <typename T>
+void launch_border_init(T* A, int64_t lda, int64_t n, int64_t n_pad, const T* Y, int64_t ldy, int S, int mean_kind,
+                        double mean_c, const T* mean_v, cudaStream_t s) {
+  border_init_kernel<T><<<(unsigned)((n_pad * TB + 255) / 256), 256, 0, s>>>(A, lda, n, n_pad, Y, ldy, S, mean_kind, (T)mean_c, mean_v);
+  agp_count_launch();
+}
+template <typename T>
+void launch_extract_v(const T* A, int64_t lda, int64_t n_pad, int S, T* r, double* sq, cudaStream_t s) {
+  if (S <= 0) return;
+  extract_v_kernel<T><<<S, 256, 0, s>>>(A, lda, n_pad, S, r, sq);
+  agp_count_launch();
+}
+template <typename T>
+void launch_bwd_step(const T* A, int64_t lda, const T* Dinv, int k, T* r, cudaStream_t s) {
+  bwd_step_kernel<T><<<k + 1, 256, 0, s>>>(A, lda, Dinv, k, r);
+  agp_count_launch();
+}
+template <typename T>
+void launch_fwd_step(const T* A, int64_t lda, const T* Dinv, int k, int nblk, T* r, cudaStream_t s) {
+  fwd_step_kernel<T><<<nblk - k, 256, 0, s>>>(A, lda, Dinv, k, r);
+  agp_count_launch();
+}
+template <typename T>
+void launch_finalize_logpdf(const double* logdet_part, int nblk, const double* sq, int S, int64_t n, T* out,
+                            double* logdet_out, cudaStream_t s) {
+  finalize_logpdf_kernel<T><<<1, 32, 0, s>>>(logdet_part, nblk, sq, S, n, out, logdet_out);
+  agp_count_launch();
+}
+template <typename T>
+void launch_gemv_t(const T* B, int64_t ldb, int64_t n, int64_t m, const T* alpha, int mean_kind, double mean_c,
+                   const T* mean_v, T* mu, cudaStream_t s) {
+  if (m <= 0) return;
+  gemv_t_kernel<T><<<(unsigned)((m + 7) / 8), 256, 0, s>>>(B, ldb, n, m, alpha, mean_kind, (T)mean_c, mean_v, mu);
+  agp_count_launch();
+}
+template <typename T>
+void launch_colsumsq_var(const T* V, int64_t ldv, int64_t n, int64_t m, const T* kdiag, int noise_kind, double noise_s,
+                         const T* noise_v, T* var, cudaStream_t s) {
+  if (m <= 0) return;
+  colsumsq_var_kernel<T><<<(unsigned)((m + 7) / 8), 256, 0, s>>>(V, ldv, n, m, kdiag, noise_kind, (T)noise_s, noise_v, var);
+  agp_count_launch();
+}
+template <typename T>
+void launch_export_upper(const T* A, int64_t lda, int64_t n, T* U, int64_t ldo, cudaStream_t s) {
+  if (n <= 0) return;
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((n + 31) / 32));
+  export_upper_kernel<T><<<grid, dim3(32, 8), 0, s>>>(A, lda, n, U, ldo);
+  agp_count_launch();
+}
+template <typename T>
+void launch_add_mean_cols(T* out, int64_t ldo, int64_t n, int S, int mean_kind, double mean_c, const T* mean_v,
+                          cudaStream_t s) {
+  if (mean_kind == 0 || n * S <= 0) return;
+  add_mean_cols_kernel<T><<<(unsigned)((n * S + 255) / 256), 256, 0, s>>>(out, ldo, n, S, mean_kind, (T)mean_c, mean_v);
+  agp_count_launch();
+}
+template <typename T>
+void launch_cov_finish(T* C, int64_t ldc, const T* Kss, int64_t m, cudaStream_t s) {
+  if (m <= 0) return;
+  dim3 grid((unsigned)((m + 255) / 256), (unsigned)m);
+  cov_finish_kernel<T><<<grid, 256, 0, s>>>(C, ldc, Kss, m);
+  agp_count_launch();
+}
+template <typename T>
+void launch_fill(T* p, int64_t n, double v, cudaStream_t s) {
+  if (n <= 0) return;
+  fill_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n, (T)v);
+  agp_count_launch();
+}
+template <typename T>
+void launch_copy2d(const T* src, int64_t lds, T* dst, int64_t ldd, int64_t rows, int64_t cols, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return;
+  dim3 grid((unsigned)((rows + 255) / 256), (unsigned)cols);
+  copy2d_kernel<T><<<grid, 256, 0, s>>>(src, lds, dst, ldd, rows, cols);
+  agp_count_launch();
+}
+template <typename T>
+void launch_scale_cols(T* B, int64_t ldb, int64_t rows, int64_t cols, const T* cs, cudaStream_t s) {
+  if (rows <= 0 || cols <= 0) return;
+  dim3 grid((unsigned)((rows + 255) / 256), (unsigned)cols);
+  scale_cols_kernel<T><<<grid, 256, 0, s>>>(B, ldb, rows, cols, cs);
+  agp_count_launch();
+}
+template <typename T>
+void launch_add_diag(T* A, int64_t lda, int64_t n, double v, cudaStream_t s) {
+  if (n <= 0) return;
+  add_diag_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(A, lda, n, (T)v);
+  agp_count_launch();
+}
+template <typename T>
+void launch_sumsq(const T* p, int64_t n, double* out, cudaStream_t s) {
+  if (n <= 0) return;
+  int blocks = (int)((n + 1023) / 1024);
+  if (blocks > 592) blocks = 592;
+  sumsq_kernel<T><<<blocks, 256, 0, s>>>(p, n, out);
+  agp_count_launch();
+}
+template <typename T>
+void launch_vfe_prep(const T* y, int64_t n, int mean_kind, double mean_c, const T* mean_v, int noise_kind, double noise_s,
+                     const T* noise_v, const T* kdiag, T* delta, T* isn, double* scal, cudaStream_t s) {
+  if (n <= 0) return;
+  int blocks = (int)((n + 1023) / 1024);
+  if (blocks > 592) blocks = 592;
+  vfe_prep_kernel<T><<<blocks, 256, 0, s>>>(y, n, mean_kind, (T)mean_c, mean_v, noise_kind, (T)noise_s, noise_v, kdiag, delta, isn, scal);
+  agp_count_launch();
+}
+
+// explicit instantiations
+template void launch_border_init<float>(float*, int64_t, int64_t, int64_t, const float*, int64_t, int, int, double, const float*, cudaStream_t);
+template void launch_extract_v<float>(const float*, int64_t, int64_t, int, float*, double*, cudaStream_t);
+template void launch_bwd_step<float>(const float*, int64_t, const float*, int, float*, cudaStream_t);
+template void launch_fwd_step<float>(const float*, int64_t, const float*, int, int, float*, cudaStream_t);
+template void launch_finalize_logpdf<float>(const double*, int, const double*, int, int64_t, float*, double*, cudaStream_t);
+template void launch_gemv_t<float>(const float*, int64_t, int64_t, int64_t, const float*, int, double, const float*, float*, cudaStream_t);
+template void launch_colsumsq_var<float>(const float*, int64_t, int64_t, int64_t, const float*, int, double, const float*, float*, cudaStream_t);
+template void launch_export_upper<float>(const float*, int64_t, int64_t, float*, int64_t, cudaStream_t);
+template void launch_add_mean_cols<float>(float*, int64_t, int64_t, int, int, double, const float*, cudaStream_t);
+template void launch_cov_finish<float>(float*, int64_t, const float*, int64_t, cudaStream_t);
+template void launch_fill<float>(float*, int64_t, double, cudaStream_t);
+template void launch_copy2d<float>(const float*, int64_t, float*, int64_t, int64_t, int64_t, cudaStream_t);
+template void launch_scale_cols<float>(float*, int64_t, int64_t, int64_t, const float*, cudaStream_t);
+template void launch_add_diag<float>(float*, int64_t, int64_t, double, cudaStream_t);
+template void launch_sumsq<float>(const float*, int64_t, double*, cudaStream_t);
+template void launch_vfe_prep<float>(const float*, int64_t, int, double, const float*, int, double, const float*, const float*, float*, float*, double*, cudaStream_t);
+template void launch_border_init<double>(double*, int64_t, int64_t, int64_t, const double*, int64_t, int, int, double, const double*, cudaStream_t);
+template void launch_extract_v<double>(const double*, int64_t, int64_t, int, double*, double*, cudaStream_t);
+template void launch_bwd_step<double>(const double*, int64_t, const double*, int, double*, cudaStream_t);
+template void launch_fwd_step<double>(const double*, int64_t, const double*, int, int, double*, cudaStream_t);
+template void launch_finalize_logpdf<double>(const double*, int, const double*, int, int64_t, double*, double*, cudaStream_t);
+template void launch_gemv_t<double>(const double*, int64_t, int64_t, int64_t, const double*, int, double, const double*, double*, cudaStream_t);
+template void launch_colsumsq_var<double>(const double*, int64_t, int64_t, int64_t, const double*, int, double, const double*, double*, cudaStream_t);
+template void launch_export_upper<double>(const double*, int64_t, int64_t, double*, int64_t, cudaStream_t);
+template void launch_add_mean_cols<double>(double*, int64_t, int64_t, int, int, double, const double*, cudaStream_t);
+template void launch_cov_finish<double>(double*, int64_t, const double*, int64_t, cudaStream_t);
+template void launch_fill<double>(double*, int64_t, double, cudaStream_t);
+template void launch_copy2d<double>(const double*, int64_t, double*, int64_t, int64_t, int64_t, cudaStream_t);
+template void launch_scale_cols<double>(double*, int64_t, int64_t, int64_t, const double*, cudaStream_t);
+template void launch_add_diag<double>(double*, int64_t, int64_t, double, cudaStream_t);
+template void launch_sumsq<double>(const double*, int64_t, double*, cudaStream_t);
+template void launch_vfe_prep<double>(const double*, int64_t, int, double, const double*, int, double, const double*, const double*, double*, double*, double*, cudaStream_t);

@@ -1,0 +1,177 @@
+/* agp.h -- C ABI of libagp.so, the Blackwell-native (sm_100a) exact-GP engine that sits
+ * behind AbstractGPs.jl's dense hot path.
+ *
+ * The reference (pure Julia, /root/reference) has no FFI; the two seams a drop-in uses are
+ * Julia multiple dispatch on FiniteGP / PosteriorGP.  Each entry point
+ * below names the reference method(s) it replaces (path:line relative to /root/reference).
+ * The Julia shim that `ccall`s these symbols is julia/AGPBlackwell.jl; the identical symbols
+ * are driven from Python ctypes in abstractgps.jl_b200/_cabi.py (the only host toolchain in
+ * this image).  See INTEGRATION.md.
+ *
+ * Conventions
+ *   - all functions return int32_t status (AGP_OK == 0); no exception crosses the ABI.
+ *   - every data pointer is HOST memory owned by the caller unless the ctx was switched
+ *     with agp_set_memspace(ctx, AGP_MEM_DEVICE) (then X / Y / Xs / Z-normals / outputs that
+ *     are arrays are DEVICE pointers on the ctx's GPU; scalars-out stay host).
+ *   - element type is `dtype` (AGP_F32 / AGP_F64) for every array argument.
+ *   - points: AGP_POINT_MAJOR   = ColVecs(X),  X is D x N column-major (a point is contiguous)
+ *             AGP_FEATURE_MAJOR = RowVecs(X),  X is N x D column-major
+ *   - matrices out are column-major (Julia layout).
+ *   - calls are blocking (stream-synchronised before return) and a ctx is not re-entrant.
+ */
+#ifndef AGP_H
+#define AGP_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct agp_ctx agp_ctx;           /* device, streams, workspace arena, (NCCL comm)      */
+typedef struct agp_post agp_post;         /* device-resident factor L (=U'), alpha, x, kernel     */
+typedef struct agp_vfe_post agp_vfe_post; /* device-resident VFE cache (m_e, Lambda, U, alpha, z) */
+
+enum { AGP_F32 = 0, AGP_F64 = 1 };
+enum { AGP_SE = 0, AGP_MATERN12 = 1, AGP_MATERN32 = 2, AGP_MATERN52 = 3, AGP_LINEAR = 4 };
+enum { AGP_T_NONE = 0, AGP_T_SCALE = 1, AGP_T_ARD = 2 };
+enum { AGP_POINT_MAJOR = 0, AGP_FEATURE_MAJOR = 1 };
+enum { AGP_MEM_HOST = 0, AGP_MEM_DEVICE = 1 };
+
+enum {
+  AGP_OK = 0,
+  AGP_ERR_NOT_POSDEF = 1,   /* -> Julia PosDefException(info); info via agp_last_info()      */
+  AGP_ERR_DIM_MISMATCH = 2, /* -> DimensionMismatch (src/sparse_approximations.jl:290-294)   */
+  AGP_ERR_UNSUPPORTED = 3,
+  AGP_ERR_CUDA = 4,
+  AGP_ERR_NCCL = 5,
+  AGP_ERR_INVALID = 6
+};
+
+/* sigma_f^2 * (kappa o transform): KernelFunctions ScaledKernel / TransformedKernel with
+ * ScaleTransform(s) | ARDTransform(v); with_lengthscale(k,l) == scale 1/l.
+ * Reference call sites: src/base_gp.jl:70,72,74. */
+typedef struct {
+  int32_t family;    /* AGP_SE ... AGP_LINEAR */
+  int32_t transform; /* AGP_T_* */
+  double variance;   /* sigma_f^2 */
+  double scale;      /* ScaleTransform s */
+  double linear_c;   /* LinearKernel c */
+  const void* ard;   /* ARDTransform v: D values in `dtype`, HOST memory always */
+} agp_kernel;
+
+/* ZeroMean / ConstMean / CustomMean-evaluated-to-a-vector (src/mean_function.jl:27,40,52-55) */
+typedef struct {
+  int32_t kind; /* 0 zero, 1 const, 2 vector */
+  double c;
+  const void* v; /* `dtype`, length = number of points; HOST memory always */
+} agp_mean;
+
+/* Diagonal Sigma_y: Fill(sigma^2) or per-point vector (src/finite_gp_projection.jl:13-21) */
+typedef struct {
+  int32_t kind; /* 0 scalar, 1 per-point vector */
+  double s;
+  const void* v; /* `dtype`; HOST memory always */
+} agp_noise;
+
+typedef struct {
+  int32_t tile_nb;       /* panel width; 0 -> default (128) */
+  int32_t fp64_mode;     /* 0 = DMMA mma.sync trailing update, 1 = int8-sliced (Ozaki) on tcgen05 */
+  int32_t fp32_mode;     /* 0 = SIMT FFMA, 1 = 3xTF32 on tcgen05 */
+  int32_t lookahead;     /* 0/1: overlap next panel with the trailing update */
+  int32_t use_graph;     /* 0/1: replay the factorisation as a CUDA graph */
+  int32_t reserved[11];
+} agp_config; /* NULL -> defaults; env AGP_NB, AGP_FP64_MODE, AGP_FP32_MODE, AGP_LOOKAHEAD, AGP_GRAPH override */
+
+/* ---- context ------------------------------------------------------------------------- */
+int32_t agp_init(agp_ctx** ctx, int32_t device, const agp_config* cfg);
+/* one process per GPU, NCCL across processes (rank 0 creates the id, host code ships it) */
+int32_t agp_nccl_unique_id(void* out128);
+int32_t agp_init_dist(agp_ctx** ctx, int32_t device, int32_t rank, int32_t nranks,
+                      int32_t grid_p, int32_t grid_q, const void* nccl_unique_id128,
+                      const agp_config* cfg);
+int32_t agp_destroy(agp_ctx* ctx);
+const char* agp_last_error(const agp_ctx* ctx);
+int64_t agp_last_info(const agp_ctx* ctx); /* LAPACK-style failing pivot (1-based) after NOT_POSDEF */
+int32_t agp_set_memspace(agp_ctx* ctx, int32_t memspace);
+const char* agp_version(void);
+
+/* instrumentation for bench.py: per-phase device times (CUDA events on the launching stream)
+ * of the LAST call: out[0]=total [1]=h2d [2]=gram [3]=cholesky [4]=solves [5]=d2h [6]=predict
+ * [7]=trailing-update kernels only (sum), all in ms; returns number of doubles written. */
+int32_t agp_last_timings(const agp_ctx* ctx, double* out, int32_t n);
+int64_t agp_launch_count(const agp_ctx* ctx); /* kernels launched by this ctx so far */
+
+/* ---- Gram only: cov(f, x) / cov(f, x, z) / cov(fx)  ---------------------------------------
+ * replaces kernelmatrix(k,x[,z]) at src/base_gp.jl:70,74 and `C + Sigma_y`
+ * src/finite_gp_projection.jl:96,135.  Z == NULL -> symmetric N x N (+ noise on the diagonal
+ * when noise != NULL); else N x M cross-Gram.  K_out column-major, leading dim N. */
+int32_t agp_gram(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, int32_t layout, const void* X,
+                 int64_t N, int32_t D, const void* Z, int64_t M, const agp_noise* noise,
+                 void* K_out);
+
+/* ---- fused fit: ONE Gram + ONE Cholesky -> logpdf for S columns of Y, alpha, posterior ------
+ * replaces logpdf(::FiniteGP, Y) src/finite_gp_projection.jl:306-311 (+ _sqmahal :325-326,
+ * tr_Xt_invA_X / diag_Xt_invA_X src/util/common_covmat_ops.jl:90,101) AND
+ * posterior(fx, y) src/exact_gpr_posterior.jl:29-35 (alpha = C \ (y - m) for column 0 of Y).
+ * Y: N x S column-major.  logpdf_out: S values (`dtype`).  alpha_out: N values or NULL.
+ * post_out: NULL or receives a handle owning the device-resident factor. */
+int32_t agp_fit(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, const agp_mean* mean,
+                const agp_noise* noise, int32_t layout, const void* X, int64_t N, int32_t D,
+                const void* Y, int32_t S, void* logpdf_out, void* alpha_out, agp_post** post_out);
+
+/* mean_and_var(::PosteriorGP, x*) src/exact_gpr_posterior.jl:85-90 (+ mean :60-62, var :68-70);
+ * with noise != NULL also mean_and_var(::FiniteGP) src/finite_gp_projection.jl:154-158.
+ * mean_s == NULL -> the prior mean given at fit time (zero/const only). */
+int32_t agp_post_mean_var(agp_post* p, int32_t layout, const void* Xs, int64_t M,
+                          const agp_mean* mean_s, const agp_noise* noise_s, void* mean_out,
+                          void* var_out);
+/* mean_and_cov(::PosteriorGP, x*) src/exact_gpr_posterior.jl:78-83 (Xt_invA_X
+ * src/util/common_covmat_ops.jl:54-58).  cov_out M x M column-major. */
+int32_t agp_post_mean_cov(agp_post* p, int32_t layout, const void* Xs, int64_t M,
+                          const agp_mean* mean_s, void* mean_out, void* cov_out);
+/* V = U' \ B (N x nrhs, column-major): backs Xt_invA_X / diag_Xt_invA_X / Xt_invA_Y /
+ * tr_Xt_invA_X on a device factor, src/util/common_covmat_ops.jl:54-60,90,101. */
+int32_t agp_post_solve_lower(agp_post* p, const void* B, int64_t nrhs, void* V_out);
+/* C.U for p.data.C.U compatibility (test/exact_gpr_posterior.jl:40): N x N column-major upper */
+int32_t agp_post_factor_export(agp_post* p, void* U_out);
+int32_t agp_post_logdet(agp_post* p, double* logdet_out); /* logdet(C) = 2 sum log U_ii */
+int64_t agp_post_n(const agp_post* p);
+/* sequential conditioning: posterior(fx::FiniteGP{<:PosteriorGP}, y) src/exact_gpr_posterior.jl:46-56
+ * via update_chol src/util/common_covmat_ops.jl:38-42.  Extends the factor in place; alpha_out
+ * receives the N1+N2 re-solved weights (or NULL). */
+int32_t agp_post_extend(agp_post* p, int32_t layout, const void* X2, int64_t N2, const void* y2,
+                        const agp_mean* mean2, const agp_noise* noise2, void* alpha_out);
+int32_t agp_post_free(agp_post* p);
+
+/* rand(rng, fx, S) / _rand! src/finite_gp_projection.jl:233-237,271-277: out = m + U' Z with the
+ * caller's standard normals Z (N x S column-major) -- the RNG stream stays host-defined. */
+int32_t agp_rand(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, const agp_mean* mean,
+                 const agp_noise* noise, int32_t layout, const void* X, int64_t N, int32_t D,
+                 const void* Z, int32_t S, void* out);
+
+/* ---- VFE (Titsias) -------------------------------------------------------------------------
+ * approx_log_evidence(::VFE)/elbo src/sparse_approximations.jl:248-254 with
+ * _compute_intermediates :289-305 and tr_Cf_invSigma_y :307-313; dtc_out (optional) is the DTC
+ * objective :282-286.  Only diagonal Sigma_y (as in the reference, :307-313). */
+int32_t agp_vfe_elbo(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, const agp_mean* mean,
+                     const agp_noise* noise, int32_t layout, const void* X, int64_t N, int32_t D,
+                     const void* Zind, int64_t M, const agp_noise* jitter, const void* y,
+                     void* elbo_out, void* dtc_out);
+/* posterior(::VFE, fx, y) src/sparse_approximations.jl:58-75 */
+int32_t agp_vfe_fit(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, const agp_mean* mean,
+                    const agp_noise* noise, int32_t layout, const void* X, int64_t N, int32_t D,
+                    const void* Zind, int64_t M, const agp_noise* jitter, const void* y,
+                    agp_vfe_post** out);
+/* mean_and_var(::ApproxPosteriorGP, x*) src/sparse_approximations.jl:212-217 */
+int32_t agp_vfe_mean_var(agp_vfe_post* p, int32_t layout, const void* Xs, int64_t Ms,
+                         void* mean_out, void* var_out);
+int32_t agp_vfe_post_free(agp_vfe_post* p);
+
+/* ---- host-only helpers of the 2D block-cyclic tile map (no GPU needed; used by the CPU
+ * world_size-2 tests): owner rank of tile (i,j) on a P x Q grid and local tile counts. */
+int32_t agp_bc_owner(int32_t ti, int32_t tj, int32_t grid_p, int32_t grid_q);
+int64_t agp_bc_local_tiles(int32_t ntiles, int32_t rank, int32_t grid_p, int32_t grid_q);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGP_H */
