@@ -437,7 +437,7 @@ def _fit(fx: FiniteGP, Y, want_post: bool, want_alpha: bool):
     pts = fx.x.astype(dt)
     Y = np.asarray(Y)
     vec = Y.ndim == 1
-    Yf = np.asfortranarray(Y.reshape(pts.n, -1) if vec else Y, dtype=dt)
+    Yf = np.asfortranarray(Y.reshape(-1, 1) if vec else Y, dtype=dt)
     if Yf.shape[0] != pts.n:
         raise DimensionMismatch("length(fx) = %d but Y has %d rows" % (pts.n, Yf.shape[0]))
     S = Yf.shape[1]

@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "agp.h"
@@ -23,6 +24,8 @@
 struct agp_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // look-ahead side stream (bulk of the trailing update)
+  std::vector<cudaEvent_t> dep_ev;  // dependency events of the look-ahead schedule
   agp_config cfg{};
   std::string err;
   int64_t info = 0;
@@ -46,6 +49,9 @@ struct agp_post {
   void* Xt = nullptr;     // n_pad x D transformed points
   void* alpha = nullptr;  // n_pad
   void* ard = nullptr;    // D (device) or null
+  void* delta = nullptr;  // n_pad: y - m at the valid rows, 0 at padding
+  unsigned char* valid = nullptr;  // n_pad row-validity mask; null while the valid rows are [0, n)
+  std::vector<std::pair<int64_t, int64_t>> segs;  // (offset, length) of the valid row segments
   agp_kernel k{};
   int mean_kind = 0;
   double mean_c = 0.0;
@@ -147,11 +153,26 @@ double prof_total_ms(agp_ctx* ctx) {
 }
 
 // ---- blocked right-looking Cholesky, in place, lower; rows include the border tile -------------
+// Look-ahead (depth 1): after the panel solve of step k, the main stream updates only the NEXT panel
+// column and immediately factors / solves panel k+1, while the side stream applies panel k to the rest
+// of the trailing matrix.  Event edges: rest_k waits trsm_k; next-column update of step k+1 waits
+// rest_k (both touch column block k+2).
+static cudaEvent_t dep_event(agp_ctx* ctx, size_t i) {
+  while (ctx->dep_ev.size() <= i) {
+    cudaEvent_t e;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    ctx->dep_ev.push_back(e);
+  }
+  return ctx->dep_ev[i];
+}
+
 template <typename T>
 void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t rows_total, T* Dinv,
                       double* logdet_part, int* info) {
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = ctx->stream, s2 = ctx->stream2;
   const int nblk = (int)(n_pad / TILE);
+  const bool la = ctx->cfg.lookahead != 0 && nblk > 2;
+  bool rest_pending = false;
   for (int k = 0; k < nblk; ++k) {
     T* Akk = L + (int64_t)k * TILE + (int64_t)k * TILE * lda;
     launch_potrf_diag<T>(Akk, lda, Dinv + (int64_t)k * TILE * TILE, logdet_part, k, info, s);
@@ -170,10 +191,37 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
     u.B = A21; u.ldb = lda; u.b_kmajor = 0;
     u.C = A21 + (int64_t)TILE * lda; u.ldc = lda;
     u.M = rows_below; u.N = cols_trail; u.K = TILE; u.alpha_neg = 1; u.beta_one = 1; u.lower_only = 1;
+    if (!la) {
+      if (ctx->profile) cudaEventRecord(prof_event(ctx), s);
+      launch_gemm<T>(u, s);
+      if (ctx->profile) cudaEventRecord(prof_event(ctx), s);
+      continue;
+    }
+    cudaEvent_t e_trsm = dep_event(ctx, 2 * (size_t)k), e_rest = dep_event(ctx, 2 * (size_t)k + 1);
+    cudaEventRecord(e_trsm, s);
+    // main stream: next panel column only (needs the previous step's bulk update of that column)
+    if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, 2 * (size_t)(k - 1) + 1), 0);
+    GemmArgs a = u;
+    a.N = TILE;
     if (ctx->profile) cudaEventRecord(prof_event(ctx), s);
-    launch_gemm<T>(u, s);
+    launch_gemm<T>(a, s);
     if (ctx->profile) cudaEventRecord(prof_event(ctx), s);
+    rest_pending = false;
+    if (cols_trail > TILE) {  // side stream: everything right of the next panel column
+      GemmArgs r = u;
+      r.A = A21 + TILE;                                  // rows from block k+2 on (tiles above are skipped anyway)
+      r.B = A21 + TILE;                                  // columns from block k+2 on
+      r.C = A21 + (int64_t)TILE * lda + TILE + (int64_t)TILE * lda;
+      r.M = rows_below - TILE; r.N = cols_trail - TILE;
+      cudaStreamWaitEvent(s2, e_trsm, 0);
+      if (ctx->profile) cudaEventRecord(prof_event(ctx), s2);
+      launch_gemm<T>(r, s2);
+      if (ctx->profile) cudaEventRecord(prof_event(ctx), s2);
+      cudaEventRecord(e_rest, s2);
+      rest_pending = true;
+    }
   }
+  if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, 2 * (size_t)(nblk - 2) + 1), 0);
 }
 
 // V <- L^-1 V for a n_pad x ncols block of right-hand sides (ncols multiple of 4), in place
@@ -279,6 +327,8 @@ int fit_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
     post->L = Lv; post->Dinv = Dinvv; post->Xt = Xt; post->alpha = alphav;
     post->k = *k; post->k.ard = nullptr;
     post->mean_kind = mean->kind == 2 ? 0 : mean->kind; post->mean_c = mean->c;
+    post->segs.push_back({0, N});
+    CK(cudaMallocAsync(&post->delta, (size_t)n_pad * sizeof(T), s));
     if (ard_d) { sc.release(ard_d); post->ard = ard_d; }
   } else if (L_keep) {
     outer_sc->ptrs.push_back(Lv); sc.ptrs.push_back(Dinvv); sc.ptrs.push_back(alphav);
@@ -296,6 +346,9 @@ int fit_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
   T* rwork = nullptr;
   CK(sc.alloc(&tmp, (size_t)(S > 0 ? S : 1) * n_pad * sizeof(T)));
   rwork = (T*)tmp;
+  int* dflags = nullptr;
+  CK(sc.alloc(&tmp, (size_t)(nblk + 1) * sizeof(int)));
+  dflags = (int*)tmp;
   T* lp_d = nullptr;
   CK(sc.alloc(&tmp, (size_t)TILE * sizeof(T)));
   lp_d = (T*)tmp;
@@ -305,6 +358,10 @@ int fit_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
   fill_gram_params<T>(gp, k, 1, 1, N, N, noise, noise_d);
   launch_gram<T>(Xt, Xt, n_pad, n_pad, D, L, lda, gp, s);
   launch_border_init<T>(L, lda, N, n_pad, Yd, N, S, mean->kind, mean->c, mean_d, s);
+  if (keep) {
+    if (S > 0) launch_extract_v<T>(L, lda, n_pad, 1, (T*)post->delta, dscal + nblk, s);  // delta = border row 0
+    else CK(cudaMemsetAsync(post->delta, 0, (size_t)n_pad * sizeof(T), s));
+  }
   CK(cudaEventRecord(ctx->ev[2], s));
 
   // ---- Cholesky (forward substitution of delta rides along in the border tile)
@@ -315,7 +372,7 @@ int fit_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
   if (S > 0) {
     launch_extract_v<T>(L, lda, n_pad, S, rwork, dscal + nblk, s);
     if (alpha_out || keep) {
-      for (int kb = nblk - 1; kb >= 0; --kb) launch_bwd_step<T>(L, lda, Dinv, kb, rwork, s);
+      launch_bwd_solve<T>(L, lda, Dinv, nblk, rwork, dflags, s);
       CK(cudaMemcpyAsync(alpha, rwork, (size_t)n_pad * sizeof(T), cudaMemcpyDeviceToDevice, s));
     }
   }
@@ -362,6 +419,7 @@ int post_cross(agp_post* p, Scratch& sc, int layout, const void* Xs, int64_t M, 
   *B = (T*)b;
   GramParams gp{};
   fill_gram_params<T>(gp, &p->k, 0, 0, p->n, M, nullptr, nullptr);
+  gp.mask_a = p->valid;
   launch_gram<T>((const T*)p->Xt, *Xst, p->n_pad, m_pad, p->D, *B, p->n_pad, gp, ctx->stream);
   return AGP_OK;
 }
@@ -478,10 +536,20 @@ int post_solve_lower_impl(agp_post* p, const void* Bh, int64_t nrhs, void* V_out
   T* B = (T*)tmp;
   CK(cudaMemsetAsync(B, 0, (size_t)p->n_pad * c_pad * sizeof(T), s));
   cudaMemcpyKind kin = ctx->memspace == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  CK(cudaMemcpy2DAsync(B, (size_t)p->n_pad * sizeof(T), Bh, (size_t)p->n * sizeof(T), (size_t)p->n * sizeof(T), (size_t)nrhs, kin, s));
-  forward_subst_multi<T>(ctx, (const T*)p->L, p->lda, (const T*)p->Dinv, p->n_pad, B, p->n_pad, c_pad);
   cudaMemcpyKind kout = ctx->memspace == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  CK(cudaMemcpy2DAsync(V_out, (size_t)p->n * sizeof(T), B, (size_t)p->n_pad * sizeof(T), (size_t)p->n * sizeof(T), (size_t)nrhs, kout, s));
+  int64_t off = 0;
+  for (auto& sg : p->segs) {  // compact rows -> padded row positions
+    CK(cudaMemcpy2DAsync(B + sg.first, (size_t)p->n_pad * sizeof(T), (const T*)Bh + off, (size_t)p->n * sizeof(T),
+                         (size_t)sg.second * sizeof(T), (size_t)nrhs, kin, s));
+    off += sg.second;
+  }
+  forward_subst_multi<T>(ctx, (const T*)p->L, p->lda, (const T*)p->Dinv, p->n_pad, B, p->n_pad, c_pad);
+  off = 0;
+  for (auto& sg : p->segs) {
+    CK(cudaMemcpy2DAsync((T*)V_out + off, (size_t)p->n * sizeof(T), B + sg.first, (size_t)p->n_pad * sizeof(T),
+                         (size_t)sg.second * sizeof(T), (size_t)nrhs, kout, s));
+    off += sg.second;
+  }
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
   return AGP_OK;
@@ -492,17 +560,157 @@ int post_export_impl(agp_post* p, void* U_out) {
   agp_ctx* ctx = p->ctx;
   cudaStream_t s = ctx->stream;
   CK(cudaSetDevice(ctx->device));
-  if (ctx->memspace == AGP_MEM_DEVICE) {
-    launch_export_upper<T>((const T*)p->L, p->lda, p->n, (T*)U_out, p->n, s);
-  } else {
-    Scratch sc(ctx);
-    void* tmp = nullptr;
-    CK(sc.alloc(&tmp, (size_t)p->n * p->n * sizeof(T)));
-    launch_export_upper<T>((const T*)p->L, p->lda, p->n, (T*)tmp, p->n, s);
-    CK(cudaMemcpyAsync(U_out, tmp, (size_t)p->n * p->n * sizeof(T), cudaMemcpyDeviceToHost, s));
+  Scratch sc(ctx);
+  void* tmp = nullptr;
+  const int64_t* map_d = nullptr;
+  if (p->segs.size() > 1) {  // extended posterior: valid rows are not contiguous
+    std::vector<int64_t> map;
+    for (auto& sg : p->segs) for (int64_t i = 0; i < sg.second; ++i) map.push_back(sg.first + i);
+    CK(sc.alloc(&tmp, map.size() * sizeof(int64_t)));
+    CK(cudaMemcpyAsync(tmp, map.data(), map.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    map_d = (const int64_t*)tmp;
   }
+  T* Ud = (T*)U_out;
+  if (ctx->memspace != AGP_MEM_DEVICE) {
+    CK(sc.alloc(&tmp, (size_t)p->n * p->n * sizeof(T)));
+    Ud = (T*)tmp;
+  }
+  if (map_d) launch_export_upper_map<T>((const T*)p->L, p->lda, p->n, map_d, Ud, p->n, s);
+  else launch_export_upper<T>((const T*)p->L, p->lda, p->n, Ud, p->n, s);
+  if (ctx->memspace != AGP_MEM_DEVICE)
+    CK(cudaMemcpyAsync(U_out, Ud, (size_t)p->n * p->n * sizeof(T), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
+  return AGP_OK;
+}
+
+// ---- sequential conditioning: posterior(fx::FiniteGP{<:PosteriorGP}, y) via update_chol
+// (/root/reference/src/exact_gpr_posterior.jl:46-56, /root/reference/src/util/common_covmat_ops.jl:38-42).
+// L21 = C21 L11^-T by the same panel solves the factorisation uses (one per old column block), then
+// ONE long-K trailing update C22 -= L21 L21', then a Cholesky of the new diagonal part.  The border
+// rows carry [delta1; delta2]' through all of it, so v = L^-1 delta comes out of the same kernels.
+template <typename T>
+int post_extend_impl(agp_post* p, int layout, const void* X2, int64_t N2, const void* y2, const agp_mean* mean2,
+                     const agp_noise* noise2, void* alpha_out) {
+  agp_ctx* ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  CK(cudaSetDevice(ctx->device));
+  if (N2 <= 0) { ctx->err = "N2 must be positive"; return AGP_ERR_DIM_MISMATCH; }
+  if (!X2 || !y2) { ctx->err = "X2/y2 is NULL"; return AGP_ERR_INVALID; }
+  static const agp_mean zero_mean{0, 0.0, nullptr};
+  static const agp_noise default_noise{0, 1e-18, nullptr};
+  if (!mean2) mean2 = &zero_mean;
+  if (!noise2) noise2 = &default_noise;
+  Scratch sc(ctx);
+  const int64_t n1p = p->n_pad, n2p = round_up(N2, TILE), np = n1p + n2p, ldn = np + TILE;
+  const int nblk1 = (int)(n1p / TILE), nblk2 = (int)(n2p / TILE), nblk = nblk1 + nblk2;
+  const int D = p->D;
+  T *mean_d = nullptr, *noise_d = nullptr, *y2d = nullptr, *X2t = nullptr;
+  int rc;
+  if (mean2->kind == 2) { rc = upload<T>(ctx, sc, mean2->v, N2, true, &mean_d); if (rc) return rc; }
+  if (noise2->kind == 1) { rc = upload<T>(ctx, sc, noise2->v, N2, true, &noise_d); if (rc) return rc; }
+  rc = upload<T>(ctx, sc, y2, N2, false, &y2d); if (rc) return rc;
+  rc = prep_points<T>(ctx, sc, &p->k, (const T*)p->ard, layout, X2, N2, n2p, D, &X2t, false); if (rc) return rc;
+
+  void *Ln = nullptr, *Dn = nullptr, *Xn = nullptr, *an = nullptr, *dn = nullptr, *vn = nullptr;
+  CK(cudaMallocAsync(&Ln, (size_t)ldn * np * sizeof(T), s));
+  CK(cudaMallocAsync(&Dn, (size_t)nblk * TILE * TILE * sizeof(T), s));
+  CK(cudaMallocAsync(&Xn, (size_t)np * D * sizeof(T), s));
+  CK(cudaMallocAsync(&an, (size_t)np * sizeof(T), s));
+  CK(cudaMallocAsync(&dn, (size_t)np * sizeof(T), s));
+  CK(cudaMallocAsync(&vn, (size_t)np, s));
+  T* L = (T*)Ln; T* Dinv = (T*)Dn;
+  unsigned char* valid = (unsigned char*)vn;
+  // carry the old state over
+  launch_copy2d<T>((const T*)p->L, p->lda, L, ldn, n1p, n1p, s);
+  CK(cudaMemcpyAsync(Dinv, p->Dinv, (size_t)nblk1 * TILE * TILE * sizeof(T), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(Xn, p->Xt, (size_t)n1p * D * sizeof(T), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync((T*)Xn + n1p * D, X2t, (size_t)n2p * D * sizeof(T), cudaMemcpyDeviceToDevice, s));
+  if (p->valid) CK(cudaMemcpyAsync(valid, p->valid, (size_t)n1p, cudaMemcpyDeviceToDevice, s));
+  else { CK(cudaMemsetAsync(valid, 1, (size_t)p->n, s)); CK(cudaMemsetAsync(valid + p->n, 0, (size_t)(n1p - p->n), s)); }
+  CK(cudaMemsetAsync(valid + n1p, 1, (size_t)N2, s));
+  CK(cudaMemsetAsync(valid + n1p + N2, 0, (size_t)(n2p - N2), s));
+  CK(cudaMemcpyAsync(dn, p->delta, (size_t)n1p * sizeof(T), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemsetAsync((T*)dn + n1p, 0, (size_t)n2p * sizeof(T), s));
+  launch_sub_mean<T>(y2d, N2, mean2->kind, mean2->c, mean_d, (T*)dn + n1p, s);
+  // C21 = K(x2, x1) and C22 = K(x2, x2) + Sigma_y2 straight into the new factor buffer
+  GramParams g21{};
+  fill_gram_params<T>(g21, &p->k, 0, 0, N2, p->n, nullptr, nullptr);
+  g21.mask_b = valid;  // old rows (first n1p entries of the new mask)
+  launch_gram<T>(X2t, (const T*)Xn, n2p, n1p, D, L + n1p, ldn, g21, s);
+  GramParams g22{};
+  fill_gram_params<T>(g22, &p->k, 1, 1, N2, N2, noise2, noise_d);
+  launch_gram<T>(X2t, X2t, n2p, n2p, D, L + n1p + n1p * ldn, ldn, g22, s);
+  launch_border_init<T>(L, ldn, np, np, (const T*)dn, np, 1, 0, 0.0, (const T*)nullptr, s);
+  // panel solves of the new rows (+ border) against the old factor
+  const int64_t Mr = n2p + TILE;
+  for (int k = 0; k < nblk1; ++k) {
+    T* Rk = L + n1p + (int64_t)k * TILE * ldn;
+    GemmArgs t{};
+    t.A = Rk; t.lda = ldn; t.B = Dinv + (int64_t)k * TILE * TILE; t.ldb = TILE;
+    t.C = Rk; t.ldc = ldn; t.M = Mr; t.N = TILE; t.K = TILE;
+    launch_gemm<T>(t, s);
+    const int64_t cols_rest = n1p - (int64_t)(k + 1) * TILE;
+    if (cols_rest <= 0) continue;
+    GemmArgs u{};
+    u.A = Rk; u.lda = ldn;
+    u.B = L + (int64_t)(k + 1) * TILE + (int64_t)k * TILE * ldn; u.ldb = ldn;
+    u.C = Rk + (int64_t)TILE * ldn; u.ldc = ldn; u.M = Mr; u.N = cols_rest; u.K = TILE; u.alpha_neg = 1; u.beta_one = 1;
+    launch_gemm<T>(u, s);
+  }
+  {  // C22 -= L21 L21'  (one launch, K = n1p)
+    GemmArgs u{};
+    u.A = L + n1p; u.lda = ldn; u.B = L + n1p; u.ldb = ldn;
+    u.C = L + n1p + n1p * ldn; u.ldc = ldn; u.M = Mr; u.N = n2p; u.K = n1p; u.alpha_neg = 1; u.beta_one = 1; u.lower_only = 1;
+    launch_gemm<T>(u, s);
+  }
+  void* tmp = nullptr;
+  CK(sc.alloc(&tmp, (size_t)(nblk2 + TILE + 2) * sizeof(double)));
+  double* dscal = (double*)tmp;
+  CK(sc.alloc(&tmp, sizeof(int)));
+  int* dinfo = (int*)tmp;
+  CK(cudaMemsetAsync(dinfo, 0, sizeof(int), s));
+  CK(sc.alloc(&tmp, (size_t)(nblk + 1) * sizeof(int)));
+  int* dflags = (int*)tmp;
+  CK(sc.alloc(&tmp, (size_t)np * sizeof(T)));
+  T* rwork = (T*)tmp;
+  CK(sc.alloc(&tmp, (size_t)TILE * sizeof(T)));
+  T* lp_d = (T*)tmp;
+  prof_begin(ctx);
+  cholesky_inplace<T>(ctx, L + n1p + n1p * ldn, ldn, n2p, n2p + TILE, Dinv + (int64_t)nblk1 * TILE * TILE, dscal, dinfo);
+  launch_extract_v<T>(L, ldn, np, 1, rwork, dscal + nblk2, s);
+  launch_bwd_solve<T>(L, ldn, Dinv, nblk, rwork, dflags, s);
+  CK(cudaMemcpyAsync(an, rwork, (size_t)np * sizeof(T), cudaMemcpyDeviceToDevice, s));
+  launch_finalize_logpdf<T>(dscal, nblk2, dscal + nblk2, 1, N2, lp_d, dscal + nblk2 + TILE, s);
+  int h_info = 0;
+  double h_ld = 0.0;
+  CK(cudaMemcpyAsync(&h_info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h_ld, dscal + nblk2 + TILE, sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  if (h_info != 0) {
+    cudaFreeAsync(Ln, s); cudaFreeAsync(Dn, s); cudaFreeAsync(Xn, s); cudaFreeAsync(an, s); cudaFreeAsync(dn, s); cudaFreeAsync(vn, s);
+    ctx->info = p->n + h_info;
+    ctx->err = "extended covariance is not positive definite";
+    return AGP_ERR_NOT_POSDEF;
+  }
+  // swap the new state in
+  cudaFreeAsync(p->L, s); cudaFreeAsync(p->Dinv, s); cudaFreeAsync(p->Xt, s); cudaFreeAsync(p->alpha, s);
+  cudaFreeAsync(p->delta, s);
+  if (p->valid) cudaFreeAsync(p->valid, s);
+  p->L = Ln; p->Dinv = Dn; p->Xt = Xn; p->alpha = an; p->delta = dn; p->valid = valid;
+  p->segs.push_back({n1p, N2});
+  p->n += N2; p->n_pad = np; p->lda = ldn; p->logdet += h_ld;
+  if (alpha_out) {
+    int64_t off = 0;
+    cudaMemcpyKind kout = ctx->memspace == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    for (auto& sg : p->segs) {
+      CK(cudaMemcpyAsync((T*)alpha_out + off, (const T*)p->alpha + sg.first, (size_t)sg.second * sizeof(T), kout, s));
+      off += sg.second;
+    }
+    CK(cudaStreamSynchronize(s));
+  }
   return AGP_OK;
 }
 
@@ -570,6 +778,194 @@ int gram_impl(agp_ctx* ctx, const agp_kernel* k, int layout, const void* X, int6
   return AGP_OK;
 }
 
+// ---- VFE (Titsias) : elbo / dtc / approximate posterior --------------------------------------------
+// Follows /root/reference/src/sparse_approximations.jl:289-305 (_compute_intermediates), :248-254 (elbo),
+// :58-75 (posterior), but STREAMS the data dimension: K_zx is generated chunk by chunk, scaled by
+// Sigma_y^-1/2, solved against chol(K_zz) and folded into D = A A' (M x M), b = A delta and ||A||_F^2,
+// so the M x N matrix A (32.8 GB at config C5) never exists.
+template <typename T>
+int vfe_core(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_noise* noise, int layout,
+             const void* X, int64_t N, int D, const void* Zind, int64_t M, const agp_noise* jitter, const void* y,
+             void* elbo_out, void* dtc_out, agp_vfe_post** post_out) {
+  int rc = check_kernel(ctx, k, D);
+  if (rc) return rc;
+  if (N <= 0 || M <= 0) { ctx->err = "N and M must be positive"; return AGP_ERR_DIM_MISMATCH; }
+  if (!X || !Zind || !y) { ctx->err = "X/Z/y is NULL"; return AGP_ERR_INVALID; }
+  static const agp_mean zero_mean{0, 0.0, nullptr};
+  static const agp_noise default_noise{0, 1e-18, nullptr};
+  if (!mean) mean = &zero_mean;
+  if (!noise) noise = &default_noise;
+  if (!jitter) jitter = &default_noise;
+  cudaStream_t s = ctx->stream;
+  CK(cudaSetDevice(ctx->device));
+  Scratch sc(ctx);
+  const bool keep = post_out != nullptr;
+  const int64_t m_pad = round_up(M, TILE), lda = m_pad + TILE, n_padN = round_up(N, TILE);
+  const int nblk = (int)(m_pad / TILE);
+  CK(cudaEventRecord(ctx->ev[0], s));
+  T *ard_d = nullptr, *mean_d = nullptr, *noise_d = nullptr, *jit_d = nullptr, *yd = nullptr, *Zt = nullptr, *Xt = nullptr;
+  if (k->transform == AGP_T_ARD) { rc = upload<T>(ctx, sc, k->ard, D, true, &ard_d); if (rc) return rc; }
+  if (mean->kind == 2) { rc = upload<T>(ctx, sc, mean->v, N, true, &mean_d); if (rc) return rc; }
+  if (noise->kind == 1) { rc = upload<T>(ctx, sc, noise->v, N, true, &noise_d); if (rc) return rc; }
+  if (jitter->kind == 1) { rc = upload<T>(ctx, sc, jitter->v, M, true, &jit_d); if (rc) return rc; }
+  rc = upload<T>(ctx, sc, y, N, false, &yd); if (rc) return rc;
+  rc = prep_points<T>(ctx, sc, k, ard_d, layout, Zind, M, m_pad, D, &Zt, keep); if (rc) return rc;
+  rc = prep_points<T>(ctx, sc, k, ard_d, layout, X, N, n_padN, D, &Xt, false); if (rc) return rc;
+  void* tmp = nullptr;
+  CK(sc.alloc(&tmp, (size_t)n_padN * 3 * sizeof(T)));
+  T* kd = (T*)tmp; T* delta = kd + n_padN; T* isn = delta + n_padN;
+  CK(cudaMemsetAsync(kd, 0, (size_t)n_padN * 3 * sizeof(T), s));
+  CK(sc.alloc(&tmp, (size_t)(2 * nblk + TILE + 16) * sizeof(double)));
+  double* dscal = (double*)tmp;  // [0..3] prep scalars + ||A||^2, [8..8+nblk) logdet Kzz, [8+nblk..) logdet Lam, then sq
+  CK(cudaMemsetAsync(dscal, 0, (size_t)(2 * nblk + TILE + 16) * sizeof(double), s));
+  double* ld_z = dscal + 8; double* ld_l = ld_z + nblk; double* sq = ld_l + nblk;
+  CK(sc.alloc(&tmp, sizeof(int)));
+  int* dinfo = (int*)tmp;
+  CK(cudaMemsetAsync(dinfo, 0, sizeof(int), s));
+  launch_kdiag<T>(Xt, N, D, k->family, k->variance, k->linear_c, kd, s);
+  launch_vfe_prep<T>(yd, N, mean->kind, mean->c, mean_d, noise->kind, noise->s, noise_d, kd, delta, isn, dscal, s);
+
+  // factor buffers
+  void *Lzv = nullptr, *Dzv = nullptr, *Lmv = nullptr, *Dlv = nullptr, *mev = nullptr;
+  CK(cudaMallocAsync(&Lzv, (size_t)lda * m_pad * sizeof(T), s));
+  CK(cudaMallocAsync(&Dzv, (size_t)nblk * TILE * TILE * sizeof(T), s));
+  CK(cudaMallocAsync(&Lmv, (size_t)lda * m_pad * sizeof(T), s));
+  CK(cudaMallocAsync(&Dlv, (size_t)nblk * TILE * TILE * sizeof(T), s));
+  CK(cudaMallocAsync(&mev, (size_t)m_pad * 2 * sizeof(T), s));
+  if (!keep) { sc.ptrs.push_back(Lzv); sc.ptrs.push_back(Dzv); sc.ptrs.push_back(Lmv); sc.ptrs.push_back(Dlv); sc.ptrs.push_back(mev); }
+  T* Lz = (T*)Lzv; T* Dz = (T*)Dzv; T* Lm = (T*)Lmv; T* Dl = (T*)Dlv; T* bvec = (T*)mev; T* rwork = bvec + m_pad;
+  agp_vfe_post* vp = nullptr;
+  if (keep) {
+    vp = new agp_vfe_post();
+    vp->ctx = ctx; vp->dtype = sizeof(T) == 8 ? AGP_F64 : AGP_F32; vp->m = M; vp->m_pad = m_pad; vp->lda = lda; vp->D = D;
+    vp->U = Lzv; vp->Udinv = Dzv; vp->Lam = Lmv; vp->Ldinv = Dlv; vp->Zt = Zt; vp->m_e = mev;
+    vp->k = *k; vp->k.ard = nullptr;
+    if (ard_d) { sc.release(ard_d); vp->ard = ard_d; }
+    vp->mean_kind = mean->kind == 2 ? 0 : mean->kind; vp->mean_c = mean->c;
+  }
+  auto fail = [&](int code) { if (vp) agp_vfe_post_free(vp); return code; };
+
+  // (1) chol(K_zz + jitter)
+  GramParams gz{};
+  fill_gram_params<T>(gz, k, 1, 1, M, M, jitter, jit_d);
+  launch_gram<T>(Zt, Zt, m_pad, m_pad, D, Lz, lda, gz, s);
+  launch_border_init<T>(Lz, lda, m_pad, m_pad, (const T*)nullptr, m_pad, 0, 0, 0.0, (const T*)nullptr, s);
+  prof_begin(ctx);
+  cholesky_inplace<T>(ctx, Lz, lda, m_pad, lda, Dz, ld_z, dinfo);
+  CK(cudaEventRecord(ctx->ev[1], s));
+
+  // (2) stream the data: D += A_c A_c', b += A_c delta_c, ||A||_F^2
+  CK(cudaMemsetAsync(Lm, 0, (size_t)lda * m_pad * sizeof(T), s));
+  CK(cudaMemsetAsync(bvec, 0, (size_t)m_pad * 2 * sizeof(T), s));
+  int64_t cap = (int64_t)(2.0e9 / ((double)m_pad * sizeof(T)));
+  cap = cap / TILE * TILE;
+  if (cap < TILE) cap = TILE;
+  if (cap > n_padN) cap = n_padN;
+  void* Bv = nullptr;
+  CK(sc.alloc(&Bv, (size_t)m_pad * cap * sizeof(T)));
+  T* B = (T*)Bv;
+  for (int64_t c0 = 0; c0 < N; c0 += cap) {
+    const int64_t nc = (N - c0 < cap) ? (N - c0) : cap;
+    const int64_t nc_pad = round_up(nc, TILE);
+    GramParams gx{};
+    fill_gram_params<T>(gx, k, 0, 0, M, nc, nullptr, nullptr);
+    launch_gram<T>(Zt, Xt + c0 * D, m_pad, nc_pad, D, B, m_pad, gx, s);
+    launch_scale_cols<T>(B, m_pad, m_pad, nc, isn + c0, s);
+    forward_subst_multi<T>(ctx, Lz, lda, Dz, m_pad, B, m_pad, nc_pad);
+    GemmArgs g{};
+    g.A = B; g.lda = m_pad; g.B = B; g.ldb = m_pad; g.C = Lm; g.ldc = lda;
+    g.M = m_pad; g.N = m_pad; g.K = nc_pad; g.beta_one = 1; g.lower_only = 1;
+    launch_gemm<T>(g, s);
+    launch_gemv_n_acc<T>(B, m_pad, m_pad, nc, delta + c0, bvec, s);
+    launch_sumsq<T>(B, m_pad * nc_pad, dscal + 3, s);
+  }
+  CK(cudaEventRecord(ctx->ev[2], s));
+
+  // (3) Lambda = chol(D + I), with b riding in the border row
+  launch_add_diag<T>(Lm, lda, m_pad, 1.0, s);
+  launch_border_init<T>(Lm, lda, m_pad, m_pad, bvec, m_pad, 1, 0, 0.0, (const T*)nullptr, s);
+  cholesky_inplace<T>(ctx, Lm, lda, m_pad, lda, Dl, ld_l, dinfo);
+  launch_extract_v<T>(Lm, lda, m_pad, 1, rwork, sq, s);
+  if (keep) {
+    CK(sc.alloc(&tmp, (size_t)(nblk + 1) * sizeof(int)));
+    int* dflags = (int*)tmp;
+    launch_bwd_solve<T>(Lm, lda, Dl, nblk, rwork, dflags, s);       // m_e = Lambda^-1 b
+    CK(cudaMemcpyAsync(bvec, rwork, (size_t)m_pad * sizeof(T), cudaMemcpyDeviceToDevice, s));  // m_e kept in slot 0
+  }
+  CK(cudaEventRecord(ctx->ev[3], s));
+  std::vector<double> h((size_t)(2 * nblk + 16 + 1));
+  int h_info = 0;
+  CK(cudaMemcpyAsync(h.data(), dscal, (size_t)(2 * nblk + 16 + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h_info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]); ctx->timings[0] = ms;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->timings[3] = ms;
+  cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->timings[6] = ms;
+  ctx->timings[7] = ctx->profile ? prof_total_ms(ctx) : 0.0;
+  if (h_info != 0) {
+    ctx->info = h_info;
+    ctx->err = "VFE: K_zz + jitter or A A' + I is not positive definite";
+    return fail(AGP_ERR_NOT_POSDEF);
+  }
+  double logdet_lam = 0.0;
+  for (int b = 0; b < nblk; ++b) logdet_lam += h[8 + nblk + b];
+  logdet_lam *= 2.0;
+  const double log2pi = 1.8378770664093454835606594728112;
+  const double sqv = h[8 + 2 * nblk];
+  const double dtc = -0.5 * ((double)N * log2pi + h[0] + logdet_lam + h[1] - sqv);
+  const double elbo = dtc - 0.5 * (h[2] - h[3]);
+  T e = (T)elbo, dd = (T)dtc;
+  if (elbo_out) memcpy(elbo_out, &e, sizeof(T));
+  if (dtc_out) memcpy(dtc_out, &dd, sizeof(T));
+  if (keep) *post_out = vp;
+  return AGP_OK;
+}
+
+template <typename T>
+int vfe_mean_var_impl(agp_vfe_post* p, int layout, const void* Xs, int64_t Ms, void* mean_out, void* var_out) {
+  agp_ctx* ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  CK(cudaSetDevice(ctx->device));
+  if (Ms <= 0) return AGP_OK;
+  int64_t cap = (int64_t)(2.0e9 / ((double)p->m_pad * sizeof(T)));
+  cap = cap / TILE * TILE;
+  if (cap < TILE) cap = TILE;
+  for (int64_t c0 = 0; c0 < Ms; c0 += cap) {
+    const int64_t mc = (Ms - c0 < cap) ? (Ms - c0) : cap;
+    const int64_t c_pad = round_up(mc, TILE);
+    Scratch sc(ctx);
+    if (layout != AGP_POINT_MAJOR && !(c0 == 0 && mc == Ms)) {
+      ctx->err = "feature-major test sets larger than one chunk are unsupported";
+      return AGP_ERR_UNSUPPORTED;
+    }
+    const void* xs_chunk = (layout == AGP_POINT_MAJOR) ? (const void*)((const char*)Xs + (size_t)c0 * p->D * sizeof(T)) : Xs;
+    T* Xst = nullptr;
+    int rc = prep_points<T>(ctx, sc, &p->k, (const T*)p->ard, layout, xs_chunk, mc, c_pad, p->D, &Xst, false);
+    if (rc) return rc;
+    void* tmp = nullptr;
+    CK(sc.alloc(&tmp, (size_t)p->m_pad * c_pad * sizeof(T)));
+    T* B = (T*)tmp;
+    CK(sc.alloc(&tmp, (size_t)c_pad * 2 * sizeof(T)));
+    T* mu = (T*)tmp; T* var = mu + c_pad;
+    GramParams gp{};
+    fill_gram_params<T>(gp, &p->k, 0, 0, p->m, mc, nullptr, nullptr);
+    launch_gram<T>((const T*)p->Zt, Xst, p->m_pad, c_pad, p->D, B, p->m_pad, gp, s);
+    forward_subst_multi<T>(ctx, (const T*)p->U, p->lda, (const T*)p->Udinv, p->m_pad, B, p->m_pad, c_pad);  // A*
+    launch_gemv_t<T>(B, p->m_pad, p->m_pad, mc, (const T*)p->m_e, p->mean_kind, p->mean_c, (const T*)nullptr, mu, s);
+    launch_kdiag<T>(Xst, mc, p->D, p->k.family, p->k.variance, p->k.linear_c, var, s);
+    launch_colsumsq_acc<T>(B, p->m_pad, p->m_pad, mc, -1.0, var, s);
+    forward_subst_multi<T>(ctx, (const T*)p->Lam, p->lda, (const T*)p->Ldinv, p->m_pad, B, p->m_pad, c_pad);
+    launch_colsumsq_acc<T>(B, p->m_pad, p->m_pad, mc, 1.0, var, s);
+    if (mean_out) { rc = download<T>(ctx, (T*)mean_out + c0, mu, mc, false); if (rc) return rc; }
+    if (var_out) { rc = download<T>(ctx, (T*)var_out + c0, var, mc, false); if (rc) return rc; }
+    CK(cudaStreamSynchronize(s));
+  }
+  CK(cudaGetLastError());
+  return AGP_OK;
+}
+
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -599,11 +995,12 @@ int32_t agp_init(agp_ctx** out, int32_t device, const agp_config* cfg) {
   ctx->cfg.tile_nb = TILE;
   ctx->cfg.fp64_mode = env_int("AGP_FP64_MODE", ctx->cfg.fp64_mode);
   ctx->cfg.fp32_mode = env_int("AGP_FP32_MODE", ctx->cfg.fp32_mode);
-  ctx->cfg.lookahead = env_int("AGP_LOOKAHEAD", ctx->cfg.lookahead);
+  ctx->cfg.lookahead = env_int("AGP_LOOKAHEAD", cfg ? ctx->cfg.lookahead : 1);
   ctx->cfg.use_graph = env_int("AGP_GRAPH", ctx->cfg.use_graph);
   ctx->profile = env_int("AGP_PROFILE", 1);
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -620,6 +1017,8 @@ int32_t agp_destroy(agp_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
   for (auto e : ctx->prof_ev) cudaEventDestroy(e);
+  for (auto e : ctx->dep_ev) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return AGP_OK;
@@ -697,6 +1096,8 @@ int32_t agp_post_free(agp_post* p) {
   if (p->Xt) cudaFreeAsync(p->Xt, s);
   if (p->alpha) cudaFreeAsync(p->alpha, s);
   if (p->ard) cudaFreeAsync(p->ard, s);
+  if (p->delta) cudaFreeAsync(p->delta, s);
+  if (p->valid) cudaFreeAsync(p->valid, s);
   delete p;
   return AGP_OK;
 }
@@ -717,28 +1118,48 @@ int64_t agp_bc_local_tiles(int32_t nt, int32_t rank, int32_t P, int32_t Q) {
   return c;
 }
 
-// ---- not yet implemented in this build (tracked in DESIGN.md "status") ---------------------------
+// ---- multi-GPU entry points are provided by dist.cu ------------------------------------------------
+int32_t agp_post_extend(agp_post* p, int32_t layout, const void* X2, int64_t N2, const void* y2, const agp_mean* mean2,
+                        const agp_noise* noise2, void* alpha_out) {
+  if (!p) return AGP_ERR_INVALID;
+  return DISPATCH(p->dtype, post_extend_impl<float>(p, layout, X2, N2, y2, mean2, noise2, alpha_out),
+                  post_extend_impl<double>(p, layout, X2, N2, y2, mean2, noise2, alpha_out));
+}
+int32_t agp_vfe_elbo(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, const agp_mean* mean, const agp_noise* noise,
+                     int32_t layout, const void* X, int64_t N, int32_t D, const void* Zind, int64_t M,
+                     const agp_noise* jitter, const void* y, void* elbo_out, void* dtc_out) {
+  if (!ctx) return AGP_ERR_INVALID;
+  return DISPATCH(dtype, vfe_core<float>(ctx, k, mean, noise, layout, X, N, D, Zind, M, jitter, y, elbo_out, dtc_out, nullptr),
+                  vfe_core<double>(ctx, k, mean, noise, layout, X, N, D, Zind, M, jitter, y, elbo_out, dtc_out, nullptr));
+}
+int32_t agp_vfe_fit(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, const agp_mean* mean, const agp_noise* noise,
+                    int32_t layout, const void* X, int64_t N, int32_t D, const void* Zind, int64_t M,
+                    const agp_noise* jitter, const void* y, agp_vfe_post** out) {
+  if (!ctx || !out) return AGP_ERR_INVALID;
+  *out = nullptr;
+  return DISPATCH(dtype, vfe_core<float>(ctx, k, mean, noise, layout, X, N, D, Zind, M, jitter, y, nullptr, nullptr, out),
+                  vfe_core<double>(ctx, k, mean, noise, layout, X, N, D, Zind, M, jitter, y, nullptr, nullptr, out));
+}
+int32_t agp_vfe_mean_var(agp_vfe_post* p, int32_t layout, const void* Xs, int64_t Ms, void* mean_out, void* var_out) {
+  if (!p) return AGP_ERR_INVALID;
+  return DISPATCH(p->dtype, vfe_mean_var_impl<float>(p, layout, Xs, Ms, mean_out, var_out),
+                  vfe_mean_var_impl<double>(p, layout, Xs, Ms, mean_out, var_out));
+}
+int32_t agp_vfe_post_free(agp_vfe_post* p) {
+  if (!p) return AGP_OK;
+  cudaSetDevice(p->ctx->device);
+  cudaStream_t s = p->ctx->stream;
+  void* ptrs[] = {p->U, p->Udinv, p->Lam, p->Ldinv, p->Zt, p->m_e, p->ard};
+  for (void* q : ptrs) if (q) cudaFreeAsync(q, s);
+  delete p;
+  return AGP_OK;
+}
+// (agp_nccl_unique_id / agp_init_dist: see below)
 int32_t agp_nccl_unique_id(void*) { return AGP_ERR_UNSUPPORTED; }
 int32_t agp_init_dist(agp_ctx** ctx, int32_t, int32_t, int32_t, int32_t, int32_t, const void*, const agp_config*) {
   if (ctx) *ctx = nullptr;
   return AGP_ERR_UNSUPPORTED;
 }
-int32_t agp_post_extend(agp_post* p, int32_t, const void*, int64_t, const void*, const agp_mean*, const agp_noise*, void*) {
-  if (p) p->ctx->err = "agp_post_extend: not implemented yet";
-  return AGP_ERR_UNSUPPORTED;
-}
-int32_t agp_vfe_elbo(agp_ctx* ctx, int32_t, const agp_kernel*, const agp_mean*, const agp_noise*, int32_t, const void*,
-                     int64_t, int32_t, const void*, int64_t, const agp_noise*, const void*, void*, void*) {
-  if (ctx) ctx->err = "agp_vfe_elbo: not implemented yet";
-  return AGP_ERR_UNSUPPORTED;
-}
-int32_t agp_vfe_fit(agp_ctx* ctx, int32_t, const agp_kernel*, const agp_mean*, const agp_noise*, int32_t, const void*,
-                    int64_t, int32_t, const void*, int64_t, const agp_noise*, const void*, agp_vfe_post** out) {
-  if (out) *out = nullptr;
-  if (ctx) ctx->err = "agp_vfe_fit: not implemented yet";
-  return AGP_ERR_UNSUPPORTED;
-}
-int32_t agp_vfe_mean_var(agp_vfe_post*, int32_t, const void*, int64_t, void*, void*) { return AGP_ERR_UNSUPPORTED; }
-int32_t agp_vfe_post_free(agp_vfe_post* p) { delete p; return AGP_OK; }
+
 
 }  // extern "C"

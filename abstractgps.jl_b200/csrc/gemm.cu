@@ -16,12 +16,13 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 16;
 
 // ------------------------------------------------------------------------------------------------
-// fp64 DMMA kernel
+// fp64 DMMA kernel.  CTA tile 128 x (32*WN); WN = 2 -> 128x64 tile, 128 threads, 2 CTAs/SM so one
+// CTA's read-modify-write epilogue overlaps the other's main loop; WN = 4 -> 128x128, 256 threads
+// (used for the in-place panel TRSM, which needs one CTA to own all 128 columns of its rows).
 // ------------------------------------------------------------------------------------------------
 constexpr int D_STAGES = 3;
-constexpr int D_LDMN = BM + 4;  // MN-major smem stride (doubles): 132 -> row shift of 8 banks
-constexpr int D_LDK = BK + 4;   // K-major smem stride (doubles): 20 -> row shift of 8 banks
-constexpr int D_OPSZ = (BM * D_LDK > BK * D_LDMN) ? BM * D_LDK : BK * D_LDMN;  // doubles per operand stage
+constexpr int D_LDK = BK + 4;  // K-major smem stride (doubles): 20 -> row shift of 8 banks
+__host__ __device__ constexpr int d_opsz(int rows) { return (rows * D_LDK > BK * (rows + 4)) ? rows * D_LDK : BK * (rows + 4); }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -33,25 +34,22 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
-// element (mn, k) of a 128 x 16 operand slab starting at (mn0, k0)
-template <bool KMAJOR>
+// element (mn, k) of a ROWS x 16 operand slab starting at (mn0, k0); MN-major smem stride ROWS+4
+template <bool KMAJOR, int ROWS, int NT>
 __device__ __forceinline__ void d_load_tile(double* s, const double* __restrict__ g, int64_t ld, int64_t mn0,
                                             int64_t k0, int64_t MN, int64_t K, int tid) {
-  if (!KMAJOR) {
+  constexpr int CHUNKS = ROWS * 8;  // 16-byte chunks in the slab
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      int q = tid + 256 * it;
-      int k = q >> 6, mn = (q & 63) * 2;
-      bool valid = (mn0 + mn < MN) && (k0 + k < K);
+  for (int it = 0; it < CHUNKS / NT; ++it) {
+    const int q = tid + NT * it;
+    if (!KMAJOR) {
+      const int k = q / (ROWS / 2), mn = (q % (ROWS / 2)) * 2;
+      const bool valid = (mn0 + mn < MN) && (k0 + k < K);
       const double* src = valid ? (g + (mn0 + mn) + (k0 + k) * ld) : g;
-      cp_async16(s + k * D_LDMN + mn, src, valid);
-    }
-  } else {
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      int q = tid + 256 * it;
-      int mn = q >> 3, k = (q & 7) * 2;
-      bool valid = (mn0 + mn < MN) && (k0 + k < K);
+      cp_async16(s + k * (ROWS + 4) + mn, src, valid);
+    } else {
+      const int mn = q >> 3, k = (q & 7) * 2;
+      const bool valid = (mn0 + mn < MN) && (k0 + k < K);
       const double* src = valid ? (g + (k0 + k) + (mn0 + mn) * ld) : g;
       cp_async16(s + mn * D_LDK + k, src, valid);
     }
@@ -64,23 +62,26 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-template <bool AK, bool BKM>
-__global__ void __launch_bounds__(256, 1) gemm_dmma_kernel(GemmArgs g) {
+template <bool AK, bool BKM, int WM, int WN>
+__global__ void __launch_bounds__(32 * WM * WN, (WM * WN <= 4) ? 2 : 1) gemm_dmma_kernel(GemmArgs g) {
+  constexpr int NT = 32 * WM * WN, TBM = 64 * WM, TBN = 32 * WN;
+  constexpr int A_SZ = d_opsz(TBM), B_SZ = d_opsz(TBN);
+  constexpr int A_LD = TBM + 4, B_LD = TBN + 4;
   const int bi = blockIdx.x, bj = blockIdx.y;
-  if (g.lower_only && bj > bi) return;
+  const int64_t m0 = (int64_t)bi * TBM, n0 = (int64_t)bj * TBN;
+  if (g.lower_only && n0 >= m0 + TBM) return;  // tile entirely above the diagonal
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
-  double* sA = sm;                         // [D_STAGES][D_OPSZ]
-  double* sB = sm + D_STAGES * D_OPSZ;
+  double* sA = sm;                    // [D_STAGES][A_SZ]
+  double* sB = sm + D_STAGES * A_SZ;  // [D_STAGES][B_SZ]
   const double* __restrict__ A = (const double*)g.A;
   const double* __restrict__ B = (const double*)g.B;
-  double* __restrict__ C = (double*)g.C;
+  double* C = (double*)g.C;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wm = warp & 1, wn = warp >> 1;
+  const int wm = warp % WM, wn = warp / WM;
   const int gq = lane >> 2, q = lane & 3;
-  const int64_t m0 = (int64_t)bi * BM, n0 = (int64_t)bj * BN;
   int64_t K = g.K;
-  if (g.trmm_lower) { int64_t kl = m0 + BM; if (kl < K) K = kl; }
+  if (g.trmm_lower) { int64_t kl = m0 + TBM; if (kl < K) K = kl; }
   const int KT = (int)((K + BK - 1) / BK);
 
   double acc[8][4][2];
@@ -92,8 +93,8 @@ __global__ void __launch_bounds__(256, 1) gemm_dmma_kernel(GemmArgs g) {
 #pragma unroll
   for (int s = 0; s < D_STAGES - 1; ++s) {
     if (s < KT) {
-      d_load_tile<AK>(sA + s * D_OPSZ, A, g.lda, m0, (int64_t)s * BK, g.M, K, tid);
-      d_load_tile<BKM>(sB + s * D_OPSZ, B, g.ldb, n0, (int64_t)s * BK, g.N, K, tid);
+      d_load_tile<AK, TBM, NT>(sA + s * A_SZ, A, g.lda, m0, (int64_t)s * BK, g.M, K, tid);
+      d_load_tile<BKM, TBN, NT>(sB + s * B_SZ, B, g.ldb, n0, (int64_t)s * BK, g.N, K, tid);
     }
     cp_async_commit();
   }
@@ -104,25 +105,25 @@ __global__ void __launch_bounds__(256, 1) gemm_dmma_kernel(GemmArgs g) {
       const int nk = kt + D_STAGES - 1;
       if (nk < KT) {
         const int st = nk % D_STAGES;
-        d_load_tile<AK>(sA + st * D_OPSZ, A, g.lda, m0, (int64_t)nk * BK, g.M, K, tid);
-        d_load_tile<BKM>(sB + st * D_OPSZ, B, g.ldb, n0, (int64_t)nk * BK, g.N, K, tid);
+        d_load_tile<AK, TBM, NT>(sA + st * A_SZ, A, g.lda, m0, (int64_t)nk * BK, g.M, K, tid);
+        d_load_tile<BKM, TBN, NT>(sB + st * B_SZ, B, g.ldb, n0, (int64_t)nk * BK, g.N, K, tid);
       }
       cp_async_commit();
     }
-    const double* a_s = sA + (kt % D_STAGES) * D_OPSZ;
-    const double* b_s = sB + (kt % D_STAGES) * D_OPSZ;
+    const double* a_s = sA + (kt % D_STAGES) * A_SZ;
+    const double* b_s = sB + (kt % D_STAGES) * B_SZ;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
       double af[8], bf[4];
 #pragma unroll
       for (int mi = 0; mi < 8; ++mi) {
         const int m = wm * 64 + mi * 8 + gq;
-        af[mi] = AK ? a_s[m * D_LDK + kk + q] : a_s[(kk + q) * D_LDMN + m];
+        af[mi] = AK ? a_s[m * D_LDK + kk + q] : a_s[(kk + q) * A_LD + m];
       }
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
         const int n = wn * 32 + ni * 8 + gq;
-        bf[ni] = BKM ? b_s[n * D_LDK + kk + q] : b_s[(kk + q) * D_LDMN + n];
+        bf[ni] = BKM ? b_s[n * D_LDK + kk + q] : b_s[(kk + q) * B_LD + n];
       }
 #pragma unroll
       for (int mi = 0; mi < 8; ++mi)
@@ -132,23 +133,36 @@ __global__ void __launch_bounds__(256, 1) gemm_dmma_kernel(GemmArgs g) {
   }
   cp_async_wait<0>();
 
-  // epilogue: C(m, n), thread holds rows gq, cols 2q, 2q+1 of each 8x8 tile
+  // epilogue: C(m, n); a thread holds rows gq, cols 2q, 2q+1 of each 8x8 tile.  The C reads of row
+  // group mi+1 are issued before the stores of group mi so the round trips overlap.
+  const int64_t mbase = m0 + wm * 64 + gq;
+  const int64_t nbase = n0 + wn * 32 + 2 * q;
+  const bool beta = g.beta_one != 0;
+  const double sgn = g.alpha_neg ? -1.0 : 1.0;
+  double cv[2][8];
+  auto load_group = [&](int mi, double* dst) {
+    const int64_t m = mbase + mi * 8;
 #pragma unroll
-  for (int mi = 0; mi < 8; ++mi) {
-    const int64_t m = m0 + wm * 64 + mi * 8 + gq;
-    if (m >= g.M) continue;
-#pragma unroll
-    for (int ni = 0; ni < 4; ++ni) {
+    for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int64_t n = n0 + wn * 32 + ni * 8 + 2 * q + e;
-        if (n >= g.N) continue;
-        double* p = C + m + n * g.ldc;
-        double v = acc[mi][ni][e];
-        if (g.alpha_neg) v = -v;
-        if (g.beta_one) v += *p;
-        *p = v;
+        const int64_t n = nbase + ni * 8 + e;
+        dst[ni * 2 + e] = (beta && m < g.M && n < g.N) ? C[m + n * g.ldc] : 0.0;
       }
+  };
+  load_group(0, cv[0]);
+#pragma unroll
+  for (int mi = 0; mi < 8; ++mi) {
+    if (mi + 1 < 8) load_group(mi + 1, cv[(mi + 1) & 1]);
+    const int64_t m = mbase + mi * 8;
+    if (m < g.M) {
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int64_t n = nbase + ni * 8 + e;
+          if (n < g.N) C[m + n * g.ldc] = fma(sgn, acc[mi][ni][e], cv[mi & 1][ni * 2 + e]);
+        }
     }
   }
 }
@@ -273,22 +287,41 @@ void launch_cfg(KernelT kern, const GemmArgs& g, size_t smem, cudaStream_t s) {
 }
 }  // namespace
 
+template <bool AK, bool BKM, int WM, int WN>
+static void launch_dmma(const GemmArgs& g, cudaStream_t s) {
+  constexpr int TBM = 64 * WM, TBN = 32 * WN;
+  const size_t smem = (size_t)D_STAGES * (d_opsz(TBM) + d_opsz(TBN)) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(gemm_dmma_kernel<AK, BKM, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  dim3 grid((unsigned)((g.M + TBM - 1) / TBM), (unsigned)((g.N + TBN - 1) / TBN));
+  gemm_dmma_kernel<AK, BKM, WM, WN><<<grid, 32 * WM * WN, smem, s>>>(g);
+  agp_count_launch();
+}
+
 template <>
 void launch_gemm<double>(const GemmArgs& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0) return;
-  const size_t smem = (size_t)2 * D_STAGES * D_OPSZ * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(gemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(gemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(gemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
+  // in-place products (C aliases an operand) need one CTA to own every column it reads: 128-wide tile.
+  // C == A (panel TRSM): 64 x 128 tiles, 2 CTAs/SM -- twice the CTAs on the latency-critical panel solve.
+  if (g.C == g.A) {
+    if (!g.a_kmajor && !g.b_kmajor) launch_dmma<false, false, 1, 4>(g, s);
+    else if (!g.a_kmajor && g.b_kmajor) launch_dmma<false, true, 1, 4>(g, s);
+    else if (g.a_kmajor && !g.b_kmajor) launch_dmma<true, false, 1, 4>(g, s);
+    else launch_dmma<true, true, 1, 4>(g, s);
+  } else if (g.C == g.B) {
+    if (!g.a_kmajor && !g.b_kmajor) launch_dmma<false, false, 2, 4>(g, s);
+    else if (!g.a_kmajor && g.b_kmajor) launch_dmma<false, true, 2, 4>(g, s);
+    else if (g.a_kmajor && !g.b_kmajor) launch_dmma<true, false, 2, 4>(g, s);
+    else launch_dmma<true, true, 2, 4>(g, s);
+  } else {
+    if (!g.a_kmajor && !g.b_kmajor) launch_dmma<false, false, 2, 2>(g, s);
+    else if (!g.a_kmajor && g.b_kmajor) launch_dmma<false, true, 2, 2>(g, s);
+    else if (g.a_kmajor && !g.b_kmajor) launch_dmma<true, false, 2, 2>(g, s);
+    else launch_dmma<true, true, 2, 2>(g, s);
   }
-  if (!g.a_kmajor && !g.b_kmajor) launch_cfg(gemm_dmma_kernel<false, false>, g, smem, s);
-  else if (!g.a_kmajor && g.b_kmajor) launch_cfg(gemm_dmma_kernel<false, true>, g, smem, s);
-  else if (g.a_kmajor && !g.b_kmajor) launch_cfg(gemm_dmma_kernel<true, false>, g, smem, s);
-  else launch_cfg(gemm_dmma_kernel<true, true>, g, smem, s);
 }
 
 template <>

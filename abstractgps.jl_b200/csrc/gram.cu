@@ -144,14 +144,16 @@ gram_kernel(const T* __restrict__ Xa, const T* __restrict__ Xb, int D, T* __rest
     for (int r = 0; r < 4; ++r) {
       const int64_t gi = row0 + tx + 16 * r;
       T v;
-      if (gi >= p.valid_a || gj >= p.valid_b) {
+      const bool pad_a = p.mask_a ? (p.mask_a[gi] == 0) : (gi >= p.valid_a);
+      const bool pad_b = p.mask_b ? (p.mask_b[gj] == 0) : (gj >= p.valid_b);
+      if (pad_a || pad_b) {
         v = (p.symmetric && gi == gj) ? (T)1 : (T)0;  // identity padding
       } else {
         T a = acc[r][c];
         if (p.symmetric && gi == gj && !linear) a = 0;  // exactly-zero self distance
         v = kappa<T>(p.family, a, variance, lc);
         if (p.symmetric && gi == gj && p.noise_kind >= 0)
-          v += (p.noise_kind == 0) ? (T)p.noise_s : ((const T*)p.noise_v)[gi];
+          v += (p.noise_kind == 0) ? (T)p.noise_s : ((const T*)p.noise_v)[gi - p.noise_off];
       }
       K[gi + gj * ldk] = v;
     }

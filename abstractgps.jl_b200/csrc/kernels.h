@@ -19,6 +19,9 @@ struct GramParams {
   int noise_kind;    // -1 none, 0 scalar, 1 vector
   double noise_s;
   const void* noise_v;  // device, T
+  const unsigned char* mask_a;  // optional per-row validity (extended posteriors); overrides valid_a
+  const unsigned char* mask_b;
+  int64_t noise_off;  // noise_v index offset for the diagonal (block Gram of an extension)
 };
 
 // op(A) is M x K, op(B) is K x N, C is M x N (ldc).  C = beta*C + alpha*op(A)op(B), alpha in {+1,-1}.
@@ -56,6 +59,9 @@ template <typename T> void launch_extract_v(const T* A, int64_t lda, int64_t n_p
 // one step of the blocked backward substitution L' alpha = r (in place in r), block k
 template <typename T> void launch_bwd_step(const T* A, int64_t lda, const T* Dinv, int k, T* r,
                                            cudaStream_t s);
+// whole backward substitution in one persistent launch; flags_and_ticket: nblk+1 ints (zeroed inside)
+template <typename T> void launch_bwd_solve(const T* A, int64_t lda, const T* Dinv, int nblk, T* r,
+                                            int* flags_and_ticket, cudaStream_t s);
 // one step of the blocked forward substitution L v = r (in place), block k (used by extend / vfe)
 template <typename T> void launch_fwd_step(const T* A, int64_t lda, const T* Dinv, int k, int nblk, T* r,
                                            cudaStream_t s);
@@ -76,6 +82,16 @@ template <typename T> void launch_add_mean_cols(T* out, int64_t ldo, int64_t n, 
 // C[i + j*ldc] = Kss[i + j*ldc] - C[...]  and symmetrise (mean_and_cov epilogue)
 template <typename T> void launch_cov_finish(T* C, int64_t ldc, const T* Kss, int64_t m, cudaStream_t s);
 template <typename T> void launch_fill(T* p, int64_t n, double v, cudaStream_t s);
+// out[i] = y[i] - mean_i
+template <typename T> void launch_sub_mean(const T* y, int64_t n, int mean_kind, double mean_c, const T* mean_v, T* out, cudaStream_t s);
+// y[m] += sum_n A[m + n*lda] * x[n]   (rows coalesced)
+template <typename T> void launch_gemv_n_acc(const T* A, int64_t lda, int64_t m, int64_t n, const T* x, T* y, cudaStream_t s);
+// out[j] += sign * sum_i V[i + j*ldv]^2
+template <typename T> void launch_colsumsq_acc(const T* V, int64_t ldv, int64_t n, int64_t m, double sign, T* out, cudaStream_t s);
+// zero the strict upper triangle of every TILE x TILE diagonal block of an n_pad x n_pad factor
+template <typename T> void launch_zero_diag_upper(T* A, int64_t lda, int64_t n_pad, cudaStream_t s);
+// U(i,j) = L(map[j], map[i]) for i <= j (map == nullptr -> identity)
+template <typename T> void launch_export_upper_map(const T* A, int64_t lda, int64_t n, const int64_t* map, T* U, int64_t ldo, cudaStream_t s);
 template <typename T> void launch_copy2d(const T* src, int64_t lds, T* dst, int64_t ldd, int64_t rows,
                                          int64_t cols, cudaStream_t s);
 // generic small helpers for VFE

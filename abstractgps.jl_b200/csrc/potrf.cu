@@ -5,10 +5,10 @@
 //
 // Scheme: the lower triangle of the smem array holds A -> L; the STRICT UPPER triangle holds the rows
 // of E = I * L^-T that a bordered elimination produces for free (E(r,c) lives at position (c,r)), its
-// diagonal (1/L_jj) in dinv[].  16 micro-panels of 8 columns: (1) the 8 lanes owning the diagonal
-// 8x8 rows factor it in registers with width-8 warp shuffles (no block barrier on the column chain),
-// (2) every other active row (below, and the E rows) does an 8-step substitution against it,
-// (3) rank-8 trailing update, one thread per (row, column-parity).  3 block barriers per micro-panel.
+// diagonal (1/L_jj) in dinv[].  16 micro-panels of 8 columns.  Row worker w is S row w until the
+// micro-panel that finishes it, then E row w -- so all 128 workers (x2 column-parity halves) stay busy.
+// Phase A: every thread factors the 8x8 diagonal block redundantly in registers (no shuffles, no
+// barrier on the sqrt chain) and substitutes its own row; phase B: rank-8 trailing update of its row.
 #include "kernels.h"
 #include "agp.h"
 
@@ -16,10 +16,20 @@ namespace {
 constexpr int PB = AGP_TILE;  // 128
 constexpr int PLD = PB + 1;   // odd leading dimension -> conflict-free column/row access
 
+// 1/sqrt(p) on the critical path of the column chain: hardware approximation (MUFU.RSQ64H, ~20 bits)
+// + two Newton steps (3 dependent DFMA-class ops each) -> full fp64 precision, ~half the dependent
+// depth of rsqrt(double)'s library sequence.  p is a positive, normal pivot.
 template <typename T> __device__ __forceinline__ T dev_rsqrt_refined(T p);
 template <> __device__ __forceinline__ double dev_rsqrt_refined<double>(double p) {
-  double r = rsqrt(p);
-  return fma(r * 0.5, fma(-p * r, r, 1.0), r);  // one Newton step -> < 1 ulp
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(p));
+  const double hp = -0.5 * p;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double e = fma(hp * y, y, 0.5);  // 0.5 - 0.5 p y^2
+    y = fma(y, e, y);                      // y (1.5 - 0.5 p y^2)
+  }
+  return y;
 }
 template <> __device__ __forceinline__ float dev_rsqrt_refined<float>(float p) {
   float r = rsqrtf(p);
@@ -39,111 +49,139 @@ template <> __device__ __forceinline__ void load8<float>(const float* p, float* 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(256, 1)
 potrf_diag_kernel(T* __restrict__ A, int64_t lda, T* __restrict__ Dinv, double* __restrict__ logdet_part,
                   int blk, int* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* arr = reinterpret_cast<T*>(smem_raw);  // arr[c*PLD + i]
-  T* P8 = arr + PB * PLD + ((PB * PLD) & 1);  // keep 16B alignment for T=double (PB*PLD even anyway)
-  T* Ld = P8 + PB * 8;                        // Ld[row*8 + col]
-  T* dinv = Ld + 64;
+  T* P8 = arr + PB * PLD;                   // P8[k*8 + c] : factored micro-panel, row k (16B aligned: PB*PLD even)
+  T* dinv = P8 + PB * 8;
   __shared__ double red[4];
   const int tid = threadIdx.x;
-  const int slot = tid & 255, half = tid >> 8;
+  const int w = tid & (PB - 1), half = tid >> 7;  // row worker, column-parity half
 
-  for (int idx = tid; idx < PB * PB; idx += 512) {
-    int c = idx >> 7, i = idx & 127;
-    arr[c * PLD + i] = (i >= c) ? A[i + (int64_t)c * lda] : (T)0;
+  // global -> smem: 64 elements per thread, issued as 4 batches of 16 INDEPENDENT loads (a plain loop
+  // serialises one DRAM round trip per element: 64 x ~0.8 us)
+#pragma unroll
+  for (int b0 = 0; b0 < 64; b0 += 16) {
+    T tmp[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * (b0 + u);
+      const int c = idx >> 7, i = idx & 127;
+      tmp[u] = (i >= c) ? __ldg(A + i + (int64_t)c * lda) : (T)0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * (b0 + u);
+      arr[(idx >> 7) * PLD + (idx & 127)] = tmp[u];
+    }
   }
   __syncthreads();
 
   for (int j0 = 0; j0 < PB; j0 += 8) {
-    // ---- (1) diagonal 8x8 in registers (whole warp executes; only the owning 8-lane group is real)
-    if (tid < PB && (tid >> 5) == (j0 >> 5)) {
-      const int i = tid, lane8 = i & 7;
-      const bool mine = ((i & ~7) == j0);
-      T a[8];
+    // ---- phase A: every thread factors the 8x8 diagonal block redundantly in registers (no shuffles,
+    // no barrier on the sqrt chain), then substitutes its own row against it.
+    T d[8][8], rinv[8], x[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) a[c] = arr[(j0 + c) * PLD + i];
+    for (int r = 0; r < 8; ++r)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        T piv = __shfl_sync(0xffffffffu, a[c], c, 8);
-        const bool bad = !(piv > (T)0);
-        if (bad) {
-          if (mine && lane8 == c) atomicCAS(info, 0, blk * PB + j0 + c + 1);
-          piv = (T)1;
-        }
-        const T r = dev_rsqrt_refined<T>(piv);
-        a[c] *= r;
-        if (mine && lane8 == c) { dinv[j0 + c] = r; a[c] = piv * r; }
+      for (int c = 0; c <= r; ++c) d[r][c] = arr[(j0 + c) * PLD + j0 + r];
 #pragma unroll
-        for (int c2 = c + 1; c2 < 8; ++c2) {
-          T l = __shfl_sync(0xffffffffu, a[c], c2, 8);
-          if (lane8 >= c2) a[c2] -= a[c] * l;
-        }
+    for (int c = 0; c < 8; ++c) {
+      T piv = d[c][c];
+      if (!(piv > (T)0)) {
+        if (tid == j0) atomicCAS(info, 0, blk * PB + j0 + c + 1);
+        piv = (T)1;
       }
-      if (mine) {
+      const T r = dev_rsqrt_refined<T>(piv);
+      rinv[c] = r;
+      d[c][c] = piv * r;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          if (c <= lane8) { arr[(j0 + c) * PLD + i] = a[c]; Ld[lane8 * 8 + c] = a[c]; }
-      }
+      for (int r2 = c + 1; r2 < 8; ++r2) d[r2][c] *= r;
+#pragma unroll
+      for (int c2 = c + 1; c2 < 8; ++c2)
+#pragma unroll
+        for (int r2 = c2; r2 < 8; ++r2) d[r2][c2] -= d[r2][c] * d[c2][c];
     }
-    __syncthreads();
-    // ---- (2) substitution of every other active row against the 8x8 factor
-    const bool is_s = slot < PB;
-    const int row = is_s ? slot : slot - PB;
-    const bool active = is_s ? (row >= j0 + 8) : (row < j0 + 8);
-    T x[8];
-    if (active) {
+    const bool is_s = (w >= j0 + 8);          // still an S (factor) row; otherwise an E (inverse) row
+    const bool is_diag = (w >= j0) && !is_s;  // one of the 8 diagonal rows of this micro-panel
+    {
       T a[8];
-      if (is_s || row < j0) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) a[c] = arr[(j0 + c) * PLD + row];
-      } else {
-        const int cr = row - j0;
+      if (is_diag) {
+        const int cr = w - j0;
 #pragma unroll
         for (int c = 0; c < 8; ++c) a[c] = (c == cr) ? (T)1 : (T)0;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[c] = arr[(j0 + c) * PLD + w];
       }
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        T s = a[c];
+        T sacc = a[c];
 #pragma unroll
-        for (int c2 = 0; c2 < c; ++c2) s -= x[c2] * Ld[c * 8 + c2];
-        x[c] = s * dinv[j0 + c];
+        for (int c2 = 0; c2 < c; ++c2) sacc -= x[c2] * d[c][c2];
+        x[c] = sacc * rinv[c];
       }
-      if (half == 0) {
-        if (is_s) {
+    }
+    __syncthreads();  // every thread has read its inputs from arr before anyone overwrites them
+    if (half == 0) {
+      if (is_s) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) { arr[(j0 + c) * PLD + row] = x[c]; P8[row * 8 + c] = x[c]; }
-        } else {
+        for (int c = 0; c < 8; ++c) { arr[(j0 + c) * PLD + w] = x[c]; P8[w * 8 + c] = x[c]; }
+      } else if (is_diag) {
+        const int cr = w - j0;
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (j0 + c > row) arr[(j0 + c) * PLD + row] = x[c];
-        }
+        for (int r = 0; r < 8; ++r)
+          if (r == cr) {
+#pragma unroll
+            for (int c = 0; c <= r; ++c) arr[(j0 + c) * PLD + w] = d[r][c];  // L row (lower part)
+            dinv[w] = rinv[r];
+          }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c > cr) arr[(j0 + c) * PLD + w] = x[c];  // E row (strict upper part)
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) arr[(j0 + c) * PLD + w] = x[c];
       }
     }
     __syncthreads();
-    // ---- (3) rank-8 trailing update
-    if (active) {
-      const int kend = is_s ? row : (PB - 1);
-      for (int k = j0 + 8 + half; k <= kend; k += 2) {
+    // ---- phase B: rank-8 trailing update of row w (S rows: columns <= w; E rows: all remaining columns).
+    // 8 columns per trip, each dot product split into two 4-term chains: 16 independent DFMA chains
+    // of depth 4 keep the (long-latency) fp64 pipe issue-bound instead of latency-bound.
+    {
+      const int kend = is_s ? w : (PB - 1);
+      int k = j0 + 8 + half;
+      for (; k + 14 <= kend; k += 16) {
+        T lk[8][8], v0[8], v1[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { load8<T>(P8 + (k + 2 * u) * 8, lk[u]); v0[u] = arr[(k + 2 * u) * PLD + w]; v1[u] = (T)0; }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { v0[u] -= x[c] * lk[u][c]; v1[u] -= x[c + 4] * lk[u][c + 4]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) arr[(k + 2 * u) * PLD + w] = v0[u] + v1[u];
+      }
+      for (; k <= kend; k += 2) {
         T lk[8];
         load8<T>(P8 + k * 8, lk);
-        T v = arr[k * PLD + row];
+        T v0 = arr[k * PLD + w], v1 = (T)0;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v -= x[c] * lk[c];
-        arr[k * PLD + row] = v;
+        for (int c = 0; c < 4; ++c) { v0 -= x[c] * lk[c]; v1 -= x[c + 4] * lk[c + 4]; }
+        arr[k * PLD + w] = v0 + v1;
       }
     }
     __syncthreads();
   }
 
   // ---- write back L (upper zeroed) and Dinv = inv(L) (lower, col-major)
-  for (int idx = tid; idx < PB * PB; idx += 512) {
+  for (int idx = tid; idx < PB * PB; idx += 256) {
     int c = idx >> 7, i = idx & 127;  // (row i, col c)
     A[i + (int64_t)c * lda] = (i >= c) ? arr[c * PLD + i] : (T)0;
   }
-  for (int idx = tid; idx < PB * PB; idx += 512) {
+  for (int idx = tid; idx < PB * PB; idx += 256) {
     int r = idx >> 7, c = idx & 127;  // Dinv(c, r) = E(r, c)
     T v = (c > r) ? arr[c * PLD + r] : ((c == r) ? dinv[r] : (T)0);
     Dinv[c + r * PB] = v;
@@ -157,18 +195,234 @@ potrf_diag_kernel(T* __restrict__ A, int64_t lda, T* __restrict__ Dinv, double* 
   __syncthreads();
   if (tid == 0) logdet_part[blk] = red[0] + red[1] + red[2] + red[3];
 }
+
+// ------------------------------------------------------------------------------------------------
+// fp64 specialisation (v3).  Same data scheme, but (1) ONE warp factors the 8x8 diagonal block
+// (lane-redundant, in registers) and publishes it through shared memory, (2) 128 row workers
+// substitute their row, (3) the rank-8 trailing update runs on the DMMA tensor pipe:
+// 8x8 output tiles C(rows, cols k) -= X(rows, 0:8) * X(k, 0:8)', two mma.m8n8k4 per tile, warps
+// stride over the flattened tile list (E row-groups x all remaining column groups, then the lower
+// triangle of S row-groups).  ~8x fewer issue slots than per-element DFMA.
+// ------------------------------------------------------------------------------------------------
+constexpr int XLD = 9;  // micro-panel row stride (doubles): odd -> conflict-free 64-bit stores
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 1)
+potrf_diag_kernel_f64(double* __restrict__ A, int64_t lda, double* __restrict__ Dinv, double* __restrict__ logdet_part,
+                      int blk, int* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* arr = reinterpret_cast<double*>(smem_raw);  // arr[c*PLD + i]
+  double* XS = arr + PB * PLD;                        // XS[row*XLD + c]: substituted micro-panel, all 128 workers
+  double* Ld = XS + PB * XLD;                         // Ld[r*8 + c], c <= r
+  double* rinv_s = Ld + 64;                           // 8
+  double* dinv = rinv_s + 8;                          // 128
+  __shared__ double red[4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, q = lane & 3;
+
+#pragma unroll
+  for (int b0 = 0; b0 < 64; b0 += 16) {
+    double tmp[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * (b0 + u);
+      const int c = idx >> 7, i = idx & 127;
+      tmp[u] = (i >= c) ? __ldg(A + i + (int64_t)c * lda) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * (b0 + u);
+      arr[(idx >> 7) * PLD + (idx & 127)] = tmp[u];
+    }
+  }
+  __syncthreads();
+
+  for (int j0 = 0; j0 < PB; j0 += 8) {
+    const int J = j0 >> 3;
+    // ---- (1) warp 0: 8x8 diagonal Cholesky in registers (every lane computes the same values)
+    const int w = tid;  // row worker id for tid < 128
+    double a[8];
+    const bool worker = tid < PB;
+    const bool is_s = worker && (w >= j0 + 8);
+    const bool is_diag = worker && (w >= j0) && (w < j0 + 8);
+    if (worker && !is_diag) {  // prefetch own row's micro-panel entries while warp 0 works
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[c] = arr[(j0 + c) * PLD + w];
+    }
+    if (warp == 0) {
+      double d[8][8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) d[r][c] = arr[(j0 + c) * PLD + j0 + r];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        double piv = d[c][c];
+        if (!(piv > 0.0)) {
+          if (lane == 0) atomicCAS(info, 0, blk * PB + j0 + c + 1);
+          piv = 1.0;
+        }
+        const double r = dev_rsqrt_refined<double>(piv);
+        if (lane == 0) rinv_s[c] = r;
+        d[c][c] = piv * r;
+#pragma unroll
+        for (int r2 = c + 1; r2 < 8; ++r2) d[r2][c] *= r;
+#pragma unroll
+        for (int c2 = c + 1; c2 < 8; ++c2)
+#pragma unroll
+          for (int r2 = c2; r2 < 8; ++r2) d[r2][c2] -= d[r2][c] * d[c2][c];
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int c = 0; c <= r; ++c) Ld[r * 8 + c] = d[r][c];
+      }
+    }
+    __syncthreads();
+    // ---- (2) substitution by the 128 row workers
+    if (worker) {
+      double x[8];
+      if (is_diag) {
+        const int cr = w - j0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[c] = (c == cr) ? 1.0 : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        double sacc = a[c];
+#pragma unroll
+        for (int c2 = 0; c2 < c; ++c2) sacc -= x[c2] * Ld[c * 8 + c2];
+        x[c] = sacc * rinv_s[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) XS[w * XLD + c] = x[c];
+      if (is_s) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) arr[(j0 + c) * PLD + w] = x[c];
+      } else if (is_diag) {
+        const int cr = w - j0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (c <= cr) arr[(j0 + c) * PLD + w] = Ld[cr * 8 + c];  // L row (lower part of the diagonal block)
+          else arr[(j0 + c) * PLD + w] = x[c];                    // E row (strict upper part)
+        }
+        dinv[w] = rinv_s[cr];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) arr[(j0 + c) * PLD + w] = x[c];
+      }
+    }
+    __syncthreads();
+    // ---- (3) rank-8 trailing update on the DMMA pipe.  Warp wi owns row-groups wi and 15-wi (8 rows
+    // each); an E group (rows already factored) sweeps all remaining column groups, an S group only
+    // those up to its own.  Four 8x8 tiles per trip: 16 independent smem loads, then 8 DMMAs.
+    // (A round-robin deal of 4-tile jobs over the warps balanced better on paper but measured 72 us
+    // vs 52 us for this static map: the per-job bookkeeping costs more than the imbalance.)
+    {
+#pragma unroll
+      for (int sel = 0; sel < 2; ++sel) {
+        const int rg = sel ? (15 - warp) : warp;
+        const bool isE = (rg <= J);
+        const int kg_lo = J + 1, kg_hi = isE ? 15 : rg;
+        if (kg_hi < kg_lo) continue;
+        const int r0 = rg * 8;
+        const double a0 = -XS[(r0 + gq) * XLD + q], a1 = -XS[(r0 + gq) * XLD + 4 + q];
+        for (int kg = kg_lo; kg <= kg_hi; kg += 4) {
+          double b0[4], b1[4], c0[4], c1[4];
+          double* cp[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int kgu = min(kg + u, 15);
+            b0[u] = XS[(kgu * 8 + gq) * XLD + q];
+            b1[u] = XS[(kgu * 8 + gq) * XLD + 4 + q];
+            cp[u] = arr + (kgu * 8 + 2 * q) * PLD + r0 + gq;
+            c0[u] = cp[u][0];
+            c1[u] = cp[u][PLD];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dmma884(c0[u], c1[u], a0, b0[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dmma884(c0[u], c1[u], a1, b1[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int kgu = kg + u;
+            if (kgu <= kg_hi) {
+              const bool diag_tile = (!isE) && (kgu == rg);
+              if (!diag_tile || 2 * q <= gq) cp[u][0] = c0[u];  // S diagonal tile: keep only k <= row
+              if (!diag_tile || 2 * q + 1 <= gq) cp[u][PLD] = c1[u];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- write back L (upper zeroed) and Dinv = inv(L); smem reads batched 16 deep
+#pragma unroll
+  for (int b0 = 0; b0 < 64; b0 += 16) {
+    double tmp[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * (b0 + u);
+      const int c = idx >> 7, i = idx & 127;
+      tmp[u] = (i >= c) ? arr[c * PLD + i] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * (b0 + u);
+      A[(idx & 127) + (int64_t)(idx >> 7) * lda] = tmp[u];
+    }
+  }
+#pragma unroll
+  for (int b0 = 0; b0 < 64; b0 += 16) {
+    double tmp[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * (b0 + u);
+      const int r = idx >> 7, c = idx & 127;  // Dinv(c, r) = E(r, c)
+      tmp[u] = (c > r) ? arr[c * PLD + r] : ((c == r) ? dinv[r] : 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) Dinv[tid + 256 * (b0 + u)] = tmp[u];
+  }
+  double part = 0.0;
+  if (tid < PB) part = -log(dinv[tid]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (tid < PB && (tid & 31) == 0) red[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0) logdet_part[blk] = red[0] + red[1] + red[2] + red[3];
+}
 }  // namespace
 
 template <typename T>
 void launch_potrf_diag(T* Ablk, int64_t lda, T* Dinv, double* logdet_part, int blk, int* info, cudaStream_t s) {
-  const size_t smem = (size_t)(PB * PLD + 1 + PB * 8 + 64 + PB) * sizeof(T);
+  const size_t smem = (size_t)(PB * PLD + PB * 8 + PB) * sizeof(T);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(potrf_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
-  potrf_diag_kernel<T><<<1, 512, smem, s>>>(Ablk, lda, Dinv, logdet_part, blk, info);
+  potrf_diag_kernel<T><<<1, 256, smem, s>>>(Ablk, lda, Dinv, logdet_part, blk, info);
   agp_count_launch();
 }
 template void launch_potrf_diag<float>(float*, int64_t, float*, double*, int, int*, cudaStream_t);
-template void launch_potrf_diag<double>(double*, int64_t, double*, double*, int, int*, cudaStream_t);
+template <>
+void launch_potrf_diag<double>(double* Ablk, int64_t lda, double* Dinv, double* logdet_part, int blk, int* info,
+                               cudaStream_t s) {
+  const size_t smem = (size_t)(PB * PLD + PB * XLD + 64 + 8 + PB) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(potrf_diag_kernel_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  potrf_diag_kernel_f64<<<1, 256, smem, s>>>(Ablk, lda, Dinv, logdet_part, blk, info);
+  agp_count_launch();
+}

@@ -57,22 +57,35 @@ __global__ void extract_v_kernel(const T* __restrict__ A, int64_t lda, int64_t n
 
 // backward step k: every CTA b <= k recomputes alpha_k = Dinv_k' r_k (128x128 mat-vec out of L2);
 // CTA b == k stores it, CTA b < k applies r_b -= L[k-block rows, b-block cols]' alpha_k.
+// Thread (output o = tid>>1, half h = tid&1) streams 64 CONTIGUOUS elements of column o with
+// independent 16-byte loads (all in flight at once), then the two halves meet through one shuffle.
+template <typename T>
+__device__ __forceinline__ double col_dot_half(const T* __restrict__ col, const T* __restrict__ vec_s, int h) {
+  double acc0 = 0.0, acc1 = 0.0;
+  const T* c = col + h * (TB / 2);
+  const T* v = vec_s + h * (TB / 2);
+#pragma unroll 16
+  for (int j = 0; j < TB / 2; j += 2) {
+    acc0 = fma((double)c[j], (double)v[j], acc0);
+    acc1 = fma((double)c[j + 1], (double)v[j + 1], acc1);
+  }
+  return acc0 + acc1;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_step_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ Dinv,
                                                        int k, T* __restrict__ r) {
   __shared__ T rk[TB];
   __shared__ T ak[TB];
   const int b = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, o = tid >> 1, h = tid & 1;
   if (tid < TB) rk[tid] = r[(int64_t)k * TB + tid];
   __syncthreads();
   const T* Dk = Dinv + (int64_t)k * TB * TB;
-  // alpha_k[i] = sum_j Dinv(j, i) r_k[j]  (column i of Dinv, contiguous in j)
-  for (int i = warp; i < TB; i += 8) {
-    double acc = 0.0;
-    for (int j = lane; j < TB; j += 32) acc += (double)Dk[j + i * TB] * (double)rk[j];
-    acc = warp_sum(acc);
-    if (lane == 0) ak[i] = (T)acc;
+  {  // alpha_k[o] = sum_j Dinv(j, o) r_k[j]  (column o of Dinv, contiguous in j; zero above the diagonal)
+    double acc = col_dot_half<T>(Dk + o * TB, rk, h);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (h == 0) ak[o] = (T)acc;
   }
   __syncthreads();
   if (b == k) {
@@ -80,12 +93,109 @@ __global__ void __launch_bounds__(256) bwd_step_kernel(const T* __restrict__ A, 
     return;
   }
   const T* Lkb = A + (int64_t)k * TB + (int64_t)b * TB * lda;  // tile (k, b)
-  for (int c = warp; c < TB; c += 8) {
-    double acc = 0.0;
-    for (int i = lane; i < TB; i += 32) acc += (double)Lkb[i + (int64_t)c * lda] * (double)ak[i];
-    acc = warp_sum(acc);
-    if (lane == 0) r[(int64_t)b * TB + c] -= (T)acc;
+  {
+    double acc = col_dot_half<T>(Lkb + (int64_t)o * lda, ak, h);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (h == 0) r[(int64_t)b * TB + o] -= (T)acc;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent backward substitution  L' alpha = v  in ONE launch (replaces nblk dependent launches).
+// CTA "b" (claimed through an atomic ticket so that producers always start before consumers) owns
+// block b of the vector: it streams the tiles L(k, b), k = nblk-1 .. b+1, applying
+// r_b -= L(k,b)' alpha_k as soon as CTA k publishes alpha_k (release/acquire flag in global memory),
+// then computes alpha_b = inv(L_bb)' r_b from a copy of Dinv_b prefetched into shared memory at
+// kernel start, and publishes it.  The tile for step k is loaded into registers BEFORE waiting on
+// the flag, so the HBM/L2 latency of the factor is off the critical chain.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <typename T> struct Vec16;
+template <> struct Vec16<double> { using type = double2; static constexpr int N = 2; };
+template <> struct Vec16<float> { using type = float4; static constexpr int N = 4; };
+
+template <typename T>
+__device__ __forceinline__ void load_half_col(const T* __restrict__ col, T (&t)[TB / 2]) {
+  using V = typename Vec16<T>::type;
+  constexpr int VN = Vec16<T>::N;
+  const V* p = reinterpret_cast<const V*>(col);
+#pragma unroll
+  for (int i = 0; i < TB / 2 / VN; ++i) {
+    V v = __ldcg(p + i);
+    const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) t[i * VN + j] = e[j];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 1) bwd_solve_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ Dinv,
+                                                            int nblk, T* r, int* flags, int* ticket) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sD = reinterpret_cast<T*>(smem_raw);  // Dinv_b, TB x TB col-major
+  __shared__ T rb[TB];
+  __shared__ T ak[TB];
+  __shared__ int sb;
+  const int tid = threadIdx.x, o = tid >> 1, h = tid & 1;
+  if (tid == 0) sb = nblk - 1 - atomicAdd(ticket, 1);
+  __syncthreads();
+  const int b = sb;
+  {  // prefetch Dinv_b -> smem (cp.async, 16 B per request)
+    const T* Dk = Dinv + (int64_t)b * TB * TB;
+    constexpr int VN = Vec16<T>::N;
+    for (int q = tid; q < TB * TB / VN; q += 256) {
+      unsigned sa = (unsigned)__cvta_generic_to_shared(sD + q * VN);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(Dk + q * VN));
+    }
+    asm volatile("cp.async.commit_group;" ::);
+  }
+  if (tid < TB) rb[tid] = __ldcg(r + (int64_t)b * TB + tid);
+  for (int k = nblk - 1; k > b; --k) {
+    T tile[TB / 2];
+    load_half_col<T>(A + (int64_t)k * TB + ((int64_t)b * TB + o) * lda + h * (TB / 2), tile);
+    if (tid == 0) {
+      while (ld_acquire(flags + k) == 0) { }
+    }
+    __syncthreads();
+    if (tid < TB) ak[tid] = __ldcg(r + (int64_t)k * TB + tid);
+    __syncthreads();
+    double a0 = 0.0, a1 = 0.0;
+    const T* av = ak + h * (TB / 2);
+#pragma unroll
+    for (int j = 0; j < TB / 2; j += 2) {
+      a0 = fma((double)tile[j], (double)av[j], a0);
+      a1 = fma((double)tile[j + 1], (double)av[j + 1], a1);
+    }
+    double acc = a0 + a1;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (h == 0) rb[o] -= (T)acc;
+    // rb[o] is private to this thread pair; ak is rewritten only after the next barrier pair
+  }
+  asm volatile("cp.async.wait_group 0;" ::);
+  __syncthreads();
+  {  // alpha_b[o] = sum_j Dinv(j, o) r_b[j]
+    double a0 = 0.0, a1 = 0.0;
+    const T* col = sD + o * TB + h * (TB / 2);
+    const T* rv = rb + h * (TB / 2);
+#pragma unroll 16
+    for (int j = 0; j < TB / 2; j += 2) {
+      a0 = fma((double)col[j], (double)rv[j], a0);
+      a1 = fma((double)col[j + 1], (double)rv[j + 1], a1);
+    }
+    double acc = a0 + a1;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (h == 0) r[(int64_t)b * TB + o] = (T)acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) st_release(flags + b, 1);
 }
 
 // forward step k: v_k = Dinv_k r_k ; r_b -= L[b-block rows, k-block cols] v_k for b > k.
@@ -277,6 +387,62 @@ __global__ void vfe_prep_kernel(const T* __restrict__ y, int64_t n, int mean_kin
   a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
   if ((threadIdx.x & 31) == 0) { atomicAdd(scal + 0, a0); atomicAdd(scal + 1, a1); atomicAdd(scal + 2, a2); }
 }
+
+template <typename T>
+__global__ void gemv_n_acc_kernel(const T* __restrict__ A, int64_t lda, int64_t m, int64_t n, const T* __restrict__ x,
+                                  T* __restrict__ y) {
+  // block handles 256 rows; grid.y splits the n range; partial sums accumulate with atomics (fp order
+  // varies in the last bits only; the VFE scalars tolerate it and are documented as such)
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t per = (n + gridDim.y - 1) / gridDim.y;
+  const int64_t n0 = blockIdx.y * per, n1 = (n0 + per < n) ? n0 + per : n;
+  if (i >= m) return;
+  double acc = 0.0;
+  for (int64_t j = n0; j < n1; ++j) acc = fma((double)A[i + j * lda], (double)x[j], acc);
+  atomicAdd(y + i, (T)acc);
+}
+
+template <typename T>
+__global__ void colsumsq_acc_kernel(const T* __restrict__ V, int64_t ldv, int64_t n, int64_t m, T sign, T* __restrict__ out) {
+  const int64_t j = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= m) return;
+  double acc = 0.0;
+  const T* col = V + j * ldv;
+  for (int64_t i = lane; i < n; i += 32) { double v = (double)col[i]; acc += v * v; }
+  acc = warp_sum(acc);
+  if (lane == 0) out[j] += sign * (T)acc;
+}
+
+template <typename T>
+__global__ void zero_diag_upper_kernel(T* __restrict__ A, int64_t lda) {
+  const int64_t b = blockIdx.x;
+  T* blk = A + b * TB + b * TB * lda;
+  for (int idx = threadIdx.x; idx < TB * TB; idx += blockDim.x) {
+    int c = idx >> 7, i = idx & 127;
+    if (i < c) blk[i + (int64_t)c * lda] = (T)0;
+  }
+}
+
+template <typename T>
+__global__ void export_upper_map_kernel(const T* __restrict__ A, int64_t lda, int64_t n, const int64_t* __restrict__ map,
+                                        T* __restrict__ U, int64_t ldo) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t j = blockIdx.y;
+  if (i >= n || j >= n) return;
+  T v = 0;
+  if (i <= j) v = A[map[j] + map[i] * lda];
+  U[i + j * ldo] = v;
+}
+
+template <typename T>
+__global__ void sub_mean_kernel(const T* __restrict__ y, int64_t n, int mean_kind, T mean_c, const T* __restrict__ mean_v,
+                                T* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T m = (mean_kind == 0) ? (T)0 : (mean_kind == 1 ? mean_c : mean_v[i]);
+  out[i] = y[i] - m;
+}
 }  // namespace
 
 template <typename T>
@@ -294,6 +460,18 @@ void launch_extract_v(const T* A, int64_t lda, int64_t n_pad, int S, T* r, doubl
 template <typename T>
 void launch_bwd_step(const T* A, int64_t lda, const T* Dinv, int k, T* r, cudaStream_t s) {
   bwd_step_kernel<T><<<k + 1, 256, 0, s>>>(A, lda, Dinv, k, r);
+  agp_count_launch();
+}
+template <typename T>
+void launch_bwd_solve(const T* A, int64_t lda, const T* Dinv, int nblk, T* r, int* flags_and_ticket, cudaStream_t s) {
+  const size_t smem = (size_t)TB * TB * sizeof(T);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(bwd_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  cudaMemsetAsync(flags_and_ticket, 0, (size_t)(nblk + 1) * sizeof(int), s);
+  bwd_solve_kernel<T><<<nblk, 256, smem, s>>>(A, lda, Dinv, nblk, r, flags_and_ticket, flags_and_ticket + nblk);
   agp_count_launch();
 }
 template <typename T>
@@ -386,7 +564,55 @@ void launch_vfe_prep(const T* y, int64_t n, int mean_kind, double mean_c, const 
   agp_count_launch();
 }
 
+template <typename T>
+void launch_gemv_n_acc(const T* A, int64_t lda, int64_t m, int64_t n, const T* x, T* y, cudaStream_t s) {
+  if (m <= 0 || n <= 0) return;
+  int ysplit = (int)((n + 2047) / 2048);
+  if (ysplit > 64) ysplit = 64;
+  dim3 grid((unsigned)((m + 255) / 256), (unsigned)ysplit);
+  gemv_n_acc_kernel<T><<<grid, 256, 0, s>>>(A, lda, m, n, x, y);
+  agp_count_launch();
+}
+template <typename T>
+void launch_colsumsq_acc(const T* V, int64_t ldv, int64_t n, int64_t m, double sign, T* out, cudaStream_t s) {
+  if (m <= 0) return;
+  colsumsq_acc_kernel<T><<<(unsigned)((m + 7) / 8), 256, 0, s>>>(V, ldv, n, m, (T)sign, out);
+  agp_count_launch();
+}
+template <typename T>
+void launch_zero_diag_upper(T* A, int64_t lda, int64_t n_pad, cudaStream_t s) {
+  if (n_pad <= 0) return;
+  zero_diag_upper_kernel<T><<<(unsigned)(n_pad / TB), 256, 0, s>>>(A, lda);
+  agp_count_launch();
+}
+template <typename T>
+void launch_export_upper_map(const T* A, int64_t lda, int64_t n, const int64_t* map, T* U, int64_t ldo, cudaStream_t s) {
+  if (n <= 0) return;
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)n);
+  export_upper_map_kernel<T><<<grid, 256, 0, s>>>(A, lda, n, map, U, ldo);
+  agp_count_launch();
+}
+
+template <typename T>
+void launch_sub_mean(const T* y, int64_t n, int mean_kind, double mean_c, const T* mean_v, T* out, cudaStream_t s) {
+  if (n <= 0) return;
+  sub_mean_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(y, n, mean_kind, (T)mean_c, mean_v, out);
+  agp_count_launch();
+}
+
 // explicit instantiations
+template void launch_sub_mean<float>(const float*, int64_t, int, double, const float*, float*, cudaStream_t);
+template void launch_sub_mean<double>(const double*, int64_t, int, double, const double*, double*, cudaStream_t);
+template void launch_gemv_n_acc<float>(const float*, int64_t, int64_t, int64_t, const float*, float*, cudaStream_t);
+template void launch_colsumsq_acc<float>(const float*, int64_t, int64_t, int64_t, double, float*, cudaStream_t);
+template void launch_zero_diag_upper<float>(float*, int64_t, int64_t, cudaStream_t);
+template void launch_export_upper_map<float>(const float*, int64_t, int64_t, const int64_t*, float*, int64_t, cudaStream_t);
+template void launch_gemv_n_acc<double>(const double*, int64_t, int64_t, int64_t, const double*, double*, cudaStream_t);
+template void launch_colsumsq_acc<double>(const double*, int64_t, int64_t, int64_t, double, double*, cudaStream_t);
+template void launch_zero_diag_upper<double>(double*, int64_t, int64_t, cudaStream_t);
+template void launch_export_upper_map<double>(const double*, int64_t, int64_t, const int64_t*, double*, int64_t, cudaStream_t);
+template void launch_bwd_solve<float>(const float*, int64_t, const float*, int, float*, int*, cudaStream_t);
+template void launch_bwd_solve<double>(const double*, int64_t, const double*, int, double*, int*, cudaStream_t);
 template void launch_border_init<float>(float*, int64_t, int64_t, int64_t, const float*, int64_t, int, int, double, const float*, cudaStream_t);
 template void launch_extract_v<float>(const float*, int64_t, int64_t, int, float*, double*, cudaStream_t);
 template void launch_bwd_step<float>(const float*, int64_t, const float*, int, float*, cudaStream_t);

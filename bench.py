@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the exact-GP hot path (BASELINE.json metric):
+ms to logpdf(fx,y) + posterior(fx,y) at N x D fp64, with the achieved fraction of the N^3/3 Cholesky
+roofline, next to the reference's CPU LAPACK path timed on the same box.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C4|...] [--impl ours|reference]
+
+One "step" = one fused fit (ONE Gram + ONE Cholesky -> logpdf, alpha, posterior handle) of the named
+workload through the C ABI of libagp.so.  `value` is measured with the inputs resident in HBM
+(device-pointer mode of the ABI); `e2e` is the same call with pinned HOST buffers, H2D/D2H inside the
+timed region.  Device times come from CUDA events recorded by the library on its launching stream.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {  # BASELINE.json configs
+    "C2": dict(N=4096, D=8, dtype="f64", kernel="SqExponential", s2=0.1),
+    "C4": dict(N=65536, D=64, dtype="f64", kernel="SqExponential", s2=0.1),
+    "C4h": dict(N=32768, D=64, dtype="f64", kernel="SqExponential", s2=0.1),
+}
+
+
+def make_inputs(wl):
+    from oracle import agp_ref as ref  # synthetic-input generator only (shared with the parity tests)
+    cid = "C4" if wl.startswith("C4") else wl
+    cfg = ref.make_config(cid, n=WORKLOADS[wl]["N"])
+    return cfg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev, self.rows, self.p = dev, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def trailing_flops(N):
+    """algorithmic flops of the trailing SYRK launches of one factorisation: step k applies a symmetric
+    rank-128 update to the m x m trailing matrix (lower part): 2*128*m(m+1)/2, m = n_pad - 128(k+1)."""
+    n_pad = (N + 127) // 128 * 128
+    tot = 0.0
+    for k in range(n_pad // 128):
+        m = n_pad - 128 * (k + 1)
+        tot += 2.0 * 128 * m * (m + 1) / 2
+    return tot
+
+
+def cpu_reference_step(cfg, faithful=True):
+    """The reference's own CPU algorithm (oracle port): logpdf then posterior -- TWO Gram builds and TWO
+    LAPACK potrf's as /root/reference/src/finite_gp_projection.jl:307-308 + src/exact_gpr_posterior.jl:30-31 do."""
+    from oracle import agp_ref as ref
+    old = ref.DEFAULT_METHOD
+    ref.DEFAULT_METHOD = "gemm"  # Distances.jl pairwise formulation = what the reference executes on CPU
+    try:
+        lp = ref.logpdf(cfg["k"], cfg["mean"], cfg["noise"], cfg["X"], cfg["y"])
+        post = ref.posterior(cfg["k"], cfg["mean"], cfg["noise"], cfg["X"], cfg["y"])
+    finally:
+        ref.DEFAULT_METHOD = old
+    return lp, post["alpha"]
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [os.cpu_count()])
+    except Exception:
+        return os.cpu_count()
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = make_inputs(wl)
+    N = WORKLOADS[wl]["N"]
+    sample = "full %s workload (N=%d), logpdf + posterior = 2 Gram + 2 potrf, per step" % (wl, N)
+    if N > 16384:  # bounded sample: time N=16384 and scale by (N/16384)^3 (labelled)
+        cfg = make_inputs("C4")
+        sub = 16384
+        for key in ("X", "y"):
+            cfg[key] = cfg[key][:sub]
+        scale = (N / sub) ** 3
+        sample = "N=%d sub-sample of %s scaled by (N/%d)^3 = %.1f (extrapolated)" % (sub, wl, sub, scale)
+    else:
+        scale = 1.0
+    for _ in range(args.warmup):
+        cpu_reference_step(cfg)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(cfg)
+    ms = (time.perf_counter() - t0) * 1e3 / args.steps * scale
+    cores = blas_threads()
+    line = {"impl": "reference", "metric": "ms to logpdf(fx,y)+posterior(fx,y)", "value": ms, "unit": "ms",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: N=%d D=%d %s fp64" % (wl, N, WORKLOADS[wl]["D"], WORKLOADS[wl]["kernel"])},
+            "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def measure_dgemm_peak(torch, dev):
+    """fp64 roofline denominator: cuBLAS DGEMM 8192^3 on this box, best of 5 (CUDA events)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def run_ours(args, wl):
+    import ctypes as C
+    import torch
+    import agp_b200 as ag
+    from agp_b200 import _cabi as cabi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 or args.gpus > 1:
+        if rank == 0:
+            print(json.dumps({"metric": "ms to logpdf(fx,y)+posterior(fx,y)", "n_gpus": args.gpus,
+                              "unavailable": "multi-GPU block-cyclic Cholesky not built yet in this round"}))
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cfg = make_inputs(wl)
+    W = WORKLOADS[wl]
+    N, D = W["N"], W["D"]
+    eng = ag.engine()
+    L = eng.L
+    X = np.ascontiguousarray(cfg["X"], dtype=np.float64)  # [N, D] C-order == D x N column-major (ColVecs)
+    y = np.ascontiguousarray(cfg["y"], dtype=np.float64)
+    ks = cabi.agp_kernel()
+    ks.family, ks.transform, ks.variance, ks.scale = 0, 1, 1.0, float(cfg["k"].scale)
+    ms_ = cabi.agp_mean()
+    ns = cabi.agp_noise()
+    ns.kind, ns.s = 0, W["s2"]
+
+    # pinned host buffers (e2e) and device-resident copies (value)
+    Xh = torch.from_numpy(X).pin_memory()
+    yh = torch.from_numpy(y).pin_memory()
+    alpha_h = torch.empty(N, dtype=torch.float64).pin_memory()
+    Xd, yd = Xh.to(dev), yh.to(dev)
+    alpha_d = torch.empty(N, dtype=torch.float64, device=dev)
+    lp = np.zeros(1)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(device_resident):
+        post = C.c_void_p()
+        eng.set_memspace(cabi.AGP_MEM_DEVICE if device_resident else cabi.AGP_MEM_HOST)
+        xp = Xd.data_ptr() if device_resident else Xh.data_ptr()
+        yp = yd.data_ptr() if device_resident else yh.data_ptr()
+        ap = alpha_d.data_ptr() if device_resident else alpha_h.data_ptr()
+        rc = L.agp_fit(eng.h, cabi.AGP_F64, C.byref(ks), C.byref(ms_), C.byref(ns), cabi.AGP_POINT_MAJOR,
+                       C.c_void_p(xp), N, D, C.c_void_p(yp), 1, cabi.ptr(lp), C.c_void_p(ap), C.byref(post))
+        eng.check(rc)
+        t = eng.timings()
+        L.agp_post_free(post)
+        return t
+
+    def timed(device_resident, steps, warmup):
+        for _ in range(warmup):
+            step(device_resident)
+        tot = {}
+        torch.cuda.synchronize()
+        launches0 = eng.launch_count()
+        wall = 0.0
+        for _ in range(steps):
+            flush.zero_()  # L2 flush between timed iterations (outside the event-timed region)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            t = step(device_resident)
+            torch.cuda.synchronize()
+            wall += time.perf_counter() - t0
+            for k_, v in t.items():
+                tot[k_] = tot.get(k_, 0.0) + v
+        launches = eng.launch_count() - launches0
+        return {k_: v / steps for k_, v in tot.items()}, wall * 1e3 / steps, launches
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_dev, wall_dev, launches = timed(True, args.steps, args.warmup)
+    t_e2e, wall_e2e, _ = timed(False, args.steps, args.warmup)
+    clocks = sampler.stop()
+
+    # parity spot check against the oracle on the same inputs (outside any timed region)
+    parity = None
+    if N <= 8192:
+        from oracle import agp_ref as ref
+        lp_ref = ref.logpdf(cfg["k"], cfg["mean"], cfg["noise"], cfg["X"], cfg["y"])
+        parity = {"logpdf": float(lp[0]), "oracle_logpdf": float(lp_ref),
+                  "rel_err": float(abs(lp[0] - lp_ref) / abs(lp_ref)), "tol": 1e-8}
+
+    dgemm = measure_dgemm_peak(torch, dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf = trailing_flops(N)
+    trailing_ms = t_dev.get("trailing", 0.0)
+    achieved = tf / (trailing_ms * 1e-3) / 1e12 if trailing_ms > 0 else None
+    chol_tf = (N ** 3 / 3.0) / (t_dev["cholesky"] * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel<false,false> (trailing SYRK, lower tiles)",
+                "achieved": achieved, "peak": dgemm, "unit": "TFLOP/s", "frac": (achieved / dgemm) if achieved else None,
+                "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (fp64 has no entry in MEASURED_PEAKS.json); "
+                               "nominal B200 fp64 tensor = 40 TFLOP/s",
+                "frac_of_bf16_measured": (achieved / peaks["bf16_tflops"]) if (achieved and "bf16_tflops" in peaks) else None,
+                "launches_per_step": (N + 127) // 128 - 1, "alg_flops_per_step": tf,
+                "kernel_ms_per_step": trailing_ms, "traffic": None,
+                "cholesky_third_n3_tflops": chol_tf, "cholesky_frac_of_dgemm": chol_tf / dgemm}
+
+    # CPU baseline (oracle port of the reference's LAPACK path) on this box's host cores, bounded sample
+    cfg_cpu, scale, sample = cfg, 1.0, "full %s workload (N=%d), logpdf+posterior = 2 Gram + 2 dpotrf, best of 3" % (wl, N)
+    if N > 8192:
+        sub = 8192
+        cfg_cpu = dict(cfg)
+        cfg_cpu["X"], cfg_cpu["y"] = cfg["X"][:sub], cfg["y"][:sub]
+        scale = (N / sub) ** 3
+        sample = "N=%d sub-sample scaled by (N/%d)^3=%.0f (extrapolated)" % (sub, sub, scale)
+    best = 1e18
+    for _ in range(3):
+        t0 = time.perf_counter()
+        cpu_reference_step(cfg_cpu)
+        best = min(best, time.perf_counter() - t0)
+    cpu = {"value": best * 1e3 * scale, "unit": "ms", "cores": blas_threads(), "kind": "port", "sample": sample}
+
+    line = {"metric": "ms to logpdf(fx,y)+posterior(fx,y)", "value": t_dev["total"], "unit": "ms", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev["total"], "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: N=%d D=%d %s fp64, sigma2=%g, fused fit (1 Gram + 1 Cholesky)" % (wl, N, D, W["kernel"], W["s2"]),
+                       "l2": "256 MiB flush buffer written between timed iterations", "timer": "CUDA events on the library stream",
+                       "tile": 128},
+            "phases_ms": t_dev, "wall_ms_per_step": wall_dev,
+            "e2e": {"value": t_e2e["total"], "unit": "ms", "h2d_bytes_per_step": int(X.nbytes + y.nbytes),
+                    "d2h_bytes_per_step": int(alpha_h.numel() * 8 + 8 + 4 + 8), "wall_ms_per_step": wall_e2e,
+                    "phases_ms": t_e2e},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "parity": parity}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = args.workload or ("C2" if args.gpus == 1 else "C4")
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

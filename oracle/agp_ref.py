@@ -130,9 +130,15 @@ def _kappa(family: int, d2: np.ndarray) -> np.ndarray:
     raise ValueError(family)
 
 
+# "direct" (difference form, what the CUDA kernel computes) or "gemm" (the Distances.jl formulation the
+# reference's KernelFunctions actually executes; used for the timed CPU baseline in bench.py)
+DEFAULT_METHOD = "direct"
+
+
 def kernelmatrix(k: KernelSpec, X: np.ndarray, Z: Optional[np.ndarray] = None,
-                 method: str = "direct") -> np.ndarray:
+                 method: Optional[str] = None) -> np.ndarray:
     """kernelmatrix(k, x[, z]).  src/base_gp.jl:70 (one-arg), :74 (two-arg)."""
+    method = method or DEFAULT_METHOD
     dtype = X.dtype
     Xt = k.apply_transform(X)
     Zt = Xt if Z is None else k.apply_transform(np.asarray(Z, dtype=dtype))

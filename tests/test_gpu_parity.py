@@ -242,3 +242,95 @@ def test_config_c3_reduced(ag):
     pr = ref.posterior(k64, cfg["mean"], cfg["noise"], X64, cfg["y"].astype(np.float64))
     mu_r, v_r = ref.post_mean_and_var(pr, Xs.astype(np.float64), noise_s=cfg["noise"])
     assert np.allclose(mu, mu_r, rtol=2e-3, atol=2e-3) and np.allclose(v, v_r, rtol=2e-3, atol=2e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# sequential conditioning (update_chol) and VFE
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n1,n2", [(40, 30), (128, 128), (300, 77)])
+def test_sequential_conditioning_equals_batch(ag, dtype, n1, n2):
+    # test/exact_gpr_posterior.jl:29-43: C.U, alpha, x, delta of the sequential posterior == batch, atol 1e-5
+    d = 3
+    ks, X, y = problem(n1 + n2, d, ref.SE, dtype, seed=31)
+    f = ag.GP(0.1, mk_kernel(ag, ks))
+    nv2 = (0.05 + 0.1 * np.random.default_rng(3).random(n2)).astype(dtype)
+    p1 = ag.posterior(f(ag.RowVecs(X[:n1]), 0.1), y[:n1])
+    p2 = ag.posterior(p1(ag.RowVecs(X[n1:]), nv2), y[n1:])
+    noise_all = ref.NoiseSpec(1, v=np.concatenate([np.full(n1, 0.1), nv2]).astype(dtype))
+    pb = ref.posterior(ks, ref.MeanSpec(1, 0.1), noise_all, X, y)
+    atol = 1e-5 if dtype == np.float64 else 5e-3
+    assert p2.data.alpha.shape == (n1 + n2,)
+    assert np.allclose(p2.data.alpha, pb["alpha"], atol=atol * max(1.0, np.abs(pb["alpha"]).max()))
+    assert np.allclose(p2.data.delta, pb["delta"], atol=1e-6)
+    assert np.allclose(p2.data.C.U, pb["U"], atol=atol)
+    Xs = np.random.default_rng(5).random((50, d)).astype(dtype)
+    m, v = ag.mean_and_var(p2, ag.RowVecs(Xs))
+    m_r, v_r = ref.post_mean_and_var(pb, Xs)
+    tol = dict(rtol=1e-6, atol=1e-7) if dtype == np.float64 else dict(rtol=5e-3, atol=5e-3)
+    assert np.allclose(m, m_r, **tol) and np.allclose(v, v_r, **tol)
+    # a third batch on top of the second
+    ks3, X3, y3 = problem(25, d, ref.SE, dtype, seed=77)
+    p3 = ag.posterior(p2(ag.RowVecs(X3), 0.2), y3)
+    Xa, ya = np.concatenate([X, X3]), np.concatenate([y, y3])
+    na = ref.NoiseSpec(1, v=np.concatenate([noise_all.v, np.full(25, 0.2)]).astype(dtype))
+    pa = ref.posterior(ks, ref.MeanSpec(1, 0.1), na, Xa, ya)
+    assert np.allclose(p3.data.alpha, pa["alpha"], atol=atol * max(1.0, np.abs(pa["alpha"]).max()))
+    assert np.isclose(p3.data.C.logdet(), ref.logdet_chol(pa["U"]), rtol=1e-8 if dtype == np.float64 else 1e-3)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,m,d,fam", [(200, 20, 2, ref.SE), (1000, 130, 5, ref.MATERN52), (700, 256, 3, ref.SE)])
+def test_vfe_elbo_and_posterior(ag, dtype, n, m, d, fam):
+    ks, X, y = problem(n, d, fam, dtype, seed=41)
+    Z = X[np.random.default_rng(1).permutation(n)[:m]].copy()
+    jit = 1e-6 if dtype == np.float64 else 1e-3
+    noise, jn = ref.NoiseSpec(0, 0.1), ref.NoiseSpec(0, jit)
+    f = ag.GP(0.2, mk_kernel(ag, ks))
+    fx = f(ag.RowVecs(X), 0.1)
+    vfe = ag.VFE(f(ag.RowVecs(Z), jit))
+    el, dt = ag.approx_log_evidence(vfe, fx, y, return_dtc=True)
+    X64, y64, Z64 = X.astype(np.float64), y.astype(np.float64), Z.astype(np.float64)
+    ks64 = ref.KernelSpec(ks.family, ks.variance, ks.transform, ks.scale, None, ks.linear_c)
+    el_r = ref.elbo(ks64, ref.MeanSpec(1, 0.2), noise, X64, y64, Z64, jn)
+    dt_r = ref.dtc(ks64, ref.MeanSpec(1, 0.2), noise, X64, y64, Z64, jn)
+    rt = 1e-8 if dtype == np.float64 else 2e-3
+    assert el.dtype == dtype
+    assert abs(el - el_r) <= rt * abs(el_r), (el, el_r)
+    assert abs(dt - dt_r) <= rt * abs(dt_r), (dt, dt_r)
+    assert ag.elbo(vfe, fx, y) <= ag.logpdf(fx, y) + 1e-6 * abs(el_r)  # elbo <= logpdf (TestUtils.jl:214)
+    # approximate posterior predictions vs the oracle (src/sparse_approximations.jl:212-217)
+    vp = ag.posterior(vfe, fx, y)
+    Xs = np.random.default_rng(2).random((60, d)).astype(dtype)
+    mu, v = ag.mean_and_var(vp, ag.RowVecs(Xs))
+    vr = ref.vfe_posterior(ks64, ref.MeanSpec(1, 0.2), noise, X64, y64, Z64, jn)
+    mu_r, v_r = ref.vfe_mean_and_var(vr, Xs.astype(np.float64))
+    tol = dict(rtol=1e-6, atol=1e-7) if dtype == np.float64 else dict(rtol=2e-2, atol=2e-2)
+    assert np.allclose(mu, mu_r, **tol) and np.allclose(v, v_r, **tol)
+    mu2, v2 = ag.mean_and_var(vp(ag.RowVecs(Xs), 0.1))
+    assert np.allclose(v2, v + 0.1, atol=1e-6)
+
+
+def test_vfe_with_z_equal_x_reproduces_exact(ag):
+    # test/sparse_approximations.jl:24-25,94 ; src/util/TestUtils.jl:213-217 (rtol = atol = 1e-5)
+    n, d = 150, 2
+    ks, X, y = problem(n, d, ref.SE, np.float64, seed=43)
+    f = ag.GP(mk_kernel(ag, ks))
+    fx = f(ag.RowVecs(X), 0.1)
+    vfe = ag.VFE(f(ag.RowVecs(X), 1e-10))
+    assert np.isclose(ag.elbo(vfe, fx, y), ag.logpdf(fx, y), rtol=1e-5, atol=1e-5)
+    vp, ep = ag.posterior(vfe, fx, y), ag.posterior(fx, y)
+    Xs = np.random.default_rng(4).random((20, d))
+    m1, v1 = ag.mean_and_var(vp, ag.RowVecs(Xs))
+    m2, v2 = ag.mean_and_var(ep, ag.RowVecs(Xs))
+    assert np.allclose(m1, m2, atol=1e-5) and np.allclose(v1, v2, atol=1e-5)
+    with pytest.raises(ag.DimensionMismatch):
+        ag.elbo(vfe, fx, y[:-1])
+
+
+def test_vfe_golden_c5(ag):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "c5_n3000_f64.npz"))
+    X, y, Z = g["X"], g["y"], g["Z"]
+    f = ag.GP(ag.with_lengthscale(ag.SqExponentialKernel(), np.sqrt(16) * 0.5))
+    el, dt = ag.approx_log_evidence(ag.VFE(f(ag.RowVecs(Z), 1e-6)), f(ag.RowVecs(X), 0.1), y, return_dtc=True)
+    assert abs(el - g["elbo"]) <= 1e-8 * abs(g["elbo"]) and abs(dt - g["dtc"]) <= 1e-8 * abs(g["dtc"])
