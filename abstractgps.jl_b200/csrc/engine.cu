@@ -16,6 +16,8 @@
 #include <utility>
 #include <vector>
 
+#include <nccl.h>
+
 #include "agp.h"
 #include "kernels.h"
 
@@ -36,7 +38,7 @@ struct agp_ctx {
   int prof_used = 0;
   int profile = 1;
   int rank = 0, nranks = 1, grid_p = 1, grid_q = 1;
-  void* nccl = nullptr;
+  ncclComm_t nccl = nullptr;
 };
 
 struct agp_post {
@@ -966,6 +968,189 @@ int vfe_mean_var_impl(agp_vfe_post* p, int layout, const void* Xs, int64_t Ms, v
   return AGP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU fit: one process per GPU, block-column-cyclic tiles on a 1 x Q process grid, NCCL panel
+// broadcast over NVLink/NVSwitch, look-ahead so the broadcast of panel k+1 overlaps the bulk of the
+// trailing update of panel k.  Column block j (128 columns, all rows + the border rows) lives on
+// rank j mod Q as local block j div Q.  Every rank generates only its own Gram columns from the
+// replicated points.  (grid_p > 1 is declared in the ABI but not built: on NVSwitch the panel
+// broadcast is ~5 % of the factorisation at C4, so the 2-D row/column split buys nothing yet.)
+// ------------------------------------------------------------------------------------------------
+#define CKN(call)                                                                         \
+  do {                                                                                    \
+    ncclResult_t _r = (call);                                                             \
+    if (_r != ncclSuccess) {                                                              \
+      char _b[512];                                                                       \
+      snprintf(_b, sizeof(_b), "%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(_r)); \
+      ctx->err = _b;                                                                      \
+      return AGP_ERR_NCCL;                                                                \
+    }                                                                                     \
+  } while (0)
+
+template <typename T> struct NcclType;
+template <> struct NcclType<float> { static constexpr ncclDataType_t v = ncclFloat; };
+template <> struct NcclType<double> { static constexpr ncclDataType_t v = ncclDouble; };
+
+template <typename T>
+int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_noise* noise, int layout,
+                  const void* X, int64_t N, int D, const void* Y, int S, void* logpdf_out, void* alpha_out) {
+  int rc = check_kernel(ctx, k, D);
+  if (rc) return rc;
+  if (N <= 0) { ctx->err = "N must be positive"; return AGP_ERR_DIM_MISMATCH; }
+  if (S < 1 || S > TILE || !Y) { ctx->err = "distributed fit needs 1..128 right-hand sides"; return AGP_ERR_UNSUPPORTED; }
+  static const agp_mean zero_mean{0, 0.0, nullptr};
+  static const agp_noise default_noise{0, 1e-18, nullptr};
+  if (!mean) mean = &zero_mean;
+  if (!noise) noise = &default_noise;
+  cudaStream_t s = ctx->stream, s2 = ctx->stream2;
+  CK(cudaSetDevice(ctx->device));
+  Scratch sc(ctx);
+  const int R = ctx->nranks, me = ctx->rank;
+  const int64_t n_pad = round_up(N, TILE), lda = n_pad + TILE;
+  const int nt = (int)(n_pad / TILE);
+  const int nloc = (nt - me + R - 1) / R;  // local column blocks: global j = lj * R + me
+  prof_begin(ctx);
+  CK(cudaEventRecord(ctx->ev[0], s));
+  T *ard_d = nullptr, *mean_d = nullptr, *noise_d = nullptr, *Yd = nullptr, *Xt = nullptr;
+  if (k->transform == AGP_T_ARD) { rc = upload<T>(ctx, sc, k->ard, D, true, &ard_d); if (rc) return rc; }
+  if (mean->kind == 2) { rc = upload<T>(ctx, sc, mean->v, N, true, &mean_d); if (rc) return rc; }
+  if (noise->kind == 1) { rc = upload<T>(ctx, sc, noise->v, N, true, &noise_d); if (rc) return rc; }
+  rc = upload<T>(ctx, sc, Y, (size_t)N * S, false, &Yd); if (rc) return rc;
+  rc = prep_points<T>(ctx, sc, k, ard_d, layout, X, N, n_pad, D, &Xt, false); if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev[1], s));
+  void* tmp = nullptr;
+  CK(sc.alloc(&tmp, (size_t)lda * (nloc > 0 ? nloc : 1) * TILE * sizeof(T)));
+  T* L = (T*)tmp;
+  CK(sc.alloc(&tmp, (size_t)(nloc > 0 ? nloc : 1) * TILE * TILE * sizeof(T)));
+  T* Dinv = (T*)tmp;  // inverse diagonal blocks of the LOCAL column blocks
+  CK(sc.alloc(&tmp, (size_t)2 * lda * TILE * sizeof(T)));
+  T* P[2] = {(T*)tmp, (T*)tmp + lda * TILE};  // double-buffered packed panels (rows_below x 128, ld = rows_below)
+  CK(sc.alloc(&tmp, (size_t)(nt + TILE + 4) * sizeof(double)));
+  double* dscal = (double*)tmp;  // [0..nt) logdet parts, [nt..nt+TILE) sqmahal, [nt+TILE] logdet
+  CK(cudaMemsetAsync(dscal, 0, (size_t)(nt + TILE + 4) * sizeof(double), s));
+  CK(sc.alloc(&tmp, sizeof(int)));
+  int* dinfo = (int*)tmp;
+  CK(cudaMemsetAsync(dinfo, 0, sizeof(int), s));
+  CK(sc.alloc(&tmp, (size_t)(S + 1) * n_pad * sizeof(T)));
+  T* rwork = (T*)tmp; T* alpha = rwork + (size_t)S * n_pad;
+  CK(cudaMemsetAsync(rwork, 0, (size_t)(S + 1) * n_pad * sizeof(T), s));
+  CK(sc.alloc(&tmp, (size_t)TILE * sizeof(T)));
+  T* lp_d = (T*)tmp;
+
+  // ---- Gram: only the local column blocks, lower part, + border rows
+  for (int lj = 0; lj < nloc; ++lj) {
+    const int64_t j = (int64_t)lj * R + me;
+    GramParams gp{};
+    fill_gram_params<T>(gp, k, 1, 1, N, N, noise, noise_d);
+    gp.diag_off = j * TILE;
+    T* col = L + (int64_t)lj * TILE * lda;
+    launch_gram<T>(Xt, Xt + j * TILE * D, n_pad, TILE, D, col, lda, gp, s);
+    launch_border_init_cols<T>(col, lda, n_pad, j * TILE, TILE, N, Yd, N, S, mean->kind, mean->c, mean_d, s);
+  }
+  CK(cudaEventRecord(ctx->ev[2], s));
+
+  // ---- distributed right-looking Cholesky with look-ahead
+  auto local_first_after = [&](int kk) {  // first local block index whose global index > kk
+    int lj = (kk + 1 - me + R - 1) / R;
+    if (lj < 0) lj = 0;
+    while ((int64_t)lj * R + me <= kk) ++lj;
+    return lj;
+  };
+  auto trailing = [&](int kk, T* Pk, int lj_lo, int lj_hi, cudaStream_t st) {  // update local blocks [lj_lo, lj_hi)
+    if (lj_lo >= lj_hi) return;
+    const int64_t rows_below = lda - (int64_t)(kk + 1) * TILE;
+    const int64_t j0 = (int64_t)lj_lo * R + me;
+    GemmArgs u{};
+    u.A = Pk; u.lda = rows_below; u.B = Pk; u.ldb = rows_below;
+    u.C = L + (int64_t)(kk + 1) * TILE + (int64_t)lj_lo * TILE * lda; u.ldc = lda;
+    u.M = rows_below; u.N = (int64_t)(lj_hi - lj_lo) * TILE; u.K = TILE;
+    u.alpha_neg = 1; u.beta_one = 1; u.lower_only = 1;
+    u.b_tile_stride = (int64_t)R * TILE; u.b_off = (j0 - (kk + 1)) * TILE;
+    if (ctx->profile) cudaEventRecord(prof_event(ctx), st);
+    launch_gemm<T>(u, st);
+    if (ctx->profile) cudaEventRecord(prof_event(ctx), st);
+  };
+  bool rest_pending = false;
+  for (int kk = 0; kk < nt; ++kk) {
+    const int owner = kk % R;
+    const int64_t rows_below = lda - (int64_t)(kk + 1) * TILE;
+    T* Pk = P[kk & 1];
+    if (owner == me) {
+      const int lk = kk / R;
+      T* Akk = L + (int64_t)kk * TILE + (int64_t)lk * TILE * lda;
+      launch_potrf_diag<T>(Akk, lda, Dinv + (int64_t)lk * TILE * TILE, dscal, kk, dinfo, s);
+      GemmArgs t{};
+      t.A = Akk + TILE; t.lda = lda; t.B = Dinv + (int64_t)lk * TILE * TILE; t.ldb = TILE;
+      t.C = Akk + TILE; t.ldc = lda; t.M = rows_below; t.N = TILE; t.K = TILE;
+      launch_gemm<T>(t, s);
+      launch_copy2d<T>(Akk + TILE, lda, Pk, rows_below, rows_below, TILE, s);
+    }
+    if (R > 1) CKN(ncclBroadcast(Pk, Pk, (size_t)rows_below * TILE, NcclType<T>::v, owner, ctx->nccl, s));
+    if (kk == nt - 1) break;
+    cudaEvent_t e_panel = dep_event(ctx, 2 * (size_t)kk), e_rest = dep_event(ctx, 2 * (size_t)kk + 1);
+    cudaEventRecord(e_panel, s);
+    // next panel column first (only its owner has it), on the main stream
+    const int lj_first = local_first_after(kk);
+    int lj_bulk = lj_first;
+    if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, 2 * (size_t)(kk - 1) + 1), 0);
+    if ((kk + 1) % R == me) {
+      trailing(kk, Pk, lj_first, lj_first + 1, s);
+      lj_bulk = lj_first + 1;
+    }
+    rest_pending = false;
+    if (lj_bulk < nloc) {
+      cudaStreamWaitEvent(s2, e_panel, 0);
+      trailing(kk, Pk, lj_bulk, nloc, s2);
+      cudaEventRecord(e_rest, s2);
+      rest_pending = true;
+    } else {
+      cudaEventRecord(e_rest, s2);  // keep the event chain uniform
+      rest_pending = true;
+    }
+  }
+  if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, 2 * (size_t)(nt - 2) + 1), 0);
+  CK(cudaEventRecord(ctx->ev[3], s));
+
+  // ---- v = border rows (distributed by column), sqmahal and logdet via all-reduce
+  for (int lj = 0; lj < nloc; ++lj) {
+    const int64_t j = (int64_t)lj * R + me;
+    for (int sI = 0; sI < S; ++sI)
+      launch_copy2d<T>(L + n_pad + sI + (int64_t)lj * TILE * lda, lda, rwork + (size_t)sI * n_pad + j * TILE, 1, 1, TILE, s);
+  }
+  for (int sI = 0; sI < S; ++sI) launch_sumsq<T>(rwork + (size_t)sI * n_pad, n_pad, dscal + nt + sI, s);
+  if (R > 1) CKN(ncclAllReduce(dscal, dscal, (size_t)(nt + TILE), ncclDouble, ncclSum, ctx->nccl, s));
+  // ---- distributed backward substitution for column 0: alpha = L^-T v
+  for (int i = nt - 1; i >= 0; --i) {
+    const int owner = i % R;
+    T* a_i = alpha + (int64_t)i * TILE;
+    if (owner == me) launch_bwd_diag<T>(Dinv + (int64_t)(i / R) * TILE * TILE, rwork + (int64_t)i * TILE, a_i, s);
+    if (R > 1) CKN(ncclBroadcast(a_i, a_i, TILE, NcclType<T>::v, owner, ctx->nccl, s));
+    if (i > 0) launch_bwd_update_local<T>(L, lda, i, a_i, rwork, nloc, me, R, s);
+  }
+  launch_finalize_logpdf<T>(dscal, nt, dscal + nt, S, N, lp_d, dscal + nt + TILE, s);
+  CK(cudaEventRecord(ctx->ev[4], s));
+  int h_info = 0;
+  if (R > 1) CKN(ncclAllReduce(dinfo, dinfo, 1, ncclInt, ncclMax, ctx->nccl, s));
+  CK(cudaMemcpyAsync(&h_info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (logpdf_out) CK(cudaMemcpyAsync(logpdf_out, lp_d, (size_t)S * sizeof(T), cudaMemcpyDeviceToHost, s));
+  if (alpha_out) { rc = download<T>(ctx, alpha_out, alpha, (size_t)N, false); if (rc) return rc; }
+  CK(cudaEventRecord(ctx->ev[5], s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaStreamSynchronize(s2));
+  CK(cudaGetLastError());
+  float ms = 0;
+  auto el = [&](int a, int b) { cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]); return (double)ms; };
+  ctx->timings[0] = el(0, 5); ctx->timings[1] = el(0, 1); ctx->timings[2] = el(1, 2); ctx->timings[3] = el(2, 3);
+  ctx->timings[4] = el(3, 4); ctx->timings[5] = el(4, 5); ctx->timings[6] = 0.0;
+  ctx->timings[7] = ctx->profile ? prof_total_ms(ctx) : 0.0;
+  if (h_info != 0) {
+    ctx->info = h_info;
+    ctx->err = "matrix is not positive definite (distributed Cholesky)";
+    return AGP_ERR_NOT_POSDEF;
+  }
+  return AGP_OK;
+}
+
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -1018,6 +1203,7 @@ int32_t agp_destroy(agp_ctx* ctx) {
   for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
   for (auto e : ctx->prof_ev) cudaEventDestroy(e);
   for (auto e : ctx->dep_ev) cudaEventDestroy(e);
+  if (ctx->nccl) ncclCommDestroy(ctx->nccl);
   cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1051,6 +1237,11 @@ int32_t agp_fit(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, const agp_mean
                 void* alpha_out, agp_post** post_out) {
   if (!ctx) return AGP_ERR_INVALID;
   if (post_out) *post_out = nullptr;
+  if (ctx->nccl) {  // distributed context: every rank calls with the same (replicated) inputs
+    if (post_out) { ctx->err = "posterior handles are single-GPU in this build; distributed fit returns logpdf and alpha"; }
+    return DISPATCH(dtype, fit_dist_impl<float>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out),
+                    fit_dist_impl<double>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out));
+  }
   return DISPATCH(dtype,
                   fit_impl<float>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out, post_out, nullptr, nullptr, nullptr),
                   fit_impl<double>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out, post_out, nullptr, nullptr, nullptr));
@@ -1154,12 +1345,30 @@ int32_t agp_vfe_post_free(agp_vfe_post* p) {
   delete p;
   return AGP_OK;
 }
-// (agp_nccl_unique_id / agp_init_dist: see below)
-int32_t agp_nccl_unique_id(void*) { return AGP_ERR_UNSUPPORTED; }
-int32_t agp_init_dist(agp_ctx** ctx, int32_t, int32_t, int32_t, int32_t, int32_t, const void*, const agp_config*) {
-  if (ctx) *ctx = nullptr;
-  return AGP_ERR_UNSUPPORTED;
+int32_t agp_nccl_unique_id(void* out128) {
+  if (!out128) return AGP_ERR_INVALID;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return AGP_ERR_NCCL;
+  memcpy(out128, &id, 128);
+  return AGP_OK;
 }
-
+int32_t agp_init_dist(agp_ctx** out, int32_t device, int32_t rank, int32_t nranks, int32_t grid_p, int32_t grid_q,
+                      const void* id128, const agp_config* cfg) {
+  if (!out || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return AGP_ERR_INVALID;
+  if (grid_p != 1 || grid_q != nranks) return AGP_ERR_UNSUPPORTED;  // 1 x Q block-column-cyclic grid in this build
+  int32_t rc = agp_init(out, device, cfg);
+  if (rc != AGP_OK) return rc;
+  agp_ctx* ctx = *out;
+  ctx->rank = rank; ctx->nranks = nranks; ctx->grid_p = grid_p; ctx->grid_q = grid_q;
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  if (ncclCommInitRank(&ctx->nccl, nranks, id, rank) != ncclSuccess) {
+    agp_destroy(ctx);
+    *out = nullptr;
+    return AGP_ERR_NCCL;
+  }
+  return AGP_OK;
+}
 
 }  // extern "C"

@@ -69,13 +69,14 @@ __global__ void __launch_bounds__(32 * WM * WN, (WM * WN <= 4) ? 2 : 1) gemm_dmm
   constexpr int A_LD = TBM + 4, B_LD = TBN + 4;
   const int bi = blockIdx.x, bj = blockIdx.y;
   const int64_t m0 = (int64_t)bi * TBM, n0 = (int64_t)bj * TBN;
-  if (g.lower_only && n0 >= m0 + TBM) return;  // tile entirely above the diagonal
+  const int64_t n_src0 = g.b_tile_stride ? (n0 / 128) * g.b_tile_stride + (n0 % 128) + g.b_off : n0;
+  if (g.lower_only && n_src0 >= m0 + TBM) return;  // tile entirely above the diagonal
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
   double* sA = sm;                    // [D_STAGES][A_SZ]
   double* sB = sm + D_STAGES * A_SZ;  // [D_STAGES][B_SZ]
   const double* __restrict__ A = (const double*)g.A;
-  const double* __restrict__ B = (const double*)g.B;
+  const double* __restrict__ B = (const double*)g.B + (BKM ? (n_src0 - n0) * g.ldb : (n_src0 - n0));
   double* C = (double*)g.C;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp % WM, wn = warp / WM;
@@ -210,15 +211,17 @@ __device__ __forceinline__ void s_stash(float* s, const float4 (&r)[2], int tid)
 template <bool AK, bool BKM>
 __global__ void __launch_bounds__(256, 2) gemm_simt_kernel(GemmArgs g) {
   const int bi = blockIdx.x, bj = blockIdx.y;
-  if (g.lower_only && bj > bi) return;
   __shared__ __align__(16) float sA[2][BK * S_LD];
   __shared__ __align__(16) float sB[2][BK * S_LD];
   const float* __restrict__ A = (const float*)g.A;
-  const float* __restrict__ B = (const float*)g.B;
+  const float* B = (const float*)g.B;
   float* __restrict__ C = (float*)g.C;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int64_t m0 = (int64_t)bi * BM, n0 = (int64_t)bj * BN;
+  const int64_t n_src0 = g.b_tile_stride ? (n0 / 128) * g.b_tile_stride + (n0 % 128) + g.b_off : n0;
+  if (g.lower_only && n_src0 >= m0 + BM) return;
+  B += (BKM ? (n_src0 - n0) * g.ldb : (n_src0 - n0));
   int64_t K = g.K;
   if (g.trmm_lower) { int64_t kl = m0 + BM; if (kl < K) K = kl; }
   const int KT = (int)((K + BK - 1) / BK);

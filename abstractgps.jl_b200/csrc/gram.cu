@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256)
 gram_kernel(const T* __restrict__ Xa, const T* __restrict__ Xb, int D, T* __restrict__ K, int64_t ldk,
             GramParams p) {
   const int ti = blockIdx.x, tj = blockIdx.y;
-  if (p.lower_only && tj > ti) return;
+  if (p.lower_only && (int64_t)tj * GT + p.diag_off > (int64_t)ti * GT + (GT - 1)) return;
   __shared__ T sa[GDC][GT + 1];
   __shared__ T sb[GDC][GT + 1];
   const int tid = threadIdx.x;
@@ -140,19 +140,20 @@ gram_kernel(const T* __restrict__ Xa, const T* __restrict__ Xb, int D, T* __rest
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int64_t gj = col0 + ty + 16 * c;
+    const int64_t gjg = gj + p.diag_off;  // global column index
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int64_t gi = row0 + tx + 16 * r;
       T v;
       const bool pad_a = p.mask_a ? (p.mask_a[gi] == 0) : (gi >= p.valid_a);
-      const bool pad_b = p.mask_b ? (p.mask_b[gj] == 0) : (gj >= p.valid_b);
+      const bool pad_b = p.mask_b ? (p.mask_b[gj] == 0) : (gjg >= p.valid_b);
       if (pad_a || pad_b) {
-        v = (p.symmetric && gi == gj) ? (T)1 : (T)0;  // identity padding
+        v = (p.symmetric && gi == gjg) ? (T)1 : (T)0;  // identity padding
       } else {
         T a = acc[r][c];
-        if (p.symmetric && gi == gj && !linear) a = 0;  // exactly-zero self distance
+        if (p.symmetric && gi == gjg && !linear) a = 0;  // exactly-zero self distance
         v = kappa<T>(p.family, a, variance, lc);
-        if (p.symmetric && gi == gj && p.noise_kind >= 0)
+        if (p.symmetric && gi == gjg && p.noise_kind >= 0)
           v += (p.noise_kind == 0) ? (T)p.noise_s : ((const T*)p.noise_v)[gi - p.noise_off];
       }
       K[gi + gj * ldk] = v;

@@ -22,6 +22,7 @@ struct GramParams {
   const unsigned char* mask_a;  // optional per-row validity (extended posteriors); overrides valid_a
   const unsigned char* mask_b;
   int64_t noise_off;  // noise_v index offset for the diagonal (block Gram of an extension)
+  int64_t diag_off;   // column index offset: column gj of this launch is global column gj + diag_off
 };
 
 // op(A) is M x K, op(B) is K x N, C is M x N (ldc).  C = beta*C + alpha*op(A)op(B), alpha in {+1,-1}.
@@ -34,6 +35,9 @@ struct GemmArgs {
   int beta_one;      // 1 -> beta = 1 else 0
   int lower_only;    // 1 -> skip tiles with tile_n > tile_m (SYRK on a diagonal-anchored C)
   int trmm_lower;    // 1 -> A is lower triangular M x K anchored at (0,0): limit k <= row tile end
+  // block-cyclic column gather (multi-GPU trailing update): local column n of C takes its B rows from
+  // n_src = (n / 128) * b_tile_stride + n % 128 + b_off; 0 = identity.  The lower-only test uses n_src.
+  int64_t b_tile_stride, b_off;
 };
 
 template <typename T> void launch_prep_points(const T* X, int layout, int64_t n, int64_t n_pad, int D,
@@ -48,6 +52,11 @@ template <typename T> void launch_kdiag(const T* Xt, int64_t n, int D, int famil
 template <typename T> void launch_border_init(T* A, int64_t lda, int64_t n, int64_t n_pad, const T* Y,
                                               int64_t ldy, int S, int mean_kind, double mean_c,
                                               const T* mean_v, cudaStream_t s);
+// same for a block of `ncols` columns of a column-distributed factor: A points at the block's first
+// column, border rows start at row_off, column c of the block is global point col0 + c (valid if < n)
+template <typename T> void launch_border_init_cols(T* A, int64_t lda, int64_t row_off, int64_t col0, int64_t ncols,
+                                                   int64_t n, const T* Y, int64_t ldy, int S, int mean_kind,
+                                                   double mean_c, const T* mean_v, cudaStream_t s);
 // diagonal block factorisation + inverse: A (TILE x TILE at Ablk, lda) -> L in place (upper zeroed),
 // Dinv = inv(L) (TILE x TILE col-major, lower), logdet_part[blk] = sum log L_jj, info (first bad pivot, 1-based).
 template <typename T> void launch_potrf_diag(T* Ablk, int64_t lda, T* Dinv, double* logdet_part, int blk,
@@ -62,6 +71,10 @@ template <typename T> void launch_bwd_step(const T* A, int64_t lda, const T* Din
 // whole backward substitution in one persistent launch; flags_and_ticket: nblk+1 ints (zeroed inside)
 template <typename T> void launch_bwd_solve(const T* A, int64_t lda, const T* Dinv, int nblk, T* r,
                                             int* flags_and_ticket, cudaStream_t s);
+// distributed (column-cyclic) backward substitution pieces
+template <typename T> void launch_bwd_diag(const T* Dinv_i, const T* r_i, T* alpha_i, cudaStream_t s);
+template <typename T> void launch_bwd_update_local(const T* Lloc, int64_t lda, int i_blk, const T* alpha_i, T* r, int nloc,
+                                                   int rank, int nranks, cudaStream_t s);
 // one step of the blocked forward substitution L v = r (in place), block k (used by extend / vfe)
 template <typename T> void launch_fwd_step(const T* A, int64_t lda, const T* Dinv, int k, int nblk, T* r,
                                            cudaStream_t s);

@@ -198,6 +198,53 @@ __global__ void __launch_bounds__(256, 1) bwd_solve_kernel(const T* __restrict__
   if (tid == 0) st_release(flags + b, 1);
 }
 
+
+template <typename T>
+__global__ void border_init_cols_kernel(T* __restrict__ A, int64_t lda, int64_t row_off, int64_t col0, int64_t ncols,
+                                        int64_t n, const T* __restrict__ Y, int64_t ldy, int S, int mean_kind, T mean_c,
+                                        const T* __restrict__ mean_v) {
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= ncols * TB) return;
+  const int s = (int)(idx & (TB - 1));
+  const int64_t c = idx >> 7, j = col0 + c;
+  T v = 0;
+  if (s < S && j < n) {
+    T m = (mean_kind == 0) ? (T)0 : (mean_kind == 1 ? mean_c : mean_v[j]);
+    v = Y[j + (int64_t)s * ldy] - m;
+  }
+  A[(row_off + s) + c * lda] = v;
+}
+
+// distributed backward substitution pieces (column-cyclic factor): alpha_i = Dinv_i' r_i on the owner,
+// then every rank applies r_j -= L(i,j)' alpha_i to its local column blocks j < i.
+template <typename T>
+__global__ void __launch_bounds__(256) bwd_diag_kernel(const T* __restrict__ Dinv_i, const T* __restrict__ r_i, T* __restrict__ alpha_i) {
+  __shared__ T rk[TB];
+  const int tid = threadIdx.x, o = tid >> 1, h = tid & 1;
+  if (tid < TB) rk[tid] = r_i[tid];
+  __syncthreads();
+  double acc = col_dot_half<T>(Dinv_i + o * TB, rk, h);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (h == 0) alpha_i[o] = (T)acc;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) bwd_update_local_kernel(const T* __restrict__ Lloc, int64_t lda, int i_blk,
+                                                                const T* __restrict__ alpha_i, T* __restrict__ r,
+                                                                int rank, int nranks) {
+  // CTA c handles local column block lj = c  (global j = lj*nranks + rank), only if j < i
+  __shared__ T ak[TB];
+  const int lj = blockIdx.x;
+  const int64_t j = (int64_t)lj * nranks + rank;
+  if (j >= i_blk) return;
+  const int tid = threadIdx.x, o = tid >> 1, h = tid & 1;
+  if (tid < TB) ak[tid] = alpha_i[tid];
+  __syncthreads();
+  const T* tile = Lloc + (int64_t)i_blk * TB + ((int64_t)lj * TB + o) * lda;
+  double acc = col_dot_half<T>(tile, ak, h);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (h == 0) r[j * TB + o] -= (T)acc;
+}
+
 // forward step k: v_k = Dinv_k r_k ; r_b -= L[b-block rows, k-block cols] v_k for b > k.
 // thread (row i, half h) accumulates half of the 128-term dot product; rows are consecutive across
 // threads so every global read is coalesced.
@@ -600,7 +647,34 @@ void launch_sub_mean(const T* y, int64_t n, int mean_kind, double mean_c, const 
   agp_count_launch();
 }
 
+template <typename T>
+void launch_border_init_cols(T* A, int64_t lda, int64_t row_off, int64_t col0, int64_t ncols, int64_t n, const T* Y,
+                             int64_t ldy, int S, int mean_kind, double mean_c, const T* mean_v, cudaStream_t s) {
+  if (ncols <= 0) return;
+  border_init_cols_kernel<T><<<(unsigned)((ncols * TB + 255) / 256), 256, 0, s>>>(A, lda, row_off, col0, ncols, n, Y, ldy, S,
+                                                                                  mean_kind, (T)mean_c, mean_v);
+  agp_count_launch();
+}
+template <typename T>
+void launch_bwd_diag(const T* Dinv_i, const T* r_i, T* alpha_i, cudaStream_t s) {
+  bwd_diag_kernel<T><<<1, 256, 0, s>>>(Dinv_i, r_i, alpha_i);
+  agp_count_launch();
+}
+template <typename T>
+void launch_bwd_update_local(const T* Lloc, int64_t lda, int i_blk, const T* alpha_i, T* r, int nloc, int rank, int nranks,
+                             cudaStream_t s) {
+  if (nloc <= 0) return;
+  bwd_update_local_kernel<T><<<nloc, 256, 0, s>>>(Lloc, lda, i_blk, alpha_i, r, rank, nranks);
+  agp_count_launch();
+}
+
 // explicit instantiations
+template void launch_border_init_cols<float>(float*, int64_t, int64_t, int64_t, int64_t, int64_t, const float*, int64_t, int, int, double, const float*, cudaStream_t);
+template void launch_bwd_diag<float>(const float*, const float*, float*, cudaStream_t);
+template void launch_bwd_update_local<float>(const float*, int64_t, int, const float*, float*, int, int, int, cudaStream_t);
+template void launch_border_init_cols<double>(double*, int64_t, int64_t, int64_t, int64_t, int64_t, const double*, int64_t, int, int, double, const double*, cudaStream_t);
+template void launch_bwd_diag<double>(const double*, const double*, double*, cudaStream_t);
+template void launch_bwd_update_local<double>(const double*, int64_t, int, const double*, double*, int, int, int, cudaStream_t);
 template void launch_sub_mean<float>(const float*, int64_t, int, double, const float*, float*, cudaStream_t);
 template void launch_sub_mean<double>(const double*, int64_t, int, double, const double*, double*, cudaStream_t);
 template void launch_gemv_n_acc<float>(const float*, int64_t, int64_t, int64_t, const float*, float*, cudaStream_t);

@@ -177,10 +177,11 @@ def run_ours(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1 or args.gpus > 1:
-        if rank == 0:
-            print(json.dumps({"metric": "ms to logpdf(fx,y)+posterior(fx,y)", "n_gpus": args.gpus,
-                              "unavailable": "multi-GPU block-cyclic Cholesky not built yet in this round"}))
+    if world > 1:
+        return run_ours_dist(args, wl, rank, world, local)
+    if args.gpus > 1:
+        print(json.dumps({"metric": "ms to logpdf(fx,y)+posterior(fx,y)", "n_gpus": args.gpus,
+                          "unavailable": "launch with torchrun --nproc-per-node N (one rank per GPU)"}))
         return
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -297,6 +298,105 @@ def run_ours(args, wl):
                     "d2h_bytes_per_step": int(alpha_h.numel() * 8 + 8 + 4 + 8), "wall_ms_per_step": wall_e2e,
                     "phases_ms": t_e2e},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "parity": parity}
+    print(json.dumps(line))
+
+
+def run_ours_dist(args, wl, rank, world, local):
+    """N > 1: one rank per GPU (torchrun); block-column-cyclic Cholesky with NCCL panel broadcast inside
+    libagp.so.  Strong scaling: the SAME workload at every N.  Time = max over ranks of the library's
+    CUDA-event time, bracketed by a barrier + device sync on both sides."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from agp_b200 import _cabi as cabi
+    from agp_b200.dist import init_distributed_engine
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    eng = init_distributed_engine()
+    L = eng.L
+    cfg = make_inputs(wl)
+    W = WORKLOADS[wl]
+    N, D = W["N"], W["D"]
+    X = np.ascontiguousarray(cfg["X"], dtype=np.float64)
+    y = np.ascontiguousarray(cfg["y"], dtype=np.float64)
+    ks = cabi.agp_kernel()
+    ks.family, ks.transform, ks.variance, ks.scale = 0, 1, 1.0, float(cfg["k"].scale)
+    ms_ = cabi.agp_mean()
+    ns = cabi.agp_noise()
+    ns.kind, ns.s = 0, W["s2"]
+    Xh, yh = torch.from_numpy(X).pin_memory(), torch.from_numpy(y).pin_memory()
+    alpha_h = torch.empty(N, dtype=torch.float64).pin_memory()
+    Xd, yd = Xh.to(dev), yh.to(dev)
+    alpha_d = torch.empty(N, dtype=torch.float64, device=dev)
+    lp = np.zeros(1)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step(device_resident):
+        eng.set_memspace(cabi.AGP_MEM_DEVICE if device_resident else cabi.AGP_MEM_HOST)
+        xp = Xd.data_ptr() if device_resident else Xh.data_ptr()
+        yp = yd.data_ptr() if device_resident else yh.data_ptr()
+        ap = alpha_d.data_ptr() if device_resident else alpha_h.data_ptr()
+        rc = L.agp_fit(eng.h, cabi.AGP_F64, C.byref(ks), C.byref(ms_), C.byref(ns), cabi.AGP_POINT_MAJOR,
+                       C.c_void_p(xp), N, D, C.c_void_p(yp), 1, cabi.ptr(lp), C.c_void_p(ap), None)
+        eng.check(rc)
+        return eng.timings()
+
+    def timed(device_resident, steps, warmup):
+        for _ in range(warmup):
+            step(device_resident)
+        tot = {}
+        launches0 = eng.launch_count()
+        wall = 0.0
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            t = step(device_resident)
+            torch.cuda.synchronize()
+            dist.barrier()
+            wall += time.perf_counter() - t0
+            for k_, v in t.items():
+                tot[k_] = tot.get(k_, 0.0) + v
+        mine = {k_: v / steps for k_, v in tot.items()}
+        keys = sorted(mine)
+        tt = torch.tensor([mine[k_] for k_ in keys], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)  # max over ranks, per phase
+        return dict(zip(keys, tt.tolist())), wall * 1e3 / steps, eng.launch_count() - launches0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_dev, wall_dev, launches = timed(True, args.steps, args.warmup)
+    t_e2e, wall_e2e, _ = timed(False, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    lt = torch.tensor([float(launches)])
+    dist.all_reduce(lt)
+    if rank != 0:
+        return
+    dgemm = measure_dgemm_peak(torch, dev)
+    tf = trailing_flops(N)
+    chol_tf = (N ** 3 / 3.0) / (t_dev["cholesky"] * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel<false,false,2,2> (trailing update of the local block columns)",
+                "achieved": chol_tf, "peak": dgemm * world, "unit": "TFLOP/s", "frac": chol_tf / (dgemm * world),
+                "peak_source": "N x cuBLAS DGEMM 8192^3 measured on rank 0 in this run; achieved = (N^3/3)/max-over-ranks "
+                               "factorisation time (whole job)",
+                "alg_flops_per_step": N ** 3 / 3.0, "trailing_flops_per_step": tf,
+                "kernel_ms_per_step_rank_max": t_dev.get("trailing", 0.0), "traffic": None}
+    line = {"metric": "ms to logpdf(fx,y)+posterior(fx,y)", "value": t_dev["total"], "unit": "ms", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev["total"], "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: N=%d D=%d %s fp64, sigma2=%g, fused fit (logpdf + alpha), block-column-cyclic over %d GPUs, "
+                                   "NCCL panel broadcast" % (wl, N, D, W["kernel"], W["s2"], world),
+                       "l2": "256 MiB flush buffer written between timed iterations",
+                       "timer": "CUDA events on the library stream, max over ranks", "tile": 128, "grid": "1x%d" % world},
+            "phases_ms": t_dev, "wall_ms_per_step": wall_dev,
+            "e2e": {"value": t_e2e["total"], "unit": "ms", "h2d_bytes_per_step": int((X.nbytes + y.nbytes) * world),
+                    "d2h_bytes_per_step": int((alpha_h.numel() * 8 + 12) * world), "wall_ms_per_step": wall_e2e,
+                    "phases_ms": t_e2e},
+            "gpu_launches": int(lt.item()), "roofline": roofline, "clocks": clocks,
+            "logpdf": float(lp[0])}
     print(json.dumps(line))
 
 

@@ -1,0 +1,71 @@
+"""Run under torchrun on >= 2 GPUs: the distributed fit (column-cyclic Cholesky + NCCL panel broadcast) must
+match the oracle and the single-GPU result.  Prints DIST_OK on rank 0."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import agp_b200 as ag  # noqa: E402
+from agp_b200 import _cabi as cabi  # noqa: E402
+from agp_b200.dist import init_distributed_engine  # noqa: E402
+from oracle import agp_ref as ref  # noqa: E402
+
+
+def main():
+    eng = init_distributed_engine()
+    rank = getattr(eng, "rank", 0)
+    ok = True
+    for (n, d, dtype, fam) in [(300, 3, np.float64, ref.SE), (1537, 8, np.float64, ref.MATERN32), (1000, 4, np.float32, ref.SE),
+                               (128, 2, np.float64, ref.SE), (2100, 6, np.float64, ref.MATERN52)]:
+        rng = np.random.default_rng(n)
+        X = rng.random((n, d)).astype(dtype)
+        Y = np.asfortranarray(np.stack([np.sin(X.sum(1)), rng.standard_normal(n)], 1).astype(dtype))
+        ksr = ref.KernelSpec(fam, 1.3, ref.T_SCALE, scale=1.0 / (0.5 * np.sqrt(d)))
+        ks = cabi.agp_kernel()
+        ks.family, ks.transform, ks.variance, ks.scale = fam, 1, 1.3, ksr.scale
+        ms = cabi.agp_mean()
+        ms.kind, ms.c = 1, 0.25
+        ns = cabi.agp_noise()
+        ns.kind, ns.s = 0, 0.1
+        lp = np.zeros(2, dtype=dtype)
+        alpha = np.zeros(n, dtype=dtype)
+        rc = eng.L.agp_fit(eng.h, cabi.dtype_code(dtype), C.byref(ks), C.byref(ms), C.byref(ns), cabi.AGP_POINT_MAJOR,
+                           cabi.ptr(X), n, d, cabi.ptr(Y), 2, cabi.ptr(lp), cabi.ptr(alpha), None)
+        eng.check(rc)
+        lp_ref = ref.logpdf(ksr, ref.MeanSpec(1, 0.25), ref.NoiseSpec(0, 0.1), X, Y)
+        pr = ref.posterior(ksr, ref.MeanSpec(1, 0.25), ref.NoiseSpec(0, 0.1), X, Y[:, 0])
+        rt = 1e-8 if dtype == np.float64 else 1e-4
+        good = np.allclose(lp, lp_ref, rtol=rt, atol=0 if dtype == np.float64 else 1e-2)
+        sc = np.abs(pr["alpha"]).max()
+        good &= np.allclose(alpha, pr["alpha"], rtol=1e-6 if dtype == np.float64 else 1e-2,
+                            atol=(1e-7 if dtype == np.float64 else 5e-3) * sc)
+        if rank == 0:
+            print("n=%d %s fam=%d: logpdf %s ref %s  ok=%s" % (n, np.dtype(dtype).name, fam, lp, lp_ref, good), flush=True)
+        ok &= bool(good)
+    # non-PD must surface on every rank, not hang
+    n = 200
+    X = np.zeros((n, 1))
+    Y = np.zeros((n, 1), order="F")
+    ks = cabi.agp_kernel()
+    ks.family, ks.transform, ks.variance, ks.scale = 0, 0, 1.0, 1.0
+    ns = cabi.agp_noise()
+    ns.kind, ns.s = 0, -0.5
+    lp = np.zeros(1)
+    rc = eng.L.agp_fit(eng.h, cabi.AGP_F64, C.byref(ks), None, C.byref(ns), cabi.AGP_POINT_MAJOR, cabi.ptr(X), n, 1,
+                       cabi.ptr(Y), 1, cabi.ptr(lp), None, None)
+    ok &= (rc == cabi.AGP_ERR_NOT_POSDEF)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([1.0 if ok else 0.0])
+    if dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DIST_OK" if t.item() == 1.0 else "DIST_FAIL", flush=True)
+    sys.exit(0 if t.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
