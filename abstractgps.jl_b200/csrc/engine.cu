@@ -20,6 +20,7 @@
 
 #include "agp.h"
 #include "kernels.h"
+#include "umma_ozaki.h"
 
 #define TILE AGP_TILE
 
@@ -168,62 +169,76 @@ static cudaEvent_t dep_event(agp_ctx* ctx, size_t i) {
   return ctx->dep_ev[i];
 }
 
+// Two-level blocking: an OUTER panel is G inner blocks (G*128 columns).  Inside it, each inner step is
+// potrf -> panel TRSM -> rank-128 update of the remaining inner columns only; the trailing matrix then
+// receives ONE rank-(G*128) update per outer panel (K = G*128 halves/quarters the read-modify-write
+// passes over C and is what the tensor-core trailing kernels need to be compute-bound).
+template <typename T>
+void trailing_update(agp_ctx* ctx, T* L, int64_t lda, int64_t row0, int64_t col0, int64_t kcol0, int64_t K,
+                     int64_t M, int64_t N, cudaStream_t st) {
+  // C = L[row0.., col0..] (M x N, diagonal-anchored iff row0 == col0) -= L[row0.., kcol0..] * L[col0.., kcol0..]'
+  if (M <= 0 || N <= 0) return;
+  GemmArgs u{};
+  u.A = L + row0 + kcol0 * lda; u.lda = lda;
+  u.B = L + col0 + kcol0 * lda; u.ldb = lda;
+  u.C = L + row0 + col0 * lda; u.ldc = lda;
+  u.M = M; u.N = N; u.K = K; u.alpha_neg = 1; u.beta_one = 1; u.lower_only = 1;
+  if (row0 != col0) { u.b_tile_stride = TILE; u.b_off = col0 - row0; }  // lower-only test relative to row0
+  if (ctx->profile) cudaEventRecord(prof_event(ctx), st);
+  launch_gemm<T>(u, st);
+  if (ctx->profile) cudaEventRecord(prof_event(ctx), st);
+}
+
 template <typename T>
 void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t rows_total, T* Dinv,
                       double* logdet_part, int* info) {
   cudaStream_t s = ctx->stream, s2 = ctx->stream2;
   const int nblk = (int)(n_pad / TILE);
-  const bool la = ctx->cfg.lookahead != 0 && nblk > 2;
+  int G = ctx->cfg.tile_nb / TILE;
+  if (G < 1) G = 1;
+  const bool la = ctx->cfg.lookahead != 0 && nblk > 2 * G;
   bool rest_pending = false;
-  for (int k = 0; k < nblk; ++k) {
-    T* Akk = L + (int64_t)k * TILE + (int64_t)k * TILE * lda;
-    launch_potrf_diag<T>(Akk, lda, Dinv + (int64_t)k * TILE * TILE, logdet_part, k, info, s);
-    const int64_t rows_below = rows_total - (int64_t)(k + 1) * TILE;
-    if (rows_below <= 0) continue;
-    T* A21 = Akk + TILE;
-    GemmArgs t{};  // A21 <- A21 * inv(L11)'
-    t.A = A21; t.lda = lda; t.a_kmajor = 0;
-    t.B = Dinv + (int64_t)k * TILE * TILE; t.ldb = TILE; t.b_kmajor = 0;
-    t.C = A21; t.ldc = lda; t.M = rows_below; t.N = TILE; t.K = TILE;
-    launch_gemm<T>(t, s);
-    const int64_t cols_trail = n_pad - (int64_t)(k + 1) * TILE;
+  size_t ev_idx = 0, last_rest = 0;
+  for (int ko = 0; ko < nblk; ko += G) {
+    const int g_end = (ko + G < nblk) ? ko + G : nblk;  // inner blocks [ko, g_end)
+    for (int k = ko; k < g_end; ++k) {
+      T* Akk = L + (int64_t)k * TILE + (int64_t)k * TILE * lda;
+      launch_potrf_diag<T>(Akk, lda, Dinv + (int64_t)k * TILE * TILE, logdet_part, k, info, s);
+      const int64_t rows_below = rows_total - (int64_t)(k + 1) * TILE;
+      if (rows_below <= 0) continue;
+      T* A21 = Akk + TILE;
+      GemmArgs t{};  // A21 <- A21 * inv(L11)'
+      t.A = A21; t.lda = lda; t.B = Dinv + (int64_t)k * TILE * TILE; t.ldb = TILE;
+      t.C = A21; t.ldc = lda; t.M = rows_below; t.N = TILE; t.K = TILE;
+      launch_gemm<T>(t, s);
+      // rank-128 update of the remaining inner columns of this outer panel
+      const int64_t c0 = (int64_t)(k + 1) * TILE, ncols_in = (int64_t)(g_end - (k + 1)) * TILE;
+      if (ncols_in > 0) trailing_update<T>(ctx, L, lda, c0, c0, (int64_t)k * TILE, TILE, rows_total - c0, ncols_in, s);
+    }
+    const int64_t t0 = (int64_t)g_end * TILE;           // first trailing row/column
+    const int64_t cols_trail = n_pad - t0;
     if (cols_trail <= 0) continue;
-    GemmArgs u{};  // A22 -= A21 A21'   (lower tiles only)
-    u.A = A21; u.lda = lda; u.a_kmajor = 0;
-    u.B = A21; u.ldb = lda; u.b_kmajor = 0;
-    u.C = A21 + (int64_t)TILE * lda; u.ldc = lda;
-    u.M = rows_below; u.N = cols_trail; u.K = TILE; u.alpha_neg = 1; u.beta_one = 1; u.lower_only = 1;
+    const int64_t K = (int64_t)(g_end - ko) * TILE, kc0 = (int64_t)ko * TILE;
     if (!la) {
-      if (ctx->profile) cudaEventRecord(prof_event(ctx), s);
-      launch_gemm<T>(u, s);
-      if (ctx->profile) cudaEventRecord(prof_event(ctx), s);
+      trailing_update<T>(ctx, L, lda, t0, t0, kc0, K, rows_total - t0, cols_trail, s);
       continue;
     }
-    cudaEvent_t e_trsm = dep_event(ctx, 2 * (size_t)k), e_rest = dep_event(ctx, 2 * (size_t)k + 1);
-    cudaEventRecord(e_trsm, s);
-    // main stream: next panel column only (needs the previous step's bulk update of that column)
-    if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, 2 * (size_t)(k - 1) + 1), 0);
-    GemmArgs a = u;
-    a.N = TILE;
-    if (ctx->profile) cudaEventRecord(prof_event(ctx), s);
-    launch_gemm<T>(a, s);
-    if (ctx->profile) cudaEventRecord(prof_event(ctx), s);
+    cudaEvent_t e_panel = dep_event(ctx, ev_idx++), e_rest = dep_event(ctx, ev_idx++);
+    cudaEventRecord(e_panel, s);
+    if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, last_rest), 0);
+    const int64_t next_cols = (cols_trail < (int64_t)G * TILE) ? cols_trail : (int64_t)G * TILE;
+    trailing_update<T>(ctx, L, lda, t0, t0, kc0, K, rows_total - t0, next_cols, s);  // next outer panel first
     rest_pending = false;
-    if (cols_trail > TILE) {  // side stream: everything right of the next panel column
-      GemmArgs r = u;
-      r.A = A21 + TILE;                                  // rows from block k+2 on (tiles above are skipped anyway)
-      r.B = A21 + TILE;                                  // columns from block k+2 on
-      r.C = A21 + (int64_t)TILE * lda + TILE + (int64_t)TILE * lda;
-      r.M = rows_below - TILE; r.N = cols_trail - TILE;
-      cudaStreamWaitEvent(s2, e_trsm, 0);
-      if (ctx->profile) cudaEventRecord(prof_event(ctx), s2);
-      launch_gemm<T>(r, s2);
-      if (ctx->profile) cudaEventRecord(prof_event(ctx), s2);
+    if (cols_trail > next_cols) {
+      const int64_t r0 = t0 + next_cols;
+      cudaStreamWaitEvent(s2, e_panel, 0);
+      trailing_update<T>(ctx, L, lda, r0, r0, kc0, K, rows_total - r0, n_pad - r0, s2);
       cudaEventRecord(e_rest, s2);
       rest_pending = true;
+      last_rest = ev_idx - 1;
     }
   }
-  if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, 2 * (size_t)(nblk - 2) + 1), 0);
+  if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, last_rest), 0);
 }
 
 // V <- L^-1 V for a n_pad x ncols block of right-hand sides (ncols multiple of 4), in place
@@ -1177,7 +1192,8 @@ int32_t agp_init(agp_ctx** out, int32_t device, const agp_config* cfg) {
   agp_ctx* ctx = new agp_ctx();
   ctx->device = device;
   if (cfg) ctx->cfg = *cfg;
-  ctx->cfg.tile_nb = TILE;
+  ctx->cfg.tile_nb = env_int("AGP_NB", (cfg && cfg->tile_nb > 0) ? cfg->tile_nb : TILE);
+  if (ctx->cfg.tile_nb < TILE || ctx->cfg.tile_nb % TILE) ctx->cfg.tile_nb = TILE;
   ctx->cfg.fp64_mode = env_int("AGP_FP64_MODE", ctx->cfg.fp64_mode);
   ctx->cfg.fp32_mode = env_int("AGP_FP32_MODE", ctx->cfg.fp32_mode);
   ctx->cfg.lookahead = env_int("AGP_LOOKAHEAD", cfg ? ctx->cfg.lookahead : 1);
@@ -1298,6 +1314,22 @@ int32_t agp_rand(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, const agp_mea
   if (!ctx) return AGP_ERR_INVALID;
   return DISPATCH(dtype, rand_impl<float>(ctx, k, mean, noise, layout, X, N, D, Z, S, out),
                   rand_impl<double>(ctx, k, mean, noise, layout, X, N, D, Z, S, out));
+}
+
+int32_t agp_debug_ozaki_syrk(agp_ctx* ctx, void* C_dev, int64_t ldc, const void* P_dev, int64_t lda, int64_t M, int64_t N,
+                             int32_t K, int32_t S, int32_t lower_only) {
+  if (!ctx || !C_dev || !P_dev) return AGP_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  OzakiWs ws;
+  int rc = ozaki_ws_create(&ws, M, K, S, ctx->stream);
+  if (rc) { ctx->err = "ozaki_ws_create failed (code " + std::to_string(rc) + ")"; return rc == 1 ? AGP_ERR_INVALID : AGP_ERR_CUDA; }
+  ozaki_prepare(ws, (const double*)P_dev, lda, M, ctx->stream);
+  ozaki_syrk(ws, (double*)C_dev, ldc, M, N, lower_only, 0, 0, ctx->stream);
+  ozaki_ws_destroy(&ws, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { ctx->err = std::string("ozaki syrk: ") + cudaGetErrorString(e); return AGP_ERR_CUDA; }
+  return AGP_OK;
 }
 
 int32_t agp_bc_owner(int32_t ti, int32_t tj, int32_t P, int32_t Q) { return (ti % P) * Q + (tj % Q); }

@@ -1,0 +1,351 @@
+// umma_ozaki.cu -- K5 on the 5th-generation tensor cores: the fp64 trailing update
+//     C (m x n, lower tiles, fp64)  -=  P P'          (P = the factored outer panel, m x K, fp64)
+// executed as EXACT int8 x int8 -> int32 products on tcgen05.mma.kind::i8 with TMEM accumulators,
+// operands staged by TMA (cp.async.bulk.tensor, 64-byte swizzle), recombined in fp64 in the epilogue
+// (Ozaki-style error-free splitting).  Replaces the LAPACK potrf trailing update inside
+// cholesky(_symmetric(C)) (/root/reference/src/finite_gp_projection.jl:308) for fp64_mode = 1.
+//
+// Splitting.  Row i of P is scaled by 2^-e_i (e_i: exponent of the row maximum) to |x| < 1 and cut into
+// S signed 7-bit slices  x = sum_s q_s 2^-(7s-1),  q_s in [-64, 64]  -- every step exact in fp64.
+// Then  p_i . p_j = 2^(e_i+e_j) sum_d 2^(-7d-5) ACC_d[i,j],  ACC_d = sum_{s+t=d+1} q_s . q_t  (int32, exact);
+// diagonals d > S are dropped (relative 2^(-7S)).  S = 7 gives ~2^-49, S = 8 ~2^-56 of the row scale.
+//
+// Kernel (one CTA per 128 x 64 output tile, 192 threads):
+//   warp 0  TMA producer : per 64-byte k-block, S slices x (128 A rows + 64 B rows) -> smem (2 stages)
+//   warp 1  MMA issuer   : for A slice s one MMA against the STACK of B slices 1..S+1-s (they are
+//                          consecutive in smem, so N = (S+1-s)*64 and the products land in consecutive
+//                          TMEM column blocks d = s..S): S+ceil MMAs per 32-byte K chunk instead of S(S+1)/2
+//   warps 2-5 epilogue   : tcgen05.ld the S int32 accumulators, Horner-combine in fp64, scale, C -= ...
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "kernels.h"
+#include "umma_ozaki.h"
+
+namespace {
+
+constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KB = 64, OZ_STAGES = 2;
+
+// ---------------------------------------------------------------------------------------------
+// pre-pass 1: row exponents
+// ---------------------------------------------------------------------------------------------
+__global__ void ozaki_rowscale_kernel(const double* __restrict__ P, int64_t lda, int64_t m, int K, double* __restrict__ rscale,
+                                      double* __restrict__ rinv) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= m) return;
+  double mx = 0.0;
+  for (int k = 0; k < K; ++k) mx = fmax(mx, fabs(P[row + (int64_t)k * lda]));
+  int e = 0;
+  if (mx > 0.0 && isfinite(mx)) frexp(mx, &e);  // mx = f * 2^e, f in [0.5, 1)
+  rscale[row] = ldexp(1.0, e);
+  rinv[row] = ldexp(1.0, -e);
+}
+
+// pre-pass 2: error-free slicing, 16 consecutive k per thread -> one 16-byte store per slice
+template <int S>
+__global__ void ozaki_slice_kernel(const double* __restrict__ P, int64_t lda, int64_t m, int64_t m_fill, int64_t m_alloc,
+                                   int K, const double* __restrict__ rinv, int8_t* __restrict__ SL) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int k0 = blockIdx.y * 16;
+  if (row >= m_fill) return;
+  double r[16];
+  const double inv = (row < m) ? rinv[row] : 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = (row < m) ? P[row + (int64_t)(k0 + i) * lda] * inv : 0.0;
+  double up = 64.0, dn = 1.0 / 64.0;  // 2^(7s-1), 2^-(7s-1)
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    union { int8_t b[16]; uint4 v; } pk;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const double q = rint(r[i] * up);
+      r[i] = fma(-q, dn, r[i]);
+      pk.b[i] = (int8_t)(int)q;
+    }
+    *reinterpret_cast<uint4*>(SL + ((int64_t)s * m_alloc + row) * K + k0) = pk.v;
+    up *= 128.0;
+    dn *= (1.0 / 128.0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1u << 28)) __trap();  // turn a protocol bug into an error instead of a hang
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major operand tile, 64-byte swizzle: rows at 64 B pitch, 8-row groups at SBO = 512 B
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address  [0,14)
+  d |= (uint64_t)1 << 16;                         // LBO (ignored for swizzled K-major) [16,30)
+  d |= (uint64_t)(512 >> 4) << 32;                // SBO = 512 B  [32,46)
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)4 << 61;                         // layout type: SWIZZLE_64B
+  return d;
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct OzTileArgs {
+  double* C; int64_t ldc;
+  int64_t M, N;           // extent of C (rows of P used, columns updated)
+  int64_t m_alloc;        // row stride between slices in the slice buffer
+  int K;                  // bytes (= elements) per slice row
+  const double* rscale;   // 2^e per P row
+  int64_t b_tile_stride, b_off;  // column n of C <-> P row  (n / 128) * b_tile_stride + n % 128 + b_off  (0 stride = identity + b_off)
+  int lower_only;
+};
+
+template <int S>
+__global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_kernel(const __grid_constant__ CUtensorMap tmap, OzTileArgs a) {
+  constexpr int A_BYTES = OZ_BM * OZ_KB, B_BYTES = OZ_BN * OZ_KB;
+  constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[OZ_STAGES], empty_bar[OZ_STAGES], tmem_full_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * OZ_BM, n0 = (int64_t)blockIdx.y * OZ_BN;
+  const int64_t n_src0 = (a.b_tile_stride ? (n0 / 128) * a.b_tile_stride + (n0 % 128) : n0) + a.b_off;
+  if (a.lower_only && n_src0 >= m0 + OZ_BM) return;  // tile entirely above the diagonal (uniform exit)
+
+  // 1024-byte aligned carve-up (dynamic smem base alignment is only guaranteed to 16 B)
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+  auto a_tile = [&](int st, int sl) { return base + st * STAGE_BYTES + sl * A_BYTES; };
+  auto b_tile = [&](int st, int sl) { return base + st * STAGE_BYTES + S * A_BYTES + sl * B_BYTES; };
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < OZ_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int num_kb = a.K / OZ_KB;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int st = kb % OZ_STAGES;
+        const uint32_t ph = (kb / OZ_STAGES) & 1;
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+#pragma unroll 1
+        for (int sl = 0; sl < S; ++sl) {
+          const int rbase = (int)(sl * a.m_alloc);
+          tma_load_2d(a_tile(st, sl), &tmap, kb * OZ_KB, rbase + (int)m0, &full_bar[st]);
+          tma_load_2d(a_tile(st, sl) + 64 * OZ_KB, &tmap, kb * OZ_KB, rbase + (int)m0 + 64, &full_bar[st]);
+          tma_load_2d(b_tile(st, sl), &tmap, kb * OZ_KB, rbase + (int)n_src0, &full_bar[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D = S32 (c_format 2 @ bit 4), A/B = INT8 signed (1 @ bits 7, 10), K-major both,
+      // N>>3 @ bit 17, M>>4 @ bit 24
+      const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int st = kb % OZ_STAGES;
+        const uint32_t ph = (kb / OZ_STAGES) & 1;
+        mbar_wait(&full_bar[st], ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(a_tile(st, 0)), b0 = smem_u32(b_tile(st, 0));
+#pragma unroll
+        for (int kk = 0; kk < OZ_KB / 32; ++kk) {
+#pragma unroll 1
+          for (int sl = 0; sl < S; ++sl) {
+            const int Ns = (S - sl) * OZ_BN;  // B slices 1..S-sl stacked: columns d = sl .. S-1
+            const uint64_t adesc = umma_desc_sw64(a0 + sl * A_BYTES + kk * 32);
+            for (int c = 0; c < Ns; c += 256) {
+              const int nchunk = (Ns - c < 256) ? (Ns - c) : 256;
+              const uint64_t bdesc = umma_desc_sw64(b0 + c * OZ_KB + kk * 32);
+              const uint32_t idesc = idesc_base | ((uint32_t)(nchunk >> 3) << 17);
+              const uint32_t accum = (kb == 0 && kk == 0 && sl == 0) ? 0u : 1u;
+              umma_i8(tmem_base + (uint32_t)(sl * OZ_BN + c), adesc, bdesc, idesc, accum);
+            }
+          }
+        }
+        umma_commit(&empty_bar[st]);  // smem slot free once these MMAs have read it
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp&3) .. +31
+    const int quarter = warp & 3;
+    const int64_t row = m0 + 32 * quarter + lane;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    const bool row_ok = row < a.M;
+    const double rs = row_ok ? a.rscale[row] * (1.0 / 4096.0) : 0.0;  // 2^e_i * 2^-12
+#pragma unroll 1
+    for (int c = 0; c < OZ_BN; c += 16) {
+      double v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.0;
+#pragma unroll 1
+      for (int d = S - 1; d >= 0; --d) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(d * OZ_BN + c), r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fma(v[i], 1.0 / 128.0, (double)(int)r[i]);
+      }
+      if (row_ok) {
+        double cv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int64_t col = n0 + c + i;
+          cv[i] = (col < a.N) ? a.C[row + col * a.ldc] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int64_t col = n0 + c + i;
+          if (col < a.N) a.C[row + col * a.ldc] = fma(-v[i] * rs, a.rscale[n_src0 + c + i], cv[i]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+template <int S>
+void launch_syrk_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int lower_only, int64_t b_tile_stride,
+                   int64_t b_off, cudaStream_t s) {
+  const size_t smem = (size_t)OZ_STAGES * S * (OZ_BM * OZ_KB + OZ_BN * OZ_KB) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(umma_ozaki_syrk_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  OzTileArgs a{};
+  a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.m_alloc = ws.m_alloc; a.K = ws.K; a.rscale = ws.rscale;
+  a.b_tile_stride = b_tile_stride; a.b_off = b_off; a.lower_only = lower_only;
+  dim3 grid((unsigned)((M + OZ_BM - 1) / OZ_BM), (unsigned)((N + OZ_BN - 1) / OZ_BN));
+  umma_ozaki_syrk_kernel<S><<<grid, 192, smem, s>>>(ws.tmap, a);
+  agp_count_launch();
+}
+
+}  // namespace
+
+int ozaki_ws_create(OzakiWs* ws, int64_t max_rows, int K, int S, cudaStream_t s) {
+  memset(ws, 0, sizeof(*ws));
+  if (S < 5 || S > 8 || K % OZ_KB != 0) return 1;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return 2;
+  ws->m_alloc = (max_rows + 127) / 128 * 128;
+  ws->K = K; ws->S = S;
+  if (cudaMallocAsync((void**)&ws->SL, (size_t)S * ws->m_alloc * K, s) != cudaSuccess) return 3;
+  if (cudaMallocAsync((void**)&ws->rscale, (size_t)ws->m_alloc * 2 * sizeof(double), s) != cudaSuccess) return 3;
+  ws->rinv = ws->rscale + ws->m_alloc;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)((int64_t)S * ws->m_alloc)};
+  cuuint64_t gstr[1] = {(cuuint64_t)K};
+  cuuint32_t box[2] = {(cuuint32_t)OZ_KB, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&ws->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ws->SL, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 4;
+}
+
+void ozaki_ws_destroy(OzakiWs* ws, cudaStream_t s) {
+  if (ws->SL) cudaFreeAsync(ws->SL, s);
+  if (ws->rscale) cudaFreeAsync(ws->rscale, s);
+  memset(ws, 0, sizeof(*ws));
+}
+
+void ozaki_prepare(const OzakiWs& ws, const double* P, int64_t lda, int64_t m, cudaStream_t s) {
+  if (m <= 0) return;
+  ozaki_rowscale_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(P, lda, m, ws.K, ws.rscale, ws.rinv);
+  agp_count_launch();
+  const int64_t m_used = (m + 127) / 128 * 128;  // zero-fill up to the tile edge
+  dim3 grid((unsigned)((m_used + 127) / 128), (unsigned)(ws.K / 16));
+  switch (ws.S) {
+    case 5: ozaki_slice_kernel<5><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL); break;
+    case 6: ozaki_slice_kernel<6><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL); break;
+    case 7: ozaki_slice_kernel<7><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL); break;
+    default: ozaki_slice_kernel<8><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL); break;
+  }
+  agp_count_launch();
+}
+
+void ozaki_syrk(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int lower_only, int64_t b_tile_stride,
+                int64_t b_off, cudaStream_t s) {
+  if (M <= 0 || N <= 0) return;
+  switch (ws.S) {
+    case 5: launch_syrk_S<5>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, s); break;
+    case 6: launch_syrk_S<6>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, s); break;
+    case 7: launch_syrk_S<7>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, s); break;
+    default: launch_syrk_S<8>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, s); break;
+  }
+}

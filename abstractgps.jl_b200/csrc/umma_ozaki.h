@@ -1,0 +1,24 @@
+// umma_ozaki.h -- host interface of the tcgen05 int8-sliced (Ozaki) fp64 trailing update
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct OzakiWs {
+  int8_t* SL;       // S slices, each m_alloc rows x K bytes (K-major), slice s at row s*m_alloc
+  double* rscale;   // 2^e_i per panel row
+  double* rinv;     // 2^-e_i
+  int64_t m_alloc;  // rows per slice (multiple of 128)
+  int K;            // panel width (bytes per slice row), multiple of 64
+  int S;            // number of 7-bit slices (5..8)
+  CUtensorMap tmap; // 2-D uint8 tensor (K, S*m_alloc), box 64 B x 64 rows, 64-byte swizzle
+};
+
+int ozaki_ws_create(OzakiWs* ws, int64_t max_rows, int K, int S, cudaStream_t s);  // 0 = ok
+void ozaki_ws_destroy(OzakiWs* ws, cudaStream_t s);
+// slice the panel P (m x K fp64, column-major, lda) into ws
+void ozaki_prepare(const OzakiWs& ws, const double* P, int64_t lda, int64_t m, cudaStream_t s);
+// C (M x N, ldc) -= P P'  using the slices in ws; column n of C pairs with panel row
+// (n/128)*b_tile_stride + n%128 + b_off  (b_tile_stride = 0: n + b_off); lower_only skips tiles above the diagonal
+void ozaki_syrk(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int lower_only, int64_t b_tile_stride,
+                int64_t b_off, cudaStream_t s);

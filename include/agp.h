@@ -166,6 +166,11 @@ int32_t agp_vfe_mean_var(agp_vfe_post* p, int32_t layout, const void* Xs, int64_
                          void* mean_out, void* var_out);
 int32_t agp_vfe_post_free(agp_vfe_post* p);
 
+/* ---- test hook for the tcgen05 int8-sliced fp64 trailing update (csrc/umma_ozaki.cu): DEVICE pointers;
+ * C (M x N, ldc, fp64) -= P P' (lower tiles when lower_only), P = M x K fp64 (lda), S in 5..8 slices. */
+int32_t agp_debug_ozaki_syrk(agp_ctx* ctx, void* C_dev, int64_t ldc, const void* P_dev, int64_t lda, int64_t M,
+                             int64_t N, int32_t K, int32_t S, int32_t lower_only);
+
 /* ---- host-only helpers of the 2D block-cyclic tile map (no GPU needed; used by the CPU
  * world_size-2 tests): owner rank of tile (i,j) on a P x Q grid and local tile counts. */
 int32_t agp_bc_owner(int32_t ti, int32_t tj, int32_t grid_p, int32_t grid_q);
