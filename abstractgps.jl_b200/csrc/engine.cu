@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -40,6 +41,9 @@ struct agp_ctx {
   int profile = 1;
   int rank = 0, nranks = 1, grid_p = 1, grid_q = 1;
   ncclComm_t nccl = nullptr;
+  OzakiWs oz{};            // slice workspace of the tcgen05 fp64 path (cached across fits of the same shape)
+  int64_t oz_rows = 0;
+  int oz_S = 7;
 };
 
 struct agp_post {
@@ -175,17 +179,26 @@ static cudaEvent_t dep_event(agp_ctx* ctx, size_t i) {
 // passes over C and is what the tensor-core trailing kernels need to be compute-bound).
 template <typename T>
 void trailing_update(agp_ctx* ctx, T* L, int64_t lda, int64_t row0, int64_t col0, int64_t kcol0, int64_t K,
-                     int64_t M, int64_t N, cudaStream_t st) {
+                     int64_t M, int64_t N, cudaStream_t st, const OzakiWs* oz = nullptr, int64_t oz_row0 = 0) {
   // C = L[row0.., col0..] (M x N, diagonal-anchored iff row0 == col0) -= L[row0.., kcol0..] * L[col0.., kcol0..]'
   if (M <= 0 || N <= 0) return;
-  GemmArgs u{};
-  u.A = L + row0 + kcol0 * lda; u.lda = lda;
-  u.B = L + col0 + kcol0 * lda; u.ldb = lda;
-  u.C = L + row0 + col0 * lda; u.ldc = lda;
-  u.M = M; u.N = N; u.K = K; u.alpha_neg = 1; u.beta_one = 1; u.lower_only = 1;
-  if (row0 != col0) { u.b_tile_stride = TILE; u.b_off = col0 - row0; }  // lower-only test relative to row0
   if (ctx->profile) cudaEventRecord(prof_event(ctx), st);
-  launch_gemm<T>(u, st);
+  bool done = false;
+  if constexpr (std::is_same<T, double>::value) {
+    if (oz) {  // tcgen05 int8-sliced path: the slices of panel rows [oz_row0, ...) are already in *oz
+      ozaki_syrk(*oz, L + row0 + col0 * lda, lda, M, N, 1, 0, col0 - oz_row0, row0 - oz_row0, st);
+      done = true;
+    }
+  }
+  if (!done) {
+    GemmArgs u{};
+    u.A = L + row0 + kcol0 * lda; u.lda = lda;
+    u.B = L + col0 + kcol0 * lda; u.ldb = lda;
+    u.C = L + row0 + col0 * lda; u.ldc = lda;
+    u.M = M; u.N = N; u.K = K; u.alpha_neg = 1; u.beta_one = 1; u.lower_only = 1;
+    if (row0 != col0) { u.b_tile_stride = TILE; u.b_off = col0 - row0; }  // lower-only test relative to row0
+    launch_gemm<T>(u, st);
+  }
   if (ctx->profile) cudaEventRecord(prof_event(ctx), st);
 }
 
@@ -196,6 +209,15 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
   const int nblk = (int)(n_pad / TILE);
   int G = ctx->cfg.tile_nb / TILE;
   if (G < 1) G = 1;
+  if constexpr (std::is_same<T, double>::value) {
+    if (ctx->cfg.fp64_mode == 1 && nblk > 2 * G) {  // (re)size the slice workspace of the tcgen05 path
+      if (!ctx->oz.SL || ctx->oz.K != G * TILE || ctx->oz_rows < rows_total || ctx->oz.S != ctx->oz_S) {
+        if (ctx->oz.SL) ozaki_ws_destroy(&ctx->oz, s);
+        if (ozaki_ws_create(&ctx->oz, rows_total, G * TILE, ctx->oz_S, s) == 0) ctx->oz_rows = rows_total;
+        else { memset(&ctx->oz, 0, sizeof(ctx->oz)); ctx->oz_rows = 0; }
+      }
+    }
+  }
   const bool la = ctx->cfg.lookahead != 0 && nblk > 2 * G;
   bool rest_pending = false;
   size_t ev_idx = 0, last_rest = 0;
@@ -219,20 +241,27 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
     const int64_t cols_trail = n_pad - t0;
     if (cols_trail <= 0) continue;
     const int64_t K = (int64_t)(g_end - ko) * TILE, kc0 = (int64_t)ko * TILE;
+    const OzakiWs* oz = nullptr;
+    if constexpr (std::is_same<T, double>::value) {
+      // tcgen05 path: needs the full outer-panel width it was sized for and enough trailing work to pay for slicing
+      if (ctx->cfg.fp64_mode == 1 && ctx->oz.SL && K == ctx->oz.K && cols_trail >= 2 * TILE) oz = &ctx->oz;
+    }
     if (!la) {
-      trailing_update<T>(ctx, L, lda, t0, t0, kc0, K, rows_total - t0, cols_trail, s);
+      if constexpr (std::is_same<T, double>::value) { if (oz) ozaki_prepare(*oz, L + t0 + kc0 * lda, lda, rows_total - t0, s); }
+      trailing_update<T>(ctx, L, lda, t0, t0, kc0, K, rows_total - t0, cols_trail, s, oz, t0);
       continue;
     }
     cudaEvent_t e_panel = dep_event(ctx, ev_idx++), e_rest = dep_event(ctx, ev_idx++);
+    if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, last_rest), 0);  // also frees the slice buffer
+    if constexpr (std::is_same<T, double>::value) { if (oz) ozaki_prepare(*oz, L + t0 + kc0 * lda, lda, rows_total - t0, s); }
     cudaEventRecord(e_panel, s);
-    if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, last_rest), 0);
     const int64_t next_cols = (cols_trail < (int64_t)G * TILE) ? cols_trail : (int64_t)G * TILE;
-    trailing_update<T>(ctx, L, lda, t0, t0, kc0, K, rows_total - t0, next_cols, s);  // next outer panel first
+    trailing_update<T>(ctx, L, lda, t0, t0, kc0, K, rows_total - t0, next_cols, s, oz, t0);  // next outer panel first
     rest_pending = false;
     if (cols_trail > next_cols) {
       const int64_t r0 = t0 + next_cols;
       cudaStreamWaitEvent(s2, e_panel, 0);
-      trailing_update<T>(ctx, L, lda, r0, r0, kc0, K, rows_total - r0, n_pad - r0, s2);
+      trailing_update<T>(ctx, L, lda, r0, r0, kc0, K, rows_total - r0, n_pad - r0, s2, oz, t0);
       cudaEventRecord(e_rest, s2);
       rest_pending = true;
       last_rest = ev_idx - 1;
@@ -1199,6 +1228,8 @@ int32_t agp_init(agp_ctx** out, int32_t device, const agp_config* cfg) {
   ctx->cfg.lookahead = env_int("AGP_LOOKAHEAD", cfg ? ctx->cfg.lookahead : 1);
   ctx->cfg.use_graph = env_int("AGP_GRAPH", ctx->cfg.use_graph);
   ctx->profile = env_int("AGP_PROFILE", 1);
+  ctx->oz_S = env_int("AGP_OZAKI_S", 7);
+  if (ctx->oz_S < 5 || ctx->oz_S > 8) ctx->oz_S = 7;
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
@@ -1219,6 +1250,7 @@ int32_t agp_destroy(agp_ctx* ctx) {
   for (int i = 0; i < 8; ++i) cudaEventDestroy(ctx->ev[i]);
   for (auto e : ctx->prof_ev) cudaEventDestroy(e);
   for (auto e : ctx->dep_ev) cudaEventDestroy(e);
+  if (ctx->oz.SL) ozaki_ws_destroy(&ctx->oz, ctx->stream);
   if (ctx->nccl) ncclCommDestroy(ctx->nccl);
   cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
@@ -1324,7 +1356,7 @@ int32_t agp_debug_ozaki_syrk(agp_ctx* ctx, void* C_dev, int64_t ldc, const void*
   int rc = ozaki_ws_create(&ws, M, K, S, ctx->stream);
   if (rc) { ctx->err = "ozaki_ws_create failed (code " + std::to_string(rc) + ")"; return rc == 1 ? AGP_ERR_INVALID : AGP_ERR_CUDA; }
   ozaki_prepare(ws, (const double*)P_dev, lda, M, ctx->stream);
-  ozaki_syrk(ws, (double*)C_dev, ldc, M, N, lower_only, 0, 0, ctx->stream);
+  ozaki_syrk(ws, (double*)C_dev, ldc, M, N, lower_only, 0, 0, 0, ctx->stream);
   ozaki_ws_destroy(&ws, ctx->stream);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e == cudaSuccess) e = cudaGetLastError();

@@ -140,6 +140,7 @@ struct OzTileArgs {
   int K;                  // bytes (= elements) per slice row
   const double* rscale;   // 2^e per P row
   int64_t b_tile_stride, b_off;  // column n of C <-> P row  (n / 128) * b_tile_stride + n % 128 + b_off  (0 stride = identity + b_off)
+  int64_t a_off;                 // row r of C <-> P row r + a_off
   int lower_only;
 };
 
@@ -154,7 +155,8 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_kernel(const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = (int64_t)blockIdx.x * OZ_BM, n0 = (int64_t)blockIdx.y * OZ_BN;
   const int64_t n_src0 = (a.b_tile_stride ? (n0 / 128) * a.b_tile_stride + (n0 % 128) : n0) + a.b_off;
-  if (a.lower_only && n_src0 >= m0 + OZ_BM) return;  // tile entirely above the diagonal (uniform exit)
+  const int64_t m_src0 = m0 + a.a_off;
+  if (a.lower_only && n_src0 >= m_src0 + OZ_BM) return;  // tile entirely above the diagonal (uniform exit)
 
   // 1024-byte aligned carve-up (dynamic smem base alignment is only guaranteed to 16 B)
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
@@ -186,8 +188,8 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_kernel(const __grid_co
 #pragma unroll 1
         for (int sl = 0; sl < S; ++sl) {
           const int rbase = (int)(sl * a.m_alloc);
-          tma_load_2d(a_tile(st, sl), &tmap, kb * OZ_KB, rbase + (int)m0, &full_bar[st]);
-          tma_load_2d(a_tile(st, sl) + 64 * OZ_KB, &tmap, kb * OZ_KB, rbase + (int)m0 + 64, &full_bar[st]);
+          tma_load_2d(a_tile(st, sl), &tmap, kb * OZ_KB, rbase + (int)m_src0, &full_bar[st]);
+          tma_load_2d(a_tile(st, sl) + 64 * OZ_KB, &tmap, kb * OZ_KB, rbase + (int)m_src0 + 64, &full_bar[st]);
           tma_load_2d(b_tile(st, sl), &tmap, kb * OZ_KB, rbase + (int)n_src0, &full_bar[st]);
         }
       }
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_kernel(const __grid_co
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     const bool row_ok = row < a.M;
-    const double rs = row_ok ? a.rscale[row] * (1.0 / 4096.0) : 0.0;  // 2^e_i * 2^-12
+    const double rs = row_ok ? a.rscale[row + a.a_off] * (1.0 / 4096.0) : 0.0;  // 2^e_i * 2^-12
 #pragma unroll 1
     for (int c = 0; c < OZ_BN; c += 16) {
       double v[16];
@@ -282,7 +284,7 @@ EncodeTiledFn get_encode() {
 
 template <int S>
 void launch_syrk_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int lower_only, int64_t b_tile_stride,
-                   int64_t b_off, cudaStream_t s) {
+                   int64_t b_off, int64_t a_off, cudaStream_t s) {
   const size_t smem = (size_t)OZ_STAGES * S * (OZ_BM * OZ_KB + OZ_BN * OZ_KB) + 1024;
   static bool configured = false;
   if (!configured) {
@@ -291,7 +293,7 @@ void launch_syrk_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t
   }
   OzTileArgs a{};
   a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.m_alloc = ws.m_alloc; a.K = ws.K; a.rscale = ws.rscale;
-  a.b_tile_stride = b_tile_stride; a.b_off = b_off; a.lower_only = lower_only;
+  a.b_tile_stride = b_tile_stride; a.b_off = b_off; a.a_off = a_off; a.lower_only = lower_only;
   dim3 grid((unsigned)((M + OZ_BM - 1) / OZ_BM), (unsigned)((N + OZ_BN - 1) / OZ_BN));
   umma_ozaki_syrk_kernel<S><<<grid, 192, smem, s>>>(ws.tmap, a);
   agp_count_launch();
@@ -340,12 +342,12 @@ void ozaki_prepare(const OzakiWs& ws, const double* P, int64_t lda, int64_t m, c
 }
 
 void ozaki_syrk(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int lower_only, int64_t b_tile_stride,
-                int64_t b_off, cudaStream_t s) {
+                int64_t b_off, int64_t a_off, cudaStream_t s) {
   if (M <= 0 || N <= 0) return;
   switch (ws.S) {
-    case 5: launch_syrk_S<5>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, s); break;
-    case 6: launch_syrk_S<6>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, s); break;
-    case 7: launch_syrk_S<7>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, s); break;
-    default: launch_syrk_S<8>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, s); break;
+    case 5: launch_syrk_S<5>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, a_off, s); break;
+    case 6: launch_syrk_S<6>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, a_off, s); break;
+    case 7: launch_syrk_S<7>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, a_off, s); break;
+    default: launch_syrk_S<8>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, a_off, s); break;
   }
 }

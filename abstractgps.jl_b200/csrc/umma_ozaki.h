@@ -19,6 +19,7 @@ void ozaki_ws_destroy(OzakiWs* ws, cudaStream_t s);
 // slice the panel P (m x K fp64, column-major, lda) into ws
 void ozaki_prepare(const OzakiWs& ws, const double* P, int64_t lda, int64_t m, cudaStream_t s);
 // C (M x N, ldc) -= P P'  using the slices in ws; column n of C pairs with panel row
-// (n/128)*b_tile_stride + n%128 + b_off  (b_tile_stride = 0: n + b_off); lower_only skips tiles above the diagonal
+// (n/128)*b_tile_stride + n%128 + b_off  (b_tile_stride = 0: n + b_off), row r of C with panel row r + a_off;
+// lower_only skips tiles above the diagonal
 void ozaki_syrk(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int lower_only, int64_t b_tile_stride,
-                int64_t b_off, cudaStream_t s);
+                int64_t b_off, int64_t a_off, cudaStream_t s);
