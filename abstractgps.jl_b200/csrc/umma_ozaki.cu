@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "kernels.h"
@@ -267,6 +268,192 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_kernel(const __grid_co
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2: PERSISTENT, fully overlapped variant for the diagonal-anchored lower-triangular update
+// (a_off == b_off, identity column map).  One CTA per SM walks the tile list (row-major over the lower
+// triangle, closed-form index -> (bi,bj)); the TMA producer streams 32-byte k-blocks (32 B swizzle,
+// 4-5 stages) continuously ACROSS tiles, so the loads of tile t+1 run under the epilogue of tile t; the
+// MMA warp re-arms as soon as the epilogue has drained TMEM (tmem_empty barrier).  The epilogue issues all
+// S accumulator loads of a 16-column chunk before one wait and streams C with .cs loads/stores so the
+// int8 slices stay L2-resident.
+// ---------------------------------------------------------------------------------------------
+constexpr int V2_KB = 32;
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;  // SBO = 8 rows x 32 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;           // SWIZZLE_32B
+  return d;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ double ld_cs(const double* p) {
+  double v;
+  asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_cs(double* p, double v) { asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+
+// tile index -> (bi, bj): row tile bi (128 rows) owns column tiles 0 .. min(nbj, 2*bi+2)-1
+__device__ __forceinline__ void v2_tile(int64_t t, int nbj, int& bi, int& bj) {
+  const int64_t B = nbj / 2;            // row tiles with the unclipped count 2*bi+2
+  const int64_t t_full = B * (B + 1);
+  if (t < t_full) {
+    int64_t b = (int64_t)((sqrt(4.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((b + 1) * (b + 2) <= t) ++b;
+    while (b * (b + 1) > t) --b;
+    bi = (int)b;
+    bj = (int)(t - b * (b + 1));
+  } else {
+    const int64_t r = t - t_full;
+    bi = (int)(B + r / nbj);
+    bj = (int)(r % nbj);
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid_constant__ CUtensorMap tmapA,
+                                                                    const __grid_constant__ CUtensorMap tmapB, OzTileArgs a,
+                                                                    int64_t ntiles, int nbj) {
+  constexpr int A_BYTES = OZ_BM * V2_KB, B_BYTES = OZ_BN * V2_KB;
+  constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
+  constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+  auto a_tile = [&](int st, int sl) { return base + st * STAGE_BYTES + sl * A_BYTES; };
+  auto b_tile = [&](int st, int sl) { return base + st * STAGE_BYTES + S * A_BYTES + sl * B_BYTES; };
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    mbar_init(&tmem_empty_bar, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int num_kb = a.K / V2_KB;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int bi, bj;
+        v2_tile(t, nbj, bi, bj);
+        const int arow = (int)(bi * OZ_BM + a.a_off), brow = (int)(bj * OZ_BN + a.b_off);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int st = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+#pragma unroll 1
+          for (int sl = 0; sl < S; ++sl) {
+            const int rbase = (int)(sl * a.m_alloc);
+            tma_load_2d(a_tile(st, sl), &tmapA, kb * V2_KB, rbase + arow, &full_bar[st]);
+            tma_load_2d(b_tile(st, sl), &tmapB, kb * V2_KB, rbase + brow, &full_bar[st]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+      uint32_t it = 0, lt = 0;
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+        mbar_wait(&tmem_empty_bar, (lt & 1) ^ 1);  // epilogue has drained the previous tile's accumulators
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int st = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[st], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(a_tile(st, 0)), b0 = smem_u32(b_tile(st, 0));
+#pragma unroll 1
+          for (int sl = 0; sl < S; ++sl) {
+            const int Ns = (S - sl) * OZ_BN;
+            const uint64_t adesc = umma_desc_sw32(a0 + sl * A_BYTES);
+            for (int c = 0; c < Ns; c += 256) {
+              const int nchunk = (Ns - c < 256) ? (Ns - c) : 256;
+              const uint64_t bdesc = umma_desc_sw32(b0 + c * V2_KB);
+              const uint32_t idesc = idesc_base | ((uint32_t)(nchunk >> 3) << 17);
+              umma_i8(tmem_base + (uint32_t)(sl * OZ_BN + c), adesc, bdesc, idesc, (kb == 0 && sl == 0) ? 0u : 1u);
+            }
+          }
+          umma_commit(&empty_bar[st]);
+        }
+        umma_commit(&tmem_full_bar);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    uint32_t lt = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      int bi, bj;
+      v2_tile(t, nbj, bi, bj);
+      const int64_t m0 = (int64_t)bi * OZ_BM, n0 = (int64_t)bj * OZ_BN;
+      const int64_t row = m0 + 32 * quarter + lane;
+      const bool row_ok = row < a.M;
+      const double rs = row_ok ? a.rscale[row + a.a_off] * (1.0 / 4096.0) : 0.0;
+      double* crow = a.C + row;
+      mbar_wait(&tmem_full_bar, lt & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < OZ_BN; c += 16) {
+        uint32_t r[S][16];
+#pragma unroll
+        for (int d = 0; d < S; ++d)
+          tmem_ld16_nowait(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(d * OZ_BN + c), r[d]);
+        double cv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int64_t col = n0 + c + i;
+          cv[i] = (row_ok && col < a.N) ? ld_cs(crow + col * a.ldc) : 0.0;
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c + 16 >= OZ_BN) {  // last TMEM read of this tile: hand the accumulators back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar);
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            double v = (double)(int)r[S - 1][i];
+#pragma unroll
+            for (int d = S - 2; d >= 0; --d) v = fma(v, 1.0 / 128.0, (double)(int)r[d][i]);
+            const int64_t col = n0 + c + i;
+            if (col < a.N) st_cs(crow + col * a.ldc, fma(-v * rs, a.rscale[n0 + a.b_off + c + i], cv[i]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -283,8 +470,37 @@ EncodeTiledFn get_encode() {
 }
 
 template <int S>
+void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int64_t off, cudaStream_t s) {
+  constexpr int STAGE_BYTES = S * (OZ_BM * V2_KB + OZ_BN * V2_KB);
+  constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+  static bool configured = false;
+  static int nsm = 148;
+  if (!configured) {
+    cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  OzTileArgs a{};
+  a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.m_alloc = ws.m_alloc; a.K = ws.K; a.rscale = ws.rscale;
+  a.b_tile_stride = 0; a.b_off = off; a.a_off = off; a.lower_only = 1;
+  const int nbi = (int)((M + OZ_BM - 1) / OZ_BM), nbj = (int)(N / OZ_BN);
+  const int64_t B = nbj / 2;
+  int64_t ntiles = (nbi <= B) ? (int64_t)nbi * (nbi + 1) : B * (B + 1) + (int64_t)(nbi - B) * nbj;
+  const int grid = (int)(ntiles < nsm ? ntiles : nsm);
+  umma_ozaki_syrk_v2_kernel<S><<<grid, 192, smem, s>>>(ws.tmapA32, ws.tmapB32, a, ntiles, nbj);
+  agp_count_launch();
+}
+
+template <int S>
 void launch_syrk_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int lower_only, int64_t b_tile_stride,
                    int64_t b_off, int64_t a_off, cudaStream_t s) {
+  if (ws.use_v2 && lower_only && b_tile_stride == 0 && a_off == b_off && N % 128 == 0 && N >= 128) {
+    launch_syrk_v2_S<S>(ws, C, ldc, M, N, a_off, s);
+    return;
+  }
   const size_t smem = (size_t)OZ_STAGES * S * (OZ_BM * OZ_KB + OZ_BN * OZ_KB) + 1024;
   static bool configured = false;
   if (!configured) {
@@ -317,7 +533,17 @@ int ozaki_ws_create(OzakiWs* ws, int64_t max_rows, int K, int S, cudaStream_t s)
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(&ws->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ws->SL, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : 4;
+  if (r != CUDA_SUCCESS) return 4;
+  cuuint32_t boxA[2] = {(cuuint32_t)V2_KB, (cuuint32_t)OZ_BM}, boxB[2] = {(cuuint32_t)V2_KB, (cuuint32_t)OZ_BN};
+  r = enc(&ws->tmapA32, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ws->SL, gdim, gstr, boxA, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return 4;
+  r = enc(&ws->tmapB32, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ws->SL, gdim, gstr, boxB, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return 4;
+  const char* v = getenv("AGP_OZAKI_V2");
+  ws->use_v2 = v ? atoi(v) : 1;
+  return 0;
 }
 
 void ozaki_ws_destroy(OzakiWs* ws, cudaStream_t s) {

@@ -11,7 +11,9 @@ struct OzakiWs {
   int64_t m_alloc;  // rows per slice (multiple of 128)
   int K;            // panel width (bytes per slice row), multiple of 64
   int S;            // number of 7-bit slices (5..8)
-  CUtensorMap tmap; // 2-D uint8 tensor (K, S*m_alloc), box 64 B x 64 rows, 64-byte swizzle
+  CUtensorMap tmap; // 2-D uint8 tensor (K, S*m_alloc), box 64 B x 64 rows, 64-byte swizzle (v1 kernel)
+  CUtensorMap tmapA32, tmapB32;  // same tensor, 32 B x 128 / 64 rows, 32-byte swizzle (persistent v2 kernel)
+  int use_v2;
 };
 
 int ozaki_ws_create(OzakiWs* ws, int64_t max_rows, int K, int S, cudaStream_t s);  // 0 = ok

@@ -53,3 +53,16 @@ def test_ozaki_lower_only_leaves_upper_tiles(ag):
     low = (j // 64) * 64 < (i // 128) * 128 + 128   # tiles the kernel owns
     assert np.allclose(got[low], want[low], rtol=0, atol=1e-9)
     assert np.array_equal(got[~low], c0[~low])       # tiles entirely above the diagonal are untouched
+
+
+@pytest.mark.parametrize("N,K,S", [(128, 128, 7), (1024, 256, 7), (2048, 512, 8), (2176, 512, 6)])
+def test_ozaki_persistent_lower_with_border(ag, N, K, S):
+    """the persistent (v2) kernel on the shape the Cholesky uses: M = N + 128 border rows, lower tiles only"""
+    got, want, c0, rmax = _run(ag, N + 128, N, K, S, lower=True, seed=3)
+    i, j = np.indices(got.shape)
+    low = (j // 64) * 64 < (i // 128) * 128 + 128
+    scale = np.outer(rmax, rmax[:N]) * K
+    tol = {8: 1e-15, 7: 2e-13, 6: 3e-11}[S]
+    bound = tol * scale + 4e-16 * (np.abs(c0) + np.abs(want) + scale)
+    assert np.all(np.abs(got - want)[low] <= bound[low]), float((np.abs(got - want) / bound)[low].max())
+    assert np.array_equal(got[~low], c0[~low])
