@@ -186,7 +186,7 @@ void trailing_update(agp_ctx* ctx, T* L, int64_t lda, int64_t row0, int64_t col0
   bool done = false;
   if constexpr (std::is_same<T, double>::value) {
     if (oz) {  // tcgen05 int8-sliced path: the slices of panel rows [oz_row0, ...) are already in *oz
-      ozaki_syrk(*oz, L + row0 + col0 * lda, lda, M, N, 1, 0, col0 - oz_row0, row0 - oz_row0, st);
+      ozaki_syrk(*oz, L + row0 + col0 * lda, lda, M, N, 1, 0, 0, col0 - oz_row0, row0 - oz_row0, st);
       done = true;
     }
   }
@@ -202,15 +202,53 @@ void trailing_update(agp_ctx* ctx, T* L, int64_t lda, int64_t row0, int64_t col0
   if (ctx->profile) cudaEventRecord(prof_event(ctx), st);
 }
 
+// resolve the outer panel width (in 128-blocks) and the fp64 trailing-update engine for a problem size:
+// explicit config / env wins; "auto" = tcgen05 int8-sliced path with 512-wide panels from n_pad >= 8192
+static int resolve_G(const agp_ctx* ctx, int64_t n_pad) {
+  int nb = ctx->cfg.tile_nb;
+  if (nb <= 0) nb = (n_pad >= 8192) ? 512 : TILE;
+  int G = nb / TILE;
+  return G < 1 ? 1 : G;
+}
+static int resolve_fp64_mode(const agp_ctx* ctx, int64_t n_pad) {
+  if (ctx->cfg.fp64_mode >= 0) return ctx->cfg.fp64_mode;
+  return n_pad >= 8192 ? 1 : 0;
+}
+
+// factor one outer panel in place: Lp points at its diagonal element; Gp inner 128-blocks; rows = rows from the
+// panel's first row to the end of the (local) column storage (border rows included)
+template <typename T>
+void factor_panel(agp_ctx* ctx, T* Lp, int64_t lda, int Gp, int64_t rows, T* Dinv_p, double* logdet_part, int blk_base,
+                  int* info, cudaStream_t s) {
+  for (int g = 0; g < Gp; ++g) {
+    T* Akk = Lp + (int64_t)g * TILE + (int64_t)g * TILE * lda;
+    launch_potrf_diag<T>(Akk, lda, Dinv_p + (int64_t)g * TILE * TILE, logdet_part, blk_base + g, info, s);
+    const int64_t rows_below = rows - (int64_t)(g + 1) * TILE;
+    if (rows_below <= 0) continue;
+    GemmArgs t{};  // A21 <- A21 * inv(L11)'
+    t.A = Akk + TILE; t.lda = lda; t.B = Dinv_p + (int64_t)g * TILE * TILE; t.ldb = TILE;
+    t.C = Akk + TILE; t.ldc = lda; t.M = rows_below; t.N = TILE; t.K = TILE;
+    launch_gemm<T>(t, s);
+    const int64_t ncols_in = (int64_t)(Gp - (g + 1)) * TILE;  // rank-128 update of the remaining inner columns
+    if (ncols_in > 0) {
+      GemmArgs u{};
+      u.A = Akk + TILE; u.lda = lda; u.B = Akk + TILE; u.ldb = lda;
+      u.C = Akk + TILE + (int64_t)TILE * lda; u.ldc = lda;
+      u.M = rows_below; u.N = ncols_in; u.K = TILE; u.alpha_neg = 1; u.beta_one = 1; u.lower_only = 1;
+      launch_gemm<T>(u, s);
+    }
+  }
+}
+
 template <typename T>
 void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t rows_total, T* Dinv,
                       double* logdet_part, int* info) {
   cudaStream_t s = ctx->stream, s2 = ctx->stream2;
   const int nblk = (int)(n_pad / TILE);
-  int G = ctx->cfg.tile_nb / TILE;
-  if (G < 1) G = 1;
+  const int G = resolve_G(ctx, n_pad);
+  const int fp64_mode = resolve_fp64_mode(ctx, n_pad);
   if constexpr (std::is_same<T, double>::value) {
-    if (ctx->cfg.fp64_mode == 1 && nblk > 2 * G) {  // (re)size the slice workspace of the tcgen05 path
+    if (fp64_mode == 1 && nblk > 2 * G) {  // (re)size the slice workspace of the tcgen05 path
       if (!ctx->oz.SL || ctx->oz.K != G * TILE || ctx->oz_rows < rows_total || ctx->oz.S != ctx->oz_S) {
         if (ctx->oz.SL) ozaki_ws_destroy(&ctx->oz, s);
         if (ozaki_ws_create(&ctx->oz, rows_total, G * TILE, ctx->oz_S, s) == 0) ctx->oz_rows = rows_total;
@@ -223,20 +261,8 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
   size_t ev_idx = 0, last_rest = 0;
   for (int ko = 0; ko < nblk; ko += G) {
     const int g_end = (ko + G < nblk) ? ko + G : nblk;  // inner blocks [ko, g_end)
-    for (int k = ko; k < g_end; ++k) {
-      T* Akk = L + (int64_t)k * TILE + (int64_t)k * TILE * lda;
-      launch_potrf_diag<T>(Akk, lda, Dinv + (int64_t)k * TILE * TILE, logdet_part, k, info, s);
-      const int64_t rows_below = rows_total - (int64_t)(k + 1) * TILE;
-      if (rows_below <= 0) continue;
-      T* A21 = Akk + TILE;
-      GemmArgs t{};  // A21 <- A21 * inv(L11)'
-      t.A = A21; t.lda = lda; t.B = Dinv + (int64_t)k * TILE * TILE; t.ldb = TILE;
-      t.C = A21; t.ldc = lda; t.M = rows_below; t.N = TILE; t.K = TILE;
-      launch_gemm<T>(t, s);
-      // rank-128 update of the remaining inner columns of this outer panel
-      const int64_t c0 = (int64_t)(k + 1) * TILE, ncols_in = (int64_t)(g_end - (k + 1)) * TILE;
-      if (ncols_in > 0) trailing_update<T>(ctx, L, lda, c0, c0, (int64_t)k * TILE, TILE, rows_total - c0, ncols_in, s);
-    }
+    factor_panel<T>(ctx, L + (int64_t)ko * TILE + (int64_t)ko * TILE * lda, lda, g_end - ko, rows_total - (int64_t)ko * TILE,
+                    Dinv + (int64_t)ko * TILE * TILE, logdet_part, ko, info, s);
     const int64_t t0 = (int64_t)g_end * TILE;           // first trailing row/column
     const int64_t cols_trail = n_pad - t0;
     if (cols_trail <= 0) continue;
@@ -244,7 +270,7 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
     const OzakiWs* oz = nullptr;
     if constexpr (std::is_same<T, double>::value) {
       // tcgen05 path: needs the full outer-panel width it was sized for and enough trailing work to pay for slicing
-      if (ctx->cfg.fp64_mode == 1 && ctx->oz.SL && K == ctx->oz.K && cols_trail >= 2 * TILE) oz = &ctx->oz;
+      if (fp64_mode == 1 && ctx->oz.SL && K == ctx->oz.K && cols_trail >= 2 * TILE) oz = &ctx->oz;
     }
     if (!la) {
       if constexpr (std::is_same<T, double>::value) { if (oz) ozaki_prepare(*oz, L + t0 + kc0 * lda, lda, rows_total - t0, s); }
@@ -1050,9 +1076,14 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
   CK(cudaSetDevice(ctx->device));
   Scratch sc(ctx);
   const int R = ctx->nranks, me = ctx->rank;
-  const int64_t n_pad = round_up(N, TILE), lda = n_pad + TILE;
-  const int nt = (int)(n_pad / TILE);
-  const int nloc = (nt - me + R - 1) / R;  // local column blocks: global j = lj * R + me
+  // distribution block = one OUTER panel of G inner 128-blocks (W columns): the owner factors it locally,
+  // one NCCL broadcast per outer panel, rank-W trailing updates
+  const int G = resolve_G(ctx, round_up(N, TILE));
+  const int64_t W = (int64_t)G * TILE;
+  const int64_t n_pad = round_up(N, W), lda = n_pad + TILE;
+  const int nto = (int)(n_pad / W), nt = (int)(n_pad / TILE);
+  const int nloc = (nto - me + R - 1) / R;  // local outer blocks: global jo = ljo * R + me
+  const int fp64_mode = resolve_fp64_mode(ctx, n_pad);
   prof_begin(ctx);
   CK(cudaEventRecord(ctx->ev[0], s));
   T *ard_d = nullptr, *mean_d = nullptr, *noise_d = nullptr, *Yd = nullptr, *Xt = nullptr;
@@ -1063,12 +1094,12 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
   rc = prep_points<T>(ctx, sc, k, ard_d, layout, X, N, n_pad, D, &Xt, false); if (rc) return rc;
   CK(cudaEventRecord(ctx->ev[1], s));
   void* tmp = nullptr;
-  CK(sc.alloc(&tmp, (size_t)lda * (nloc > 0 ? nloc : 1) * TILE * sizeof(T)));
+  CK(sc.alloc(&tmp, (size_t)lda * (nloc > 0 ? nloc : 1) * W * sizeof(T)));
   T* L = (T*)tmp;
-  CK(sc.alloc(&tmp, (size_t)(nloc > 0 ? nloc : 1) * TILE * TILE * sizeof(T)));
-  T* Dinv = (T*)tmp;  // inverse diagonal blocks of the LOCAL column blocks
-  CK(sc.alloc(&tmp, (size_t)2 * lda * TILE * sizeof(T)));
-  T* P[2] = {(T*)tmp, (T*)tmp + lda * TILE};  // double-buffered packed panels (rows_below x 128, ld = rows_below)
+  CK(sc.alloc(&tmp, (size_t)(nloc > 0 ? nloc : 1) * G * TILE * TILE * sizeof(T)));
+  T* Dinv = (T*)tmp;  // inverse diagonal blocks of the LOCAL 128-blocks
+  CK(sc.alloc(&tmp, (size_t)2 * lda * W * sizeof(T)));
+  T* P[2] = {(T*)tmp, (T*)tmp + lda * W};  // double-buffered packed panels (rows_below x W, ld = rows_below)
   CK(sc.alloc(&tmp, (size_t)(nt + TILE + 4) * sizeof(double)));
   double* dscal = (double*)tmp;  // [0..nt) logdet parts, [nt..nt+TILE) sqmahal, [nt+TILE] logdet
   CK(cudaMemsetAsync(dscal, 0, (size_t)(nt + TILE + 4) * sizeof(double), s));
@@ -1080,96 +1111,112 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
   CK(cudaMemsetAsync(rwork, 0, (size_t)(S + 1) * n_pad * sizeof(T), s));
   CK(sc.alloc(&tmp, (size_t)TILE * sizeof(T)));
   T* lp_d = (T*)tmp;
+  const OzakiWs* oz = nullptr;
+  if constexpr (std::is_same<T, double>::value) {
+    if (fp64_mode == 1 && nto > 2 && W % 64 == 0) {
+      if (!ctx->oz.SL || ctx->oz.K != W || ctx->oz_rows < lda || ctx->oz.S != ctx->oz_S) {
+        if (ctx->oz.SL) ozaki_ws_destroy(&ctx->oz, s);
+        if (ozaki_ws_create(&ctx->oz, lda, (int)W, ctx->oz_S, s) == 0) ctx->oz_rows = lda;
+        else { memset(&ctx->oz, 0, sizeof(ctx->oz)); ctx->oz_rows = 0; }
+      }
+      if (ctx->oz.SL) oz = &ctx->oz;
+    }
+  }
 
-  // ---- Gram: only the local column blocks, lower part, + border rows
+  // ---- Gram: only the local outer blocks, lower part, + border rows
   for (int lj = 0; lj < nloc; ++lj) {
-    const int64_t j = (int64_t)lj * R + me;
+    const int64_t jo = (int64_t)lj * R + me;
     GramParams gp{};
     fill_gram_params<T>(gp, k, 1, 1, N, N, noise, noise_d);
-    gp.diag_off = j * TILE;
-    T* col = L + (int64_t)lj * TILE * lda;
-    launch_gram<T>(Xt, Xt + j * TILE * D, n_pad, TILE, D, col, lda, gp, s);
-    launch_border_init_cols<T>(col, lda, n_pad, j * TILE, TILE, N, Yd, N, S, mean->kind, mean->c, mean_d, s);
+    gp.diag_off = jo * W;
+    T* col = L + (int64_t)lj * W * lda;
+    launch_gram<T>(Xt, Xt + jo * W * D, n_pad, W, D, col, lda, gp, s);
+    launch_border_init_cols<T>(col, lda, n_pad, jo * W, W, N, Yd, N, S, mean->kind, mean->c, mean_d, s);
   }
   CK(cudaEventRecord(ctx->ev[2], s));
 
   // ---- distributed right-looking Cholesky with look-ahead
-  auto local_first_after = [&](int kk) {  // first local block index whose global index > kk
+  auto local_first_after = [&](int kk) {  // first local outer block whose global index > kk
     int lj = (kk + 1 - me + R - 1) / R;
     if (lj < 0) lj = 0;
     while ((int64_t)lj * R + me <= kk) ++lj;
     return lj;
   };
-  auto trailing = [&](int kk, T* Pk, int lj_lo, int lj_hi, cudaStream_t st) {  // update local blocks [lj_lo, lj_hi)
+  auto trailing = [&](int kk, T* Pk, int lj_lo, int lj_hi, bool use_oz, cudaStream_t st) {  // local outer blocks [lj_lo, lj_hi)
     if (lj_lo >= lj_hi) return;
-    const int64_t rows_below = lda - (int64_t)(kk + 1) * TILE;
+    const int64_t rows_below = lda - (int64_t)(kk + 1) * W;
     const int64_t j0 = (int64_t)lj_lo * R + me;
-    GemmArgs u{};
-    u.A = Pk; u.lda = rows_below; u.B = Pk; u.ldb = rows_below;
-    u.C = L + (int64_t)(kk + 1) * TILE + (int64_t)lj_lo * TILE * lda; u.ldc = lda;
-    u.M = rows_below; u.N = (int64_t)(lj_hi - lj_lo) * TILE; u.K = TILE;
-    u.alpha_neg = 1; u.beta_one = 1; u.lower_only = 1;
-    u.b_tile_stride = (int64_t)R * TILE; u.b_off = (j0 - (kk + 1)) * TILE;
+    T* C = L + (int64_t)(kk + 1) * W + (int64_t)lj_lo * W * lda;
+    const int64_t Ncols = (int64_t)(lj_hi - lj_lo) * W, b_off = (j0 - (kk + 1)) * W;
     if (ctx->profile) cudaEventRecord(prof_event(ctx), st);
-    launch_gemm<T>(u, st);
+    bool done = false;
+    if constexpr (std::is_same<T, double>::value) {
+      if (use_oz) { ozaki_syrk(*oz, C, lda, rows_below, Ncols, 1, (int64_t)R * W, W, b_off, 0, st); done = true; }
+    }
+    if (!done) {
+      GemmArgs u{};
+      u.A = Pk; u.lda = rows_below; u.B = Pk; u.ldb = rows_below; u.C = C; u.ldc = lda;
+      u.M = rows_below; u.N = Ncols; u.K = W; u.alpha_neg = 1; u.beta_one = 1; u.lower_only = 1;
+      u.b_tile_stride = (int64_t)R * W; u.b_tile_width = W; u.b_off = b_off;
+      launch_gemm<T>(u, st);
+    }
     if (ctx->profile) cudaEventRecord(prof_event(ctx), st);
   };
   bool rest_pending = false;
-  for (int kk = 0; kk < nt; ++kk) {
+  size_t ev_idx = 0, last_rest = 0;
+  for (int kk = 0; kk < nto; ++kk) {
     const int owner = kk % R;
-    const int64_t rows_below = lda - (int64_t)(kk + 1) * TILE;
+    const int64_t rows_below = lda - (int64_t)(kk + 1) * W;
     T* Pk = P[kk & 1];
     if (owner == me) {
       const int lk = kk / R;
-      T* Akk = L + (int64_t)kk * TILE + (int64_t)lk * TILE * lda;
-      launch_potrf_diag<T>(Akk, lda, Dinv + (int64_t)lk * TILE * TILE, dscal, kk, dinfo, s);
-      GemmArgs t{};
-      t.A = Akk + TILE; t.lda = lda; t.B = Dinv + (int64_t)lk * TILE * TILE; t.ldb = TILE;
-      t.C = Akk + TILE; t.ldc = lda; t.M = rows_below; t.N = TILE; t.K = TILE;
-      launch_gemm<T>(t, s);
-      launch_copy2d<T>(Akk + TILE, lda, Pk, rows_below, rows_below, TILE, s);
+      T* Lp = L + (int64_t)kk * W + (int64_t)lk * W * lda;
+      factor_panel<T>(ctx, Lp, lda, G, lda - (int64_t)kk * W, Dinv + (int64_t)lk * G * TILE * TILE, dscal, kk * G, dinfo, s);
+      launch_copy2d<T>(Lp + W, lda, Pk, rows_below, rows_below, W, s);
     }
-    if (R > 1) CKN(ncclBroadcast(Pk, Pk, (size_t)rows_below * TILE, NcclType<T>::v, owner, ctx->nccl, s));
-    if (kk == nt - 1) break;
-    cudaEvent_t e_panel = dep_event(ctx, 2 * (size_t)kk), e_rest = dep_event(ctx, 2 * (size_t)kk + 1);
+    if (R > 1) CKN(ncclBroadcast(Pk, Pk, (size_t)rows_below * W, NcclType<T>::v, owner, ctx->nccl, s));
+    if (kk == nto - 1) break;
+    if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, last_rest), 0);  // frees P[(kk+1)&1] and the slice buffer
+    bool use_oz = false;
+    if constexpr (std::is_same<T, double>::value) {
+      if (oz && (int64_t)(nto - 1 - kk) * W >= 2 * TILE) {
+        ozaki_prepare(*oz, (const double*)Pk, rows_below, rows_below, s);
+        use_oz = true;
+      }
+    }
+    cudaEvent_t e_panel = dep_event(ctx, ev_idx++), e_rest = dep_event(ctx, ev_idx++);
     cudaEventRecord(e_panel, s);
-    // next panel column first (only its owner has it), on the main stream
     const int lj_first = local_first_after(kk);
     int lj_bulk = lj_first;
-    if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, 2 * (size_t)(kk - 1) + 1), 0);
-    if ((kk + 1) % R == me) {
-      trailing(kk, Pk, lj_first, lj_first + 1, s);
+    if ((kk + 1) % R == me) {  // next panel first (only its owner has it), on the main stream
+      trailing(kk, Pk, lj_first, lj_first + 1, use_oz, s);
       lj_bulk = lj_first + 1;
     }
-    rest_pending = false;
-    if (lj_bulk < nloc) {
-      cudaStreamWaitEvent(s2, e_panel, 0);
-      trailing(kk, Pk, lj_bulk, nloc, s2);
-      cudaEventRecord(e_rest, s2);
-      rest_pending = true;
-    } else {
-      cudaEventRecord(e_rest, s2);  // keep the event chain uniform
-      rest_pending = true;
-    }
+    cudaStreamWaitEvent(s2, e_panel, 0);
+    trailing(kk, Pk, lj_bulk, nloc, use_oz, s2);
+    cudaEventRecord(e_rest, s2);
+    rest_pending = true;
+    last_rest = ev_idx - 1;
   }
-  if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, 2 * (size_t)(nt - 2) + 1), 0);
+  if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, last_rest), 0);
   CK(cudaEventRecord(ctx->ev[3], s));
 
   // ---- v = border rows (distributed by column), sqmahal and logdet via all-reduce
   for (int lj = 0; lj < nloc; ++lj) {
-    const int64_t j = (int64_t)lj * R + me;
+    const int64_t jo = (int64_t)lj * R + me;
     for (int sI = 0; sI < S; ++sI)
-      launch_copy2d<T>(L + n_pad + sI + (int64_t)lj * TILE * lda, lda, rwork + (size_t)sI * n_pad + j * TILE, 1, 1, TILE, s);
+      launch_copy2d<T>(L + n_pad + sI + (int64_t)lj * W * lda, lda, rwork + (size_t)sI * n_pad + jo * W, 1, 1, W, s);
   }
   for (int sI = 0; sI < S; ++sI) launch_sumsq<T>(rwork + (size_t)sI * n_pad, n_pad, dscal + nt + sI, s);
   if (R > 1) CKN(ncclAllReduce(dscal, dscal, (size_t)(nt + TILE), ncclDouble, ncclSum, ctx->nccl, s));
-  // ---- distributed backward substitution for column 0: alpha = L^-T v
+  // ---- distributed backward substitution for column 0: alpha = L^-T v  (128-block granularity)
   for (int i = nt - 1; i >= 0; --i) {
-    const int owner = i % R;
+    const int io = i / G, owner = io % R;
     T* a_i = alpha + (int64_t)i * TILE;
-    if (owner == me) launch_bwd_diag<T>(Dinv + (int64_t)(i / R) * TILE * TILE, rwork + (int64_t)i * TILE, a_i, s);
+    if (owner == me)
+      launch_bwd_diag<T>(Dinv + ((int64_t)(io / R) * G + (i % G)) * TILE * TILE, rwork + (int64_t)i * TILE, a_i, s);
     if (R > 1) CKN(ncclBroadcast(a_i, a_i, TILE, NcclType<T>::v, owner, ctx->nccl, s));
-    if (i > 0) launch_bwd_update_local<T>(L, lda, i, a_i, rwork, nloc, me, R, s);
+    if (i > 0) launch_bwd_update_local<T>(L, lda, i, a_i, rwork, nloc * G, me, R, G, s);
   }
   launch_finalize_logpdf<T>(dscal, nt, dscal + nt, S, N, lp_d, dscal + nt + TILE, s);
   CK(cudaEventRecord(ctx->ev[4], s));
@@ -1221,9 +1268,9 @@ int32_t agp_init(agp_ctx** out, int32_t device, const agp_config* cfg) {
   agp_ctx* ctx = new agp_ctx();
   ctx->device = device;
   if (cfg) ctx->cfg = *cfg;
-  ctx->cfg.tile_nb = env_int("AGP_NB", (cfg && cfg->tile_nb > 0) ? cfg->tile_nb : TILE);
-  if (ctx->cfg.tile_nb < TILE || ctx->cfg.tile_nb % TILE) ctx->cfg.tile_nb = TILE;
-  ctx->cfg.fp64_mode = env_int("AGP_FP64_MODE", ctx->cfg.fp64_mode);
+  ctx->cfg.tile_nb = env_int("AGP_NB", (cfg && cfg->tile_nb > 0) ? cfg->tile_nb : 0);  // 0 = auto
+  if (ctx->cfg.tile_nb % TILE) ctx->cfg.tile_nb = 0;
+  ctx->cfg.fp64_mode = env_int("AGP_FP64_MODE", cfg ? ctx->cfg.fp64_mode : -1);            // -1 = auto
   ctx->cfg.fp32_mode = env_int("AGP_FP32_MODE", ctx->cfg.fp32_mode);
   ctx->cfg.lookahead = env_int("AGP_LOOKAHEAD", cfg ? ctx->cfg.lookahead : 1);
   ctx->cfg.use_graph = env_int("AGP_GRAPH", ctx->cfg.use_graph);
@@ -1356,7 +1403,7 @@ int32_t agp_debug_ozaki_syrk(agp_ctx* ctx, void* C_dev, int64_t ldc, const void*
   int rc = ozaki_ws_create(&ws, M, K, S, ctx->stream);
   if (rc) { ctx->err = "ozaki_ws_create failed (code " + std::to_string(rc) + ")"; return rc == 1 ? AGP_ERR_INVALID : AGP_ERR_CUDA; }
   ozaki_prepare(ws, (const double*)P_dev, lda, M, ctx->stream);
-  ozaki_syrk(ws, (double*)C_dev, ldc, M, N, lower_only, 0, 0, 0, ctx->stream);
+  ozaki_syrk(ws, (double*)C_dev, ldc, M, N, lower_only, 0, 0, 0, 0, ctx->stream);
   ozaki_ws_destroy(&ws, ctx->stream);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e == cudaSuccess) e = cudaGetLastError();

@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(32 * WM * WN, (WM * WN <= 4) ? 2 : 1) gemm_dmm
   constexpr int A_LD = TBM + 4, B_LD = TBN + 4;
   const int bi = blockIdx.x, bj = blockIdx.y;
   const int64_t m0 = (int64_t)bi * TBM, n0 = (int64_t)bj * TBN;
-  const int64_t n_src0 = g.b_tile_stride ? (n0 / 128) * g.b_tile_stride + (n0 % 128) + g.b_off : n0;
+  const int64_t bw = g.b_tile_width ? g.b_tile_width : 128;
+  const int64_t n_src0 = g.b_tile_stride ? (n0 / bw) * g.b_tile_stride + (n0 % bw) + g.b_off : n0;
   if (g.lower_only && n_src0 >= m0 + TBM) return;  // tile entirely above the diagonal
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
@@ -219,7 +220,8 @@ __global__ void __launch_bounds__(256, 2) gemm_simt_kernel(GemmArgs g) {
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int64_t m0 = (int64_t)bi * BM, n0 = (int64_t)bj * BN;
-  const int64_t n_src0 = g.b_tile_stride ? (n0 / 128) * g.b_tile_stride + (n0 % 128) + g.b_off : n0;
+  const int64_t bw = g.b_tile_width ? g.b_tile_width : 128;
+  const int64_t n_src0 = g.b_tile_stride ? (n0 / bw) * g.b_tile_stride + (n0 % bw) + g.b_off : n0;
   if (g.lower_only && n_src0 >= m0 + BM) return;
   B += (BKM ? (n_src0 - n0) * g.ldb : (n_src0 - n0));
   int64_t K = g.K;

@@ -38,6 +38,7 @@ struct GemmArgs {
   // block-cyclic column gather (multi-GPU trailing update): local column n of C takes its B rows from
   // n_src = (n / 128) * b_tile_stride + n % 128 + b_off; 0 = identity.  The lower-only test uses n_src.
   int64_t b_tile_stride, b_off;
+  int64_t b_tile_width;  // width of a distribution block in columns (0 -> 128)
 };
 
 template <typename T> void launch_prep_points(const T* X, int layout, int64_t n, int64_t n_pad, int D,
@@ -74,7 +75,7 @@ template <typename T> void launch_bwd_solve(const T* A, int64_t lda, const T* Di
 // distributed (column-cyclic) backward substitution pieces
 template <typename T> void launch_bwd_diag(const T* Dinv_i, const T* r_i, T* alpha_i, cudaStream_t s);
 template <typename T> void launch_bwd_update_local(const T* Lloc, int64_t lda, int i_blk, const T* alpha_i, T* r, int nloc,
-                                                   int rank, int nranks, cudaStream_t s);
+                                                   int rank, int nranks, int G, cudaStream_t s);
 // one step of the blocked forward substitution L v = r (in place), block k (used by extend / vfe)
 template <typename T> void launch_fwd_step(const T* A, int64_t lda, const T* Dinv, int k, int nblk, T* r,
                                            cudaStream_t s);

@@ -230,11 +230,12 @@ __global__ void __launch_bounds__(256) bwd_diag_kernel(const T* __restrict__ Din
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_update_local_kernel(const T* __restrict__ Lloc, int64_t lda, int i_blk,
                                                                 const T* __restrict__ alpha_i, T* __restrict__ r,
-                                                                int rank, int nranks) {
-  // CTA c handles local column block lj = c  (global j = lj*nranks + rank), only if j < i
+                                                                int rank, int nranks, int G) {
+  // CTA c handles local 128-column block lj = c; distribution blocks are G*128 columns wide:
+  // global 128-block j = ((lj / G) * nranks + rank) * G + lj % G; only j < i is touched
   __shared__ T ak[TB];
   const int lj = blockIdx.x;
-  const int64_t j = (int64_t)lj * nranks + rank;
+  const int64_t j = ((int64_t)(lj / G) * nranks + rank) * G + (lj % G);
   if (j >= i_blk) return;
   const int tid = threadIdx.x, o = tid >> 1, h = tid & 1;
   if (tid < TB) ak[tid] = alpha_i[tid];
@@ -662,19 +663,19 @@ void launch_bwd_diag(const T* Dinv_i, const T* r_i, T* alpha_i, cudaStream_t s) 
 }
 template <typename T>
 void launch_bwd_update_local(const T* Lloc, int64_t lda, int i_blk, const T* alpha_i, T* r, int nloc, int rank, int nranks,
-                             cudaStream_t s) {
+                             int G, cudaStream_t s) {
   if (nloc <= 0) return;
-  bwd_update_local_kernel<T><<<nloc, 256, 0, s>>>(Lloc, lda, i_blk, alpha_i, r, rank, nranks);
+  bwd_update_local_kernel<T><<<nloc, 256, 0, s>>>(Lloc, lda, i_blk, alpha_i, r, rank, nranks, G);
   agp_count_launch();
 }
 
 // explicit instantiations
 template void launch_border_init_cols<float>(float*, int64_t, int64_t, int64_t, int64_t, int64_t, const float*, int64_t, int, int, double, const float*, cudaStream_t);
 template void launch_bwd_diag<float>(const float*, const float*, float*, cudaStream_t);
-template void launch_bwd_update_local<float>(const float*, int64_t, int, const float*, float*, int, int, int, cudaStream_t);
+template void launch_bwd_update_local<float>(const float*, int64_t, int, const float*, float*, int, int, int, int, cudaStream_t);
 template void launch_border_init_cols<double>(double*, int64_t, int64_t, int64_t, int64_t, int64_t, const double*, int64_t, int, int, double, const double*, cudaStream_t);
 template void launch_bwd_diag<double>(const double*, const double*, double*, cudaStream_t);
-template void launch_bwd_update_local<double>(const double*, int64_t, int, const double*, double*, int, int, int, cudaStream_t);
+template void launch_bwd_update_local<double>(const double*, int64_t, int, const double*, double*, int, int, int, int, cudaStream_t);
 template void launch_sub_mean<float>(const float*, int64_t, int, double, const float*, float*, cudaStream_t);
 template void launch_sub_mean<double>(const double*, int64_t, int, double, const double*, double*, cudaStream_t);
 template void launch_gemv_n_acc<float>(const float*, int64_t, int64_t, int64_t, const float*, float*, cudaStream_t);

@@ -23,6 +23,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "kernels.h"
 #include "umma_ozaki.h"
 
@@ -142,6 +144,9 @@ struct OzTileArgs {
   const double* rscale;   // 2^e per P row
   int64_t b_tile_stride, b_off;  // column n of C <-> P row  (n / 128) * b_tile_stride + n % 128 + b_off  (0 stride = identity + b_off)
   int64_t a_off;                 // row r of C <-> P row r + a_off
+  int64_t b_tile_width;          // distribution block width in columns (0 -> 128)
+  const int64_t* strip_start;    // v2, block-cyclic: first tile index of every 64-column strip (nbj + 1 entries)
+  const int32_t* strip_bimin;    // v2, block-cyclic: first valid 128-row tile of every strip
   int lower_only;
 };
 
@@ -155,7 +160,8 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m0 = (int64_t)blockIdx.x * OZ_BM, n0 = (int64_t)blockIdx.y * OZ_BN;
-  const int64_t n_src0 = (a.b_tile_stride ? (n0 / 128) * a.b_tile_stride + (n0 % 128) : n0) + a.b_off;
+  const int64_t bw = a.b_tile_width ? a.b_tile_width : 128;
+  const int64_t n_src0 = (a.b_tile_stride ? (n0 / bw) * a.b_tile_stride + (n0 % bw) : n0) + a.b_off;
   const int64_t m_src0 = m0 + a.a_off;
   if (a.lower_only && n_src0 >= m_src0 + OZ_BM) return;  // tile entirely above the diagonal (uniform exit)
 
@@ -321,6 +327,29 @@ __device__ __forceinline__ void v2_tile(int64_t t, int nbj, int& bi, int& bj) {
   }
 }
 
+// table-driven variant for the block-cyclic (multi-GPU) trailing update: strips are 64 columns wide,
+// strip j owns tiles [start[j], start[j+1]) = row tiles bimin[j] ...
+__device__ __forceinline__ void v2_tile_tab(int64_t t, int nbj, const int64_t* __restrict__ start,
+                                            const int32_t* __restrict__ bimin, int& bi, int& bj) {
+  int lo = 0, hi = nbj;  // find the last j with start[j] <= t
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (start[mid] <= t) lo = mid; else hi = mid;
+  }
+  bj = lo;
+  bi = bimin[lo] + (int)(t - start[lo]);
+}
+__device__ __forceinline__ void v2_decode(const OzTileArgs& a, int64_t t, int nbj, int& bi, int& bj, int64_t& brow) {
+  if (a.strip_start) {
+    v2_tile_tab(t, nbj, a.strip_start, a.strip_bimin, bi, bj);
+    const int64_t n0 = (int64_t)bj * OZ_BN, bw = a.b_tile_width ? a.b_tile_width : 128;
+    brow = (n0 / bw) * a.b_tile_stride + (n0 % bw) + a.b_off;
+  } else {
+    v2_tile(t, nbj, bi, bj);
+    brow = (int64_t)bj * OZ_BN + a.b_off;
+  }
+}
+
 template <int S>
 __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid_constant__ CUtensorMap tmapA,
                                                                     const __grid_constant__ CUtensorMap tmapB, OzTileArgs a,
@@ -357,8 +386,9 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
       uint32_t it = 0;
       for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int bi, bj;
-        v2_tile(t, nbj, bi, bj);
-        const int arow = (int)(bi * OZ_BM + a.a_off), brow = (int)(bj * OZ_BN + a.b_off);
+        int64_t brow64;
+        v2_decode(a, t, nbj, bi, bj, brow64);
+        const int arow = (int)(bi * OZ_BM + a.a_off), brow = (int)brow64;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int st = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -407,7 +437,8 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
     uint32_t lt = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
       int bi, bj;
-      v2_tile(t, nbj, bi, bj);
+      int64_t brow64;
+      v2_decode(a, t, nbj, bi, bj, brow64);
       const int64_t m0 = (int64_t)bi * OZ_BM, n0 = (int64_t)bj * OZ_BN;
       const int64_t row = m0 + 32 * quarter + lane;
       const bool row_ok = row < a.M;
@@ -440,7 +471,7 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
 #pragma unroll
             for (int d = S - 2; d >= 0; --d) v = fma(v, 1.0 / 128.0, (double)(int)r[d][i]);
             const int64_t col = n0 + c + i;
-            if (col < a.N) st_cs(crow + col * a.ldc, fma(-v * rs, a.rscale[n0 + a.b_off + c + i], cv[i]));
+            if (col < a.N) st_cs(crow + col * a.ldc, fma(-v * rs, a.rscale[brow64 + c + i], cv[i]));
           }
         }
       }
@@ -470,7 +501,8 @@ EncodeTiledFn get_encode() {
 }
 
 template <int S>
-void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int64_t off, cudaStream_t s) {
+void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int64_t b_tile_stride,
+                      int64_t b_tile_width, int64_t b_off, int64_t a_off, cudaStream_t s) {
   constexpr int STAGE_BYTES = S * (OZ_BM * V2_KB + OZ_BN * V2_KB);
   constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
@@ -485,10 +517,35 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
   }
   OzTileArgs a{};
   a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.m_alloc = ws.m_alloc; a.K = ws.K; a.rscale = ws.rscale;
-  a.b_tile_stride = 0; a.b_off = off; a.a_off = off; a.lower_only = 1;
+  a.b_tile_stride = b_tile_stride; a.b_tile_width = b_tile_width; a.b_off = b_off; a.a_off = a_off; a.lower_only = 1;
   const int nbi = (int)((M + OZ_BM - 1) / OZ_BM), nbj = (int)(N / OZ_BN);
-  const int64_t B = nbj / 2;
-  int64_t ntiles = (nbi <= B) ? (int64_t)nbi * (nbi + 1) : B * (B + 1) + (int64_t)(nbi - B) * nbj;
+  int64_t ntiles = 0;
+  if (b_tile_stride == 0 && a_off == b_off) {  // diagonal-anchored: closed-form enumeration
+    const int64_t B = nbj / 2;
+    ntiles = (nbi <= B) ? (int64_t)nbi * (nbi + 1) : B * (B + 1) + (int64_t)(nbi - B) * nbj;
+  } else {  // block-cyclic column map: per-strip table (host -> device, a few KB)
+    std::vector<int64_t> start((size_t)nbj + 1);
+    std::vector<int32_t> bimin((size_t)nbj);
+    const int64_t bw = b_tile_width ? b_tile_width : 128;
+    for (int j = 0; j < nbj; ++j) {
+      const int64_t n0 = (int64_t)j * OZ_BN;
+      const int64_t nsrc = (b_tile_stride ? (n0 / bw) * b_tile_stride + (n0 % bw) : n0) + b_off;
+      int64_t bm = (nsrc - a_off) >= 0 ? (nsrc - a_off) / OZ_BM : 0;  // first row tile with nsrc < a_off + bi*128 + 128
+      if (bm > nbi) bm = nbi;
+      bimin[j] = (int32_t)bm;
+      start[j] = ntiles;
+      ntiles += nbi - bm;
+    }
+    start[nbj] = ntiles;
+    const int slot = (ws.tab_slot++) & 1;  // the main- and side-stream updates of one step are in flight together
+    int64_t* d_start = ws.tab_start + (size_t)slot * (ws.tab_cap + 1);
+    int32_t* d_bimin = ws.tab_bimin + (size_t)slot * (ws.tab_cap + 1);
+    cudaMemcpyAsync(d_start, start.data(), ((size_t)nbj + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_bimin, bimin.data(), (size_t)nbj * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+    a.strip_start = d_start;
+    a.strip_bimin = d_bimin;
+  }
+  if (ntiles <= 0) return;
   const int grid = (int)(ntiles < nsm ? ntiles : nsm);
   umma_ozaki_syrk_v2_kernel<S><<<grid, 192, smem, s>>>(ws.tmapA32, ws.tmapB32, a, ntiles, nbj);
   agp_count_launch();
@@ -496,9 +553,9 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
 
 template <int S>
 void launch_syrk_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int lower_only, int64_t b_tile_stride,
-                   int64_t b_off, int64_t a_off, cudaStream_t s) {
-  if (ws.use_v2 && lower_only && b_tile_stride == 0 && a_off == b_off && N % 128 == 0 && N >= 128) {
-    launch_syrk_v2_S<S>(ws, C, ldc, M, N, a_off, s);
+                   int64_t b_tile_width, int64_t b_off, int64_t a_off, cudaStream_t s) {
+  if (ws.use_v2 && lower_only && N % 128 == 0 && N >= 128 && N / OZ_BN <= ws.tab_cap) {
+    launch_syrk_v2_S<S>(ws, C, ldc, M, N, b_tile_stride, b_tile_width, b_off, a_off, s);
     return;
   }
   const size_t smem = (size_t)OZ_STAGES * S * (OZ_BM * OZ_KB + OZ_BN * OZ_KB) + 1024;
@@ -509,7 +566,7 @@ void launch_syrk_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t
   }
   OzTileArgs a{};
   a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.m_alloc = ws.m_alloc; a.K = ws.K; a.rscale = ws.rscale;
-  a.b_tile_stride = b_tile_stride; a.b_off = b_off; a.a_off = a_off; a.lower_only = lower_only;
+  a.b_tile_stride = b_tile_stride; a.b_tile_width = b_tile_width; a.b_off = b_off; a.a_off = a_off; a.lower_only = lower_only;
   dim3 grid((unsigned)((M + OZ_BM - 1) / OZ_BM), (unsigned)((N + OZ_BN - 1) / OZ_BN));
   umma_ozaki_syrk_kernel<S><<<grid, 192, smem, s>>>(ws.tmap, a);
   agp_count_launch();
@@ -527,6 +584,9 @@ int ozaki_ws_create(OzakiWs* ws, int64_t max_rows, int K, int S, cudaStream_t s)
   if (cudaMallocAsync((void**)&ws->SL, (size_t)S * ws->m_alloc * K, s) != cudaSuccess) return 3;
   if (cudaMallocAsync((void**)&ws->rscale, (size_t)ws->m_alloc * 2 * sizeof(double), s) != cudaSuccess) return 3;
   ws->rinv = ws->rscale + ws->m_alloc;
+  ws->tab_cap = (int)(ws->m_alloc / OZ_BN) + 2;
+  if (cudaMallocAsync((void**)&ws->tab_start, (size_t)2 * (ws->tab_cap + 1) * sizeof(int64_t), s) != cudaSuccess) return 3;
+  if (cudaMallocAsync((void**)&ws->tab_bimin, (size_t)2 * (ws->tab_cap + 1) * sizeof(int32_t), s) != cudaSuccess) return 3;
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)((int64_t)S * ws->m_alloc)};
   cuuint64_t gstr[1] = {(cuuint64_t)K};
   cuuint32_t box[2] = {(cuuint32_t)OZ_KB, 64};
@@ -549,6 +609,8 @@ int ozaki_ws_create(OzakiWs* ws, int64_t max_rows, int K, int S, cudaStream_t s)
 void ozaki_ws_destroy(OzakiWs* ws, cudaStream_t s) {
   if (ws->SL) cudaFreeAsync(ws->SL, s);
   if (ws->rscale) cudaFreeAsync(ws->rscale, s);
+  if (ws->tab_start) cudaFreeAsync(ws->tab_start, s);
+  if (ws->tab_bimin) cudaFreeAsync(ws->tab_bimin, s);
   memset(ws, 0, sizeof(*ws));
 }
 
@@ -568,12 +630,12 @@ void ozaki_prepare(const OzakiWs& ws, const double* P, int64_t lda, int64_t m, c
 }
 
 void ozaki_syrk(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int lower_only, int64_t b_tile_stride,
-                int64_t b_off, int64_t a_off, cudaStream_t s) {
+                int64_t b_tile_width, int64_t b_off, int64_t a_off, cudaStream_t s) {
   if (M <= 0 || N <= 0) return;
   switch (ws.S) {
-    case 5: launch_syrk_S<5>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, a_off, s); break;
-    case 6: launch_syrk_S<6>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, a_off, s); break;
-    case 7: launch_syrk_S<7>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, a_off, s); break;
-    default: launch_syrk_S<8>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_off, a_off, s); break;
+    case 5: launch_syrk_S<5>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_tile_width, b_off, a_off, s); break;
+    case 6: launch_syrk_S<6>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_tile_width, b_off, a_off, s); break;
+    case 7: launch_syrk_S<7>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_tile_width, b_off, a_off, s); break;
+    default: launch_syrk_S<8>(ws, C, ldc, M, N, lower_only, b_tile_stride, b_tile_width, b_off, a_off, s); break;
   }
 }

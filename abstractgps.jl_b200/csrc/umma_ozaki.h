@@ -14,6 +14,10 @@ struct OzakiWs {
   CUtensorMap tmap; // 2-D uint8 tensor (K, S*m_alloc), box 64 B x 64 rows, 64-byte swizzle (v1 kernel)
   CUtensorMap tmapA32, tmapB32;  // same tensor, 32 B x 128 / 64 rows, 32-byte swizzle (persistent v2 kernel)
   int use_v2;
+  int64_t* tab_start;  // device tables of the block-cyclic tile enumeration (v2), two slots of tab_cap+1 entries:
+  int32_t* tab_bimin;  // consecutive calls (main / side stream) alternate slots
+  int tab_cap;
+  mutable int tab_slot;
 };
 
 int ozaki_ws_create(OzakiWs* ws, int64_t max_rows, int K, int S, cudaStream_t s);  // 0 = ok
@@ -24,4 +28,4 @@ void ozaki_prepare(const OzakiWs& ws, const double* P, int64_t lda, int64_t m, c
 // (n/128)*b_tile_stride + n%128 + b_off  (b_tile_stride = 0: n + b_off), row r of C with panel row r + a_off;
 // lower_only skips tiles above the diagonal
 void ozaki_syrk(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int lower_only, int64_t b_tile_stride,
-                int64_t b_off, int64_t a_off, cudaStream_t s);
+                int64_t b_tile_width, int64_t b_off, int64_t a_off, cudaStream_t s);
