@@ -33,7 +33,8 @@ class agp_noise(C.Structure):
 
 class agp_config(C.Structure):
     _fields_ = [("tile_nb", C.c_int32), ("fp64_mode", C.c_int32), ("fp32_mode", C.c_int32),
-                ("lookahead", C.c_int32), ("use_graph", C.c_int32), ("reserved", C.c_int32 * 11)]
+                ("lookahead", C.c_int32), ("use_graph", C.c_int32), ("ozaki_slices", C.c_int32),
+                ("profile_kernels", C.c_int32), ("reserved", C.c_int32 * 9)]
 
 
 # every symbol include/agp.h declares: name -> (restype, argtypes)
@@ -48,6 +49,8 @@ SIGNATURES = {
     "agp_last_error": (C.c_char_p, [_P]),
     "agp_last_info": (C.c_int64, [_P]),
     "agp_set_memspace": (C.c_int32, [_P, C.c_int32]),
+    "agp_set_config": (C.c_int32, [_P, C.POINTER(agp_config)]),
+    "agp_get_config": (C.c_int32, [_P, C.POINTER(agp_config)]),
     "agp_version": (C.c_char_p, []),
     "agp_last_timings": (C.c_int32, [_P, C.POINTER(C.c_double), C.c_int32]),
     "agp_launch_count": (C.c_int64, [_P]),

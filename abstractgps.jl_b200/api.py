@@ -258,6 +258,18 @@ class Engine:
     def set_memspace(self, m):
         self.check(self.L.agp_set_memspace(self.h, m))
 
+    def get_config(self):
+        c = cabi.agp_config()
+        self.check(self.L.agp_get_config(self.h, C.byref(c)))
+        return c
+
+    def set_config(self, **kw):
+        """tile_nb / fp64_mode / lookahead / ozaki_slices of the live context"""
+        c = self.get_config()
+        for k_, v in kw.items():
+            setattr(c, k_, v)
+        self.check(self.L.agp_set_config(self.h, C.byref(c)))
+
 
 _engine = None
 

@@ -1274,8 +1274,8 @@ int32_t agp_init(agp_ctx** out, int32_t device, const agp_config* cfg) {
   ctx->cfg.fp32_mode = env_int("AGP_FP32_MODE", ctx->cfg.fp32_mode);
   ctx->cfg.lookahead = env_int("AGP_LOOKAHEAD", cfg ? ctx->cfg.lookahead : 1);
   ctx->cfg.use_graph = env_int("AGP_GRAPH", ctx->cfg.use_graph);
-  ctx->profile = env_int("AGP_PROFILE", 1);
-  ctx->oz_S = env_int("AGP_OZAKI_S", 7);
+  ctx->profile = env_int("AGP_PROFILE", cfg ? cfg->profile_kernels : 0);
+  ctx->oz_S = env_int("AGP_OZAKI_S", (cfg && cfg->ozaki_slices) ? cfg->ozaki_slices : 7);
   if (ctx->oz_S < 5 || ctx->oz_S > 8) ctx->oz_S = 7;
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
@@ -1310,6 +1310,23 @@ int64_t agp_last_info(const agp_ctx* ctx) { return ctx ? ctx->info : 0; }
 int32_t agp_set_memspace(agp_ctx* ctx, int32_t m) {
   if (!ctx || (m != AGP_MEM_HOST && m != AGP_MEM_DEVICE)) return AGP_ERR_INVALID;
   ctx->memspace = m;
+  return AGP_OK;
+}
+int32_t agp_set_config(agp_ctx* ctx, const agp_config* cfg) {
+  if (!ctx || !cfg) return AGP_ERR_INVALID;
+  if (cfg->tile_nb < 0 || cfg->tile_nb % TILE) return AGP_ERR_INVALID;
+  ctx->cfg.tile_nb = cfg->tile_nb;
+  ctx->cfg.fp64_mode = cfg->fp64_mode;
+  ctx->cfg.lookahead = cfg->lookahead;
+  ctx->profile = cfg->profile_kernels;
+  if (cfg->ozaki_slices >= 5 && cfg->ozaki_slices <= 8) { ctx->cfg.ozaki_slices = cfg->ozaki_slices; ctx->oz_S = cfg->ozaki_slices; }
+  return AGP_OK;
+}
+int32_t agp_get_config(const agp_ctx* ctx, agp_config* out) {
+  if (!ctx || !out) return AGP_ERR_INVALID;
+  *out = ctx->cfg;
+  out->ozaki_slices = ctx->oz_S;
+  out->profile_kernels = ctx->profile;
   return AGP_OK;
 }
 int32_t agp_last_timings(const agp_ctx* ctx, double* out, int32_t n) {

@@ -9,6 +9,8 @@
 // micro-panel that finishes it, then E row w -- so all 128 workers (x2 column-parity halves) stay busy.
 // Phase A: every thread factors the 8x8 diagonal block redundantly in registers (no shuffles, no
 // barrier on the sqrt chain) and substitutes its own row; phase B: rank-8 trailing update of its row.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "agp.h"
 
@@ -400,6 +402,262 @@ potrf_diag_kernel_f64(double* __restrict__ A, int64_t lda, double* __restrict__ 
   __syncthreads();
   if (tid == 0) logdet_part[blk] = red[0] + red[1] + red[2] + red[3];
 }
+
+// ------------------------------------------------------------------------------------------------
+// Split variant (default for fp64): the inverse is 2/3 of the rank-8 update work and half of the
+// write-back, and its rows are independent of each other -- so the factorisation kernel does the S rows
+// only (one CTA, on the critical path) and the inverse is produced by 8 CTAs in parallel, CTA p owning the
+// E row-groups p and 15-p (balanced: the early groups sweep many column groups, the late ones few).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+potrf_factor_only_f64(double* __restrict__ A, int64_t lda, double* __restrict__ logdet_part, int blk, int* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* arr = reinterpret_cast<double*>(smem_raw);
+  double* XS = arr + PB * PLD;
+  double* Ld = XS + PB * XLD;
+  double* rinv_s = Ld + 64;
+  double* dinv = rinv_s + 8;
+  __shared__ double red[4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int b0 = 0; b0 < 64; b0 += 16) {
+    double tmp[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * (b0 + u);
+      const int c = idx >> 7, i = idx & 127;
+      tmp[u] = (i >= c) ? __ldg(A + i + (int64_t)c * lda) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * (b0 + u);
+      arr[(idx >> 7) * PLD + (idx & 127)] = tmp[u];
+    }
+  }
+  __syncthreads();
+  for (int j0 = 0; j0 < PB; j0 += 8) {
+    const int J = j0 >> 3;
+    const int w = tid;
+    const bool is_s = (tid < PB) && (w >= j0 + 8);
+    const bool is_diag = (tid < PB) && (w >= j0) && (w < j0 + 8);
+    double a[8];
+    if (is_s) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[c] = arr[(j0 + c) * PLD + w];
+    }
+    if (warp == 0) {
+      double d[8][8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) d[r][c] = arr[(j0 + c) * PLD + j0 + r];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        double piv = d[c][c];
+        if (!(piv > 0.0)) {
+          if (lane == 0) atomicCAS(info, 0, blk * PB + j0 + c + 1);
+          piv = 1.0;
+        }
+        const double r = dev_rsqrt_refined<double>(piv);
+        if (lane == 0) rinv_s[c] = r;
+        d[c][c] = piv * r;
+#pragma unroll
+        for (int r2 = c + 1; r2 < 8; ++r2) d[r2][c] *= r;
+#pragma unroll
+        for (int c2 = c + 1; c2 < 8; ++c2)
+#pragma unroll
+          for (int r2 = c2; r2 < 8; ++r2) d[r2][c2] -= d[r2][c] * d[c2][c];
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int c = 0; c <= r; ++c) Ld[r * 8 + c] = d[r][c];
+      }
+    }
+    __syncthreads();
+    if (is_s) {
+      double x[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        double sacc = a[c];
+#pragma unroll
+        for (int c2 = 0; c2 < c; ++c2) sacc -= x[c2] * Ld[c * 8 + c2];
+        x[c] = sacc * rinv_s[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { XS[w * XLD + c] = x[c]; arr[(j0 + c) * PLD + w] = x[c]; }
+    } else if (is_diag) {
+      const int cr = w - j0;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c <= cr) arr[(j0 + c) * PLD + w] = Ld[cr * 8 + c];
+      dinv[w] = rinv_s[cr];
+    }
+    __syncthreads();
+    {  // rank-8 update of the S rows only: warp wi owns row-groups wi and 15-wi
+#pragma unroll
+      for (int sel = 0; sel < 2; ++sel) {
+        const int rg = sel ? (15 - warp) : warp;
+        if (rg <= J) continue;
+        const int kg_lo = J + 1, kg_hi = rg;
+        const int r0 = rg * 8;
+        const double a0 = -XS[(r0 + gq) * XLD + q], a1 = -XS[(r0 + gq) * XLD + 4 + q];
+        for (int kg = kg_lo; kg <= kg_hi; kg += 4) {
+          double b0[4], b1[4], c0[4], c1[4];
+          double* cp[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int kgu = min(kg + u, 15);
+            b0[u] = XS[(kgu * 8 + gq) * XLD + q];
+            b1[u] = XS[(kgu * 8 + gq) * XLD + 4 + q];
+            cp[u] = arr + (kgu * 8 + 2 * q) * PLD + r0 + gq;
+            c0[u] = cp[u][0];
+            c1[u] = cp[u][PLD];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dmma884(c0[u], c1[u], a0, b0[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dmma884(c0[u], c1[u], a1, b1[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int kgu = kg + u;
+            if (kgu <= kg_hi) {
+              const bool diag_tile = (kgu == rg);
+              if (!diag_tile || 2 * q <= gq) cp[u][0] = c0[u];
+              if (!diag_tile || 2 * q + 1 <= gq) cp[u][PLD] = c1[u];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int b0 = 0; b0 < 64; b0 += 16) {
+    double tmp[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * (b0 + u);
+      const int c = idx >> 7, i = idx & 127;
+      tmp[u] = (i >= c) ? arr[c * PLD + i] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * (b0 + u);
+      A[(idx & 127) + (int64_t)(idx >> 7) * lda] = tmp[u];
+    }
+  }
+  double part = 0.0;
+  if (tid < PB) part = -log(dinv[tid]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (tid < PB && (tid & 31) == 0) red[tid >> 5] = part;
+  __syncthreads();
+  if (tid == 0) logdet_part[blk] = red[0] + red[1] + red[2] + red[3];
+}
+
+// inverse of a factored 128x128 lower block: CTA p (of 8) produces the rows of L^-T (= columns of L^-1) of
+// the row-groups p and 15-p by the same bordered elimination, reading L from global memory.
+__global__ void __launch_bounds__(256, 1)
+trtri_strips_f64(const double* __restrict__ A, int64_t lda, double* __restrict__ Dinv) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* arr = reinterpret_cast<double*>(smem_raw);
+  double* XS = arr + PB * PLD;
+  double* dinv = XS + PB * XLD;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, q = lane & 3;
+  const int p = blockIdx.x;            // owns E row-groups p and 15 - p
+  const int ga = p, gb = 15 - p;
+#pragma unroll
+  for (int b0 = 0; b0 < 64; b0 += 16) {
+    double tmp[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * (b0 + u);
+      const int c = idx >> 7, i = idx & 127;
+      tmp[u] = (i >= c) ? __ldg(A + i + (int64_t)c * lda) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * (b0 + u);
+      arr[(idx >> 7) * PLD + (idx & 127)] = tmp[u];
+    }
+  }
+  __syncthreads();
+  if (tid < PB) dinv[tid] = 1.0 / arr[tid * PLD + tid];
+  __syncthreads();
+  for (int j0 = ga * 8; j0 < PB; j0 += 8) {  // group ga becomes active at its own micro-panel
+    const int J = j0 >> 3;
+    const int w = tid;
+    if (tid < PB) {
+      const int rgw = w >> 3;
+      if (w >= j0 + 8) {  // S row: expose its (already final) micro-panel entries as the B operand
+#pragma unroll
+        for (int c = 0; c < 8; ++c) XS[w * XLD + c] = arr[(j0 + c) * PLD + w];
+      } else if ((rgw == ga || rgw == gb) && rgw <= J) {  // one of my E rows, already started
+        double a[8], x[8];
+        if (w >= j0) {
+          const int cr = w - j0;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a[c] = (c == cr) ? 1.0 : 0.0;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a[c] = arr[(j0 + c) * PLD + w];
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          double sacc = a[c];
+#pragma unroll
+          for (int c2 = 0; c2 < c; ++c2) sacc -= x[c2] * arr[(j0 + c2) * PLD + j0 + c];  // L_d(c, c2)
+          x[c] = sacc * dinv[j0 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          XS[w * XLD + c] = x[c];
+          if (j0 + c > w) arr[(j0 + c) * PLD + w] = x[c];
+        }
+      }
+    }
+    __syncthreads();
+    {  // E tiles: groups ga / gb (if started) x column groups J+1..15; warp wi: group by parity, 4 tiles
+      const int rg = (warp & 1) ? gb : ga;
+      if (rg <= J && J < 15) {
+        const int r0 = rg * 8;
+        const double a0 = -XS[(r0 + gq) * XLD + q], a1 = -XS[(r0 + gq) * XLD + 4 + q];
+        const int kg = J + 1 + (warp >> 1);
+        double b0[4], b1[4], c0[4], c1[4];
+        double* cp[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int kgu = min(kg + 4 * u, 15);
+          b0[u] = XS[(kgu * 8 + gq) * XLD + q];
+          b1[u] = XS[(kgu * 8 + gq) * XLD + 4 + q];
+          cp[u] = arr + (kgu * 8 + 2 * q) * PLD + r0 + gq;
+          c0[u] = cp[u][0];
+          c1[u] = cp[u][PLD];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dmma884(c0[u], c1[u], a0, b0[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dmma884(c0[u], c1[u], a1, b1[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (kg + 4 * u <= 15) { cp[u][0] = c0[u]; cp[u][PLD] = c1[u]; }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // my 16 columns of Dinv = L^-1 (column r <-> E row r)
+  for (int idx = tid; idx < 16 * PB; idx += 256) {
+    const int rr = idx >> 7, c = idx & 127;
+    const int r = (rr < 8) ? (ga * 8 + rr) : (gb * 8 + rr - 8);
+    const double v = (c > r) ? arr[c * PLD + r] : ((c == r) ? dinv[r] : 0.0);
+    Dinv[c + r * PB] = v;
+  }
+}
 }  // namespace
 
 template <typename T>
@@ -419,10 +677,21 @@ void launch_potrf_diag<double>(double* Ablk, int64_t lda, double* Dinv, double* 
                                cudaStream_t s) {
   const size_t smem = (size_t)(PB * PLD + PB * XLD + 64 + 8 + PB) * sizeof(double);
   static bool configured = false;
+  static int split = 1;
   if (!configured) {
     cudaFuncSetAttribute(potrf_diag_kernel_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(potrf_factor_only_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(trtri_strips_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const char* v = getenv("AGP_POTRF_SPLIT");
+    if (v) split = atoi(v);
     configured = true;
   }
-  potrf_diag_kernel_f64<<<1, 256, smem, s>>>(Ablk, lda, Dinv, logdet_part, blk, info);
+  if (split) {  // factor on one CTA (critical path), inverse on 8 CTAs
+    potrf_factor_only_f64<<<1, 256, smem, s>>>(Ablk, lda, logdet_part, blk, info);
+    trtri_strips_f64<<<8, 256, smem, s>>>(Ablk, lda, Dinv);
+    agp_count_launch();
+  } else {
+    potrf_diag_kernel_f64<<<1, 256, smem, s>>>(Ablk, lda, Dinv, logdet_part, blk, info);
+  }
   agp_count_launch();
 }

@@ -117,6 +117,26 @@ def blas_threads():
         return os.cpu_count()
 
 
+def best_cpu_threads(cfg):
+    """OpenBLAS with every hardware thread of a 128-thread host is often slower than with fewer on an
+    N=4096 potrf; give the CPU arm its best setting: try a few thread counts once, keep the fastest."""
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        return None, blas_threads()
+    cand = sorted({c for c in (8, 16, 32, 64, blas_threads()) if c <= (os.cpu_count() or 8)})
+    best, best_c = 1e18, cand[-1]
+    for c in cand:
+        with threadpool_limits(limits=c):
+            cpu_reference_step(cfg)  # warm
+            t0 = time.perf_counter()
+            cpu_reference_step(cfg)
+            dt = time.perf_counter() - t0
+        if dt < best:
+            best, best_c = dt, c
+    return threadpool_limits(limits=best_c), best_c
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -133,13 +153,13 @@ def run_reference(args, wl):
         sample = "N=%d sub-sample of %s scaled by (N/%d)^3 = %.1f (extrapolated)" % (sub, wl, sub, scale)
     else:
         scale = 1.0
+    limiter, cores = best_cpu_threads(cfg)
     for _ in range(args.warmup):
         cpu_reference_step(cfg)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_reference_step(cfg)
     ms = (time.perf_counter() - t0) * 1e3 / args.steps * scale
-    cores = blas_threads()
     line = {"impl": "reference", "metric": "ms to logpdf(fx,y)+posterior(fx,y)", "value": ms, "unit": "ms",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -259,18 +279,49 @@ def run_ours(args, wl):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    tf = trailing_flops(N)
-    trailing_ms = t_dev.get("trailing", 0.0)
-    achieved = tf / (trailing_ms * 1e-3) / 1e12 if trailing_ms > 0 else None
+    # ---- roofline of the dominant kernel (the trailing update).  Its launches are timed with CUDA events
+    # around every launch inside the library; the look-ahead schedule overlaps two of them on two streams,
+    # so the per-kernel time is taken in a pass with look-ahead OFF (serial launches), same inputs, same kernels.
+    cfg0 = eng.get_config()
+    eng.set_config(lookahead=0, profile_kernels=1)
+    t_serial, _, _ = timed(True, max(2, min(args.steps, 5)), 1)
+    eng.set_config(lookahead=cfg0.lookahead, profile_kernels=cfg0.profile_kernels)
+    n_pad = (N + 127) // 128 * 128
+    nb = cfg0.tile_nb if cfg0.tile_nb > 0 else (512 if n_pad >= 8192 else 128)
+    mode = cfg0.fp64_mode if cfg0.fp64_mode >= 0 else (1 if n_pad >= 8192 else 0)
+    S_sl = cfg0.ozaki_slices
+    outer = []  # (m, K) of every outer trailing update
+    t0 = 0
+    while t0 < n_pad:
+        K = min(nb, n_pad - t0)
+        t0 += K
+        if n_pad - t0 > 0:
+            outer.append((n_pad - t0, K))
+    tf = sum(2.0 * K * m * (m + 1) / 2 for m, K in outer)  # algorithmic fp64 flops of the outer trailing updates
+    trailing_ms = t_serial.get("trailing", 0.0)
+    fp64_eq = tf / (trailing_ms * 1e-3) / 1e12 if trailing_ms > 0 else None
     chol_tf = (N ** 3 / 3.0) / (t_dev["cholesky"] * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel<false,false> (trailing SYRK, lower tiles)",
-                "achieved": achieved, "peak": dgemm, "unit": "TFLOP/s", "frac": (achieved / dgemm) if achieved else None,
-                "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (fp64 has no entry in MEASURED_PEAKS.json); "
-                               "nominal B200 fp64 tensor = 40 TFLOP/s",
-                "frac_of_bf16_measured": (achieved / peaks["bf16_tflops"]) if (achieved and "bf16_tflops" in peaks) else None,
-                "launches_per_step": (N + 127) // 128 - 1, "alg_flops_per_step": tf,
-                "kernel_ms_per_step": trailing_ms, "traffic": None,
-                "cholesky_third_n3_tflops": chol_tf, "cholesky_frac_of_dgemm": chol_tf / dgemm}
+    if mode == 1:
+        pairs = S_sl * (S_sl + 1) // 2
+        int8_peak = 2.0 * peaks.get("bf16_tflops", 1590.0)  # int8 dense = 2x the measured bf16 GEMM rate (nominal 4.5 POP/s)
+        achieved = fp64_eq * pairs if fp64_eq else None      # executed int8 TOP/s: every fp64 MAC = S(S+1)/2 int8 MACs
+        roofline = {"bound": "tensor", "kernel": "umma_ozaki_syrk_v2_kernel<%d> (tcgen05.mma.kind::i8, TMA, TMEM; persistent)" % S_sl,
+                    "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8 tensor, dense)",
+                    "frac": (achieved / int8_peak) if achieved else None,
+                    "peak_source": "2 x bf16_tflops of MEASURED_PEAKS.json (%s); int8 kind runs at twice the bf16 rate (nominal 4.5 POP/s)"
+                                   % ("of measured" if "bf16_tflops" in peaks else "of fallback 1590"),
+                    "fp64_equivalent_tflops": fp64_eq, "fp64_equivalent_vs_cublas_dgemm": (fp64_eq / dgemm) if fp64_eq else None,
+                    "slices": S_sl, "int8_macs_per_fp64_mac": pairs}
+    else:
+        roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel<false,false,2,2> (DMMA mma.sync.m8n8k4.f64, lower tiles)",
+                    "achieved": fp64_eq, "peak": dgemm, "unit": "TFLOP/s (fp64)", "frac": (fp64_eq / dgemm) if fp64_eq else None,
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 entry); "
+                                   "DMMA microbenchmark on this pool: 37.0 TFLOP/s",
+                    "frac_of_bf16_measured": (fp64_eq / peaks["bf16_tflops"]) if (fp64_eq and "bf16_tflops" in peaks) else None}
+    roofline.update({"launches_per_step": len(outer), "alg_flops_per_step": tf, "kernel_ms_per_step": trailing_ms,
+                     "kernel_timing": "CUDA events around each launch, look-ahead off (serial), %d steps" % max(2, min(args.steps, 5)),
+                     "panel_width": nb, "traffic": None, "cublas_dgemm_tflops": dgemm,
+                     "cholesky_third_n3_tflops": chol_tf, "cholesky_frac_of_dgemm": chol_tf / dgemm})
 
     # CPU baseline (oracle port of the reference's LAPACK path) on this box's host cores, bounded sample
     cfg_cpu, scale, sample = cfg, 1.0, "full %s workload (N=%d), logpdf+posterior = 2 Gram + 2 dpotrf, best of 3" % (wl, N)
@@ -280,12 +331,14 @@ def run_ours(args, wl):
         cfg_cpu["X"], cfg_cpu["y"] = cfg["X"][:sub], cfg["y"][:sub]
         scale = (N / sub) ** 3
         sample = "N=%d sub-sample scaled by (N/%d)^3=%.0f (extrapolated)" % (sub, sub, scale)
+    limiter, cpu_cores = best_cpu_threads(cfg_cpu)
     best = 1e18
     for _ in range(3):
         t0 = time.perf_counter()
         cpu_reference_step(cfg_cpu)
         best = min(best, time.perf_counter() - t0)
-    cpu = {"value": best * 1e3 * scale, "unit": "ms", "cores": blas_threads(), "kind": "port", "sample": sample}
+    cpu = {"value": best * 1e3 * scale, "unit": "ms", "cores": cpu_cores, "kind": "port",
+           "sample": sample + "; BLAS threads = fastest of {8,16,32,64,all}"}
 
     line = {"metric": "ms to logpdf(fx,y)+posterior(fx,y)", "value": t_dev["total"], "unit": "ms", "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev["total"], "higher_is_better": False,
@@ -298,7 +351,35 @@ def run_ours(args, wl):
                     "d2h_bytes_per_step": int(alpha_h.numel() * 8 + 8 + 4 + 8), "wall_ms_per_step": wall_e2e,
                     "phases_ms": t_e2e},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "parity": parity}
+    if wl == "C2" and not args.no_scaling_ref:
+        # --gpus N > 1 runs the sharded config C4 (C2 is too small to shard); its single-GPU time is the
+        # base of the strong-scaling curve, measured here so the N=1 line carries it
+        line["scaling_reference"] = c4_single_gpu_reference(eng, L, cabi, C, torch, dev)
     print(json.dumps(line))
+
+
+def c4_single_gpu_reference(eng, L, cabi, C, torch, dev):
+    cfg = make_inputs("C4")
+    W = WORKLOADS["C4"]
+    N, D = W["N"], W["D"]
+    Xd = torch.from_numpy(np.ascontiguousarray(cfg["X"], dtype=np.float64)).to(dev)
+    yd = torch.from_numpy(np.ascontiguousarray(cfg["y"], dtype=np.float64)).to(dev)
+    alpha_d = torch.empty(N, dtype=torch.float64, device=dev)
+    ks = cabi.agp_kernel()
+    ks.family, ks.transform, ks.variance, ks.scale = 0, 1, 1.0, float(cfg["k"].scale)
+    ms_, ns = cabi.agp_mean(), cabi.agp_noise()
+    ns.kind, ns.s = 0, W["s2"]
+    lp = np.zeros(1)
+    eng.set_memspace(cabi.AGP_MEM_DEVICE)
+    tot = []
+    for it in range(3):
+        rc = L.agp_fit(eng.h, cabi.AGP_F64, C.byref(ks), C.byref(ms_), C.byref(ns), cabi.AGP_POINT_MAJOR,
+                       C.c_void_p(Xd.data_ptr()), N, D, C.c_void_p(yd.data_ptr()), 1, cabi.ptr(lp), C.c_void_p(alpha_d.data_ptr()), None)
+        eng.check(rc)
+        if it > 0:
+            tot.append(eng.timings()["total"])
+    return {"workload": "C4: N=65536 D=64 SqExponential fp64 on 1 GPU (the config --gpus N>1 shards)", "ms": float(np.mean(tot)),
+            "steps": len(tot), "logpdf": float(lp[0]), "third_n3_tflops": (N ** 3 / 3.0) / (np.mean(tot) * 1e-3) / 1e12}
 
 
 def run_ours_dist(args, wl, rank, world, local):
@@ -378,10 +459,11 @@ def run_ours_dist(args, wl, rank, world, local):
     dgemm = measure_dgemm_peak(torch, dev)
     tf = trailing_flops(N)
     chol_tf = (N ** 3 / 3.0) / (t_dev["cholesky"] * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel<false,false,2,2> (trailing update of the local block columns)",
-                "achieved": chol_tf, "peak": dgemm * world, "unit": "TFLOP/s", "frac": chol_tf / (dgemm * world),
-                "peak_source": "N x cuBLAS DGEMM 8192^3 measured on rank 0 in this run; achieved = (N^3/3)/max-over-ranks "
-                               "factorisation time (whole job)",
+    roofline = {"bound": "tensor", "kernel": "trailing update of the local block columns (umma_ozaki_syrk_v2_kernel, tcgen05 kind::i8, "
+                                          "for n_pad >= 8192; gemm_dmma_kernel below)",
+                "achieved": chol_tf, "peak": dgemm * world, "unit": "TFLOP/s (fp64-equivalent, whole job)", "frac": chol_tf / (dgemm * world),
+                "peak_source": "N x cuBLAS DGEMM 8192^3 measured on rank 0 in this run (native fp64 rate); achieved = (N^3/3) / "
+                               "max-over-ranks factorisation time; > 1 is possible because the int8-sliced path is not bound by the fp64 pipe",
                 "alg_flops_per_step": N ** 3 / 3.0, "trailing_flops_per_step": tf,
                 "kernel_ms_per_step_rank_max": t_dev.get("trailing", 0.0), "traffic": None}
     line = {"metric": "ms to logpdf(fx,y)+posterior(fx,y)", "value": t_dev["total"], "unit": "ms", "n_gpus": world,
@@ -407,6 +489,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
+    ap.add_argument("--no-scaling-ref", action="store_true", help="skip the C4-on-1-GPU reference measurement at N=1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = args.workload or ("C2" if args.gpus == 1 else "C4")

@@ -73,13 +73,16 @@ typedef struct {
 } agp_noise;
 
 typedef struct {
-  int32_t tile_nb;       /* panel width; 0 -> default (128) */
-  int32_t fp64_mode;     /* 0 = DMMA mma.sync trailing update, 1 = int8-sliced (Ozaki) on tcgen05 */
-  int32_t fp32_mode;     /* 0 = SIMT FFMA, 1 = 3xTF32 on tcgen05 */
-  int32_t lookahead;     /* 0/1: overlap next panel with the trailing update */
-  int32_t use_graph;     /* 0/1: replay the factorisation as a CUDA graph */
-  int32_t reserved[11];
-} agp_config; /* NULL -> defaults; env AGP_NB, AGP_FP64_MODE, AGP_FP32_MODE, AGP_LOOKAHEAD, AGP_GRAPH override */
+  int32_t tile_nb;       /* OUTER panel width (multiple of 128); 0 -> auto (512 from n_pad >= 8192, else 128) */
+  int32_t fp64_mode;     /* -1 auto (tcgen05 from n_pad >= 8192), 0 = DMMA mma.sync trailing update,
+                            1 = int8-sliced (Ozaki) trailing update on tcgen05.mma.kind::i8 */
+  int32_t fp32_mode;     /* reserved (0 = FFMA) */
+  int32_t lookahead;     /* 0/1: overlap the next panel with the bulk of the trailing update */
+  int32_t use_graph;     /* reserved */
+  int32_t ozaki_slices;  /* 5..8 seven-bit slices of the tcgen05 fp64 path; 0 -> 7 (~2^-49 of the row scale) */
+  int32_t profile_kernels; /* 1: CUDA events around every trailing-update launch (agp_last_timings[7]); default 0 */
+  int32_t reserved[9];
+} agp_config; /* NULL -> defaults; env AGP_NB, AGP_FP64_MODE, AGP_LOOKAHEAD, AGP_OZAKI_S override at agp_init */
 
 /* ---- context ------------------------------------------------------------------------- */
 int32_t agp_init(agp_ctx** ctx, int32_t device, const agp_config* cfg);
@@ -92,6 +95,8 @@ int32_t agp_destroy(agp_ctx* ctx);
 const char* agp_last_error(const agp_ctx* ctx);
 int64_t agp_last_info(const agp_ctx* ctx); /* LAPACK-style failing pivot (1-based) after NOT_POSDEF */
 int32_t agp_set_memspace(agp_ctx* ctx, int32_t memspace);
+int32_t agp_set_config(agp_ctx* ctx, const agp_config* cfg); /* change the tunables of a live ctx (bench / tests) */
+int32_t agp_get_config(const agp_ctx* ctx, agp_config* out);
 const char* agp_version(void);
 
 /* instrumentation for bench.py: per-phase device times (CUDA events on the launching stream)
