@@ -29,6 +29,9 @@ struct agp_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // look-ahead side stream (bulk of the trailing update)
+  cudaStream_t stream3 = nullptr;  // strip inverses of the diagonal blocks (needed only by the solves)
+  cudaEvent_t ev_s3 = nullptr, ev_fac = nullptr;
+  bool s3_dirty = false;
   std::vector<cudaEvent_t> dep_ev;  // dependency events of the look-ahead schedule
   agp_config cfg{};
   std::string err;
@@ -202,6 +205,14 @@ void trailing_update(agp_ctx* ctx, T* L, int64_t lda, int64_t row0, int64_t col0
   if (ctx->profile) cudaEventRecord(prof_event(ctx), st);
 }
 
+// the strip inverses run on stream3; every consumer of Dinv on the main stream joins them first
+static void join_inverses(agp_ctx* ctx) {
+  if (!ctx->s3_dirty) return;
+  cudaEventRecord(ctx->ev_s3, ctx->stream3);
+  cudaStreamWaitEvent(ctx->stream, ctx->ev_s3, 0);
+  ctx->s3_dirty = false;
+}
+
 // resolve the outer panel width (in 128-blocks) and the fp64 trailing-update engine for a problem size:
 // explicit config / env wins; "auto" = tcgen05 int8-sliced path with 512-wide panels from n_pad >= 8192
 static int resolve_G(const agp_ctx* ctx, int64_t n_pad) {
@@ -222,13 +233,31 @@ void factor_panel(agp_ctx* ctx, T* Lp, int64_t lda, int Gp, int64_t rows, T* Din
                   int* info, cudaStream_t s) {
   for (int g = 0; g < Gp; ++g) {
     T* Akk = Lp + (int64_t)g * TILE + (int64_t)g * TILE * lda;
-    launch_potrf_diag<T>(Akk, lda, Dinv_p + (int64_t)g * TILE * TILE, logdet_part, blk_base + g, info, s);
     const int64_t rows_below = rows - (int64_t)(g + 1) * TILE;
+    bool split_done = false;
+    if constexpr (std::is_same<T, double>::value) {
+      if (potrf_split_enabled()) {
+        // factor on the main stream; the 128x128 inverse (only the solves need it) on stream3;
+        // the panel TRSM by blocked substitution straight from L11
+        launch_potrf_factor_f64(Akk, lda, logdet_part, blk_base + g, info, s);
+        cudaEventRecord(ctx->ev_fac, s);
+        cudaStreamWaitEvent(ctx->stream3, ctx->ev_fac, 0);
+        launch_trtri_f64(Akk, lda, Dinv_p + (int64_t)g * TILE * TILE, ctx->stream3);
+        ctx->s3_dirty = true;
+        if (rows_below > 0) launch_trsm_sub_f64(Akk + TILE, lda, rows_below, Akk, s);
+        split_done = true;
+      }
+    }
+    if (!split_done) {
+      launch_potrf_diag<T>(Akk, lda, Dinv_p + (int64_t)g * TILE * TILE, logdet_part, blk_base + g, info, s);
+      if (rows_below > 0) {
+        GemmArgs t{};  // A21 <- A21 * inv(L11)'
+        t.A = Akk + TILE; t.lda = lda; t.B = Dinv_p + (int64_t)g * TILE * TILE; t.ldb = TILE;
+        t.C = Akk + TILE; t.ldc = lda; t.M = rows_below; t.N = TILE; t.K = TILE;
+        launch_gemm<T>(t, s);
+      }
+    }
     if (rows_below <= 0) continue;
-    GemmArgs t{};  // A21 <- A21 * inv(L11)'
-    t.A = Akk + TILE; t.lda = lda; t.B = Dinv_p + (int64_t)g * TILE * TILE; t.ldb = TILE;
-    t.C = Akk + TILE; t.ldc = lda; t.M = rows_below; t.N = TILE; t.K = TILE;
-    launch_gemm<T>(t, s);
     const int64_t ncols_in = (int64_t)(Gp - (g + 1)) * TILE;  // rank-128 update of the remaining inner columns
     if (ncols_in > 0) {
       GemmArgs u{};
@@ -294,6 +323,7 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
     }
   }
   if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, last_rest), 0);
+  join_inverses(ctx);  // Dinv (stream3) is complete before any solve on the main stream
 }
 
 // V <- L^-1 V for a n_pad x ncols block of right-hand sides (ncols multiple of 4), in place
@@ -1199,6 +1229,7 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
     last_rest = ev_idx - 1;
   }
   if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, last_rest), 0);
+  join_inverses(ctx);
   CK(cudaEventRecord(ctx->ev[3], s));
 
   // ---- v = border rows (distributed by column), sqmahal and logdet via all-reduce
@@ -1280,6 +1311,9 @@ int32_t agp_init(agp_ctx** out, int32_t device, const agp_config* cfg) {
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
+  cudaEventCreateWithFlags(&ctx->ev_s3, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_fac, cudaEventDisableTiming);
   for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -1299,6 +1333,9 @@ int32_t agp_destroy(agp_ctx* ctx) {
   for (auto e : ctx->dep_ev) cudaEventDestroy(e);
   if (ctx->oz.SL) ozaki_ws_destroy(&ctx->oz, ctx->stream);
   if (ctx->nccl) ncclCommDestroy(ctx->nccl);
+  cudaEventDestroy(ctx->ev_s3);
+  cudaEventDestroy(ctx->ev_fac);
+  cudaStreamDestroy(ctx->stream3);
   cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
   delete ctx;

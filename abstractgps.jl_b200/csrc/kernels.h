@@ -63,6 +63,12 @@ template <typename T> void launch_border_init_cols(T* A, int64_t lda, int64_t ro
 template <typename T> void launch_potrf_diag(T* Ablk, int64_t lda, T* Dinv, double* logdet_part, int blk,
                                              int* info, cudaStream_t s);
 template <typename T> void launch_gemm(const GemmArgs& g, cudaStream_t s);
+// fp64 split schedule: factor-only diagonal block, 8-CTA strip inverse (off the critical path), and the
+// panel TRSM by blocked substitution that does not need the 128x128 inverse
+int potrf_split_enabled();
+void launch_potrf_factor_f64(double* Ablk, int64_t lda, double* logdet_part, int blk, int* info, cudaStream_t s);
+void launch_trtri_f64(const double* Ablk, int64_t lda, double* Dinv, cudaStream_t s);
+void launch_trsm_sub_f64(double* A21, int64_t lda, int64_t M, const double* Lkk, cudaStream_t s);
 // v extraction from the border rows + sqmahal: r[s*n_pad + j] = E[s, j], sq[s] = sum_j E[s,j]^2
 template <typename T> void launch_extract_v(const T* A, int64_t lda, int64_t n_pad, int S, T* r, double* sq,
                                             cudaStream_t s);

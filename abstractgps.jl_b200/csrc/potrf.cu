@@ -658,6 +658,128 @@ trtri_strips_f64(const double* __restrict__ A, int64_t lda, double* __restrict__
     Dinv[c + r * PB] = v;
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Panel TRSM by blocked substitution (fp64): X <- X * L11^-T for a 32-row slab of the panel per CTA,
+// WITHOUT the 128x128 inverse -- only the sixteen 8x8 diagonal inverses (computed here from L11 in a few
+// hundred cycles).  16 micro-steps: (a) the 8 current columns are multiplied by the 8x8 inverse,
+// (b) the remaining columns receive the rank-8 update on the DMMA pipe.  Takes the strip inverse
+// (trtri_strips_f64) off the critical path of the factorisation: it now runs on a side stream.
+// ------------------------------------------------------------------------------------------------
+constexpr int TS_R = 32;        // rows per CTA
+constexpr int TS_XP = TS_R + 1; // slab column stride
+
+__global__ void __launch_bounds__(256, 1)
+trsm_sub_f64(double* __restrict__ A21, int64_t lda, int64_t M, const double* __restrict__ Lkk) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Ls = reinterpret_cast<double*>(smem_raw);  // Ls[c*PLD + i], lower
+  double* xs = Ls + PB * PLD;                        // xs[c*TS_XP + r]
+  double* X8 = xs + PB * TS_XP;                      // X8[r*XLD + c]
+  double* D8 = X8 + TS_R * XLD;                      // D8[J*64 + c*8 + c2] = inv(L_d(J))(c, c2)
+  double* dinv = D8 + 16 * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, q = lane & 3;
+  const int64_t row0 = (int64_t)blockIdx.x * TS_R;
+#pragma unroll
+  for (int b0 = 0; b0 < 64; b0 += 16) {
+    double tmp[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * (b0 + u);
+      const int c = idx >> 7, i = idx & 127;
+      tmp[u] = (i >= c) ? __ldg(Lkk + i + (int64_t)c * lda) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * (b0 + u);
+      Ls[(idx >> 7) * PLD + (idx & 127)] = tmp[u];
+    }
+  }
+  {
+    double tmp[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * u;  // 128 cols x 32 rows
+      const int c = idx >> 5, r = idx & 31;
+      tmp[u] = (row0 + r < M) ? A21[row0 + r + (int64_t)c * lda] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * u;
+      xs[(idx >> 5) * TS_XP + (idx & 31)] = tmp[u];
+    }
+  }
+  __syncthreads();
+  if (tid < PB) dinv[tid] = 1.0 / Ls[tid * PLD + tid];
+  __syncthreads();
+  if (tid < PB) {  // sixteen 8x8 inverses: thread (J, cr) solves L_d x = e_cr
+    const int J = tid >> 3, cr = tid & 7, j0 = J * 8;
+    double x[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      double sacc = (c == cr) ? 1.0 : 0.0;
+#pragma unroll
+      for (int c2 = 0; c2 < c; ++c2) sacc -= x[c2] * Ls[(j0 + c2) * PLD + j0 + c];
+      x[c] = sacc * dinv[j0 + c];
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) D8[J * 64 + c * 8 + cr] = x[c];
+  }
+  __syncthreads();
+  for (int J = 0; J < 16; ++J) {
+    const int j0 = J * 8;
+    {  // (a) 8 current columns times the 8x8 inverse (transposed): thread (r, c)
+      const int r = tid & 31, c = tid >> 5;
+      double acc = 0.0;
+#pragma unroll
+      for (int c2 = 0; c2 < 8; ++c2)
+        if (c2 <= c) acc = fma(xs[(j0 + c2) * TS_XP + r], D8[J * 64 + c * 8 + c2], acc);
+      __syncthreads();
+      xs[(j0 + c) * TS_XP + r] = acc;
+      X8[r * XLD + c] = acc;
+    }
+    __syncthreads();
+    if (J < 15) {  // (b) rank-8 update of the remaining columns: warp -> row-group (warp & 3), column parity (warp >> 2)
+      const int r0 = (warp & 3) * 8;
+      const double a0 = -X8[(r0 + gq) * XLD + q], a1 = -X8[(r0 + gq) * XLD + 4 + q];
+      for (int kg = J + 1 + (warp >> 2); kg <= 15; kg += 8) {
+        double b0[4], b1[4], c0[4], c1[4];
+        double* cp[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int kgu = min(kg + 2 * u, 15);
+          b0[u] = Ls[(j0 + q) * PLD + kgu * 8 + gq];
+          b1[u] = Ls[(j0 + 4 + q) * PLD + kgu * 8 + gq];
+          cp[u] = xs + (kgu * 8 + 2 * q) * TS_XP + r0 + gq;
+          c0[u] = cp[u][0];
+          c1[u] = cp[u][TS_XP];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dmma884(c0[u], c1[u], a0, b0[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dmma884(c0[u], c1[u], a1, b1[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (kg + 2 * u <= 15) { cp[u][0] = c0[u]; cp[u][TS_XP] = c1[u]; }
+      }
+    }
+    __syncthreads();
+  }
+  {
+    double tmp[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * u;
+      tmp[u] = xs[(idx >> 5) * TS_XP + (idx & 31)];
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = tid + 256 * u;
+      const int c = idx >> 5, r = idx & 31;
+      if (row0 + r < M) A21[row0 + r + (int64_t)c * lda] = tmp[u];
+    }
+  }
+}
 }  // namespace
 
 template <typename T>
@@ -693,5 +815,34 @@ void launch_potrf_diag<double>(double* Ablk, int64_t lda, double* Dinv, double* 
   } else {
     potrf_diag_kernel_f64<<<1, 256, smem, s>>>(Ablk, lda, Dinv, logdet_part, blk, info);
   }
+  agp_count_launch();
+}
+
+// ---- split API used by the factorisation schedule (fp64): factor / strip inverse / substitution TRSM
+int potrf_split_enabled() {
+  static int split = -1;
+  if (split < 0) { const char* v = getenv("AGP_POTRF_SPLIT"); split = v ? atoi(v) : 1; }
+  return split;
+}
+void launch_potrf_factor_f64(double* Ablk, int64_t lda, double* logdet_part, int blk, int* info, cudaStream_t s) {
+  const size_t smem = (size_t)(PB * PLD + PB * XLD + 64 + 8 + PB) * sizeof(double);
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(potrf_factor_only_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+  potrf_factor_only_f64<<<1, 256, smem, s>>>(Ablk, lda, logdet_part, blk, info);
+  agp_count_launch();
+}
+void launch_trtri_f64(const double* Ablk, int64_t lda, double* Dinv, cudaStream_t s) {
+  const size_t smem = (size_t)(PB * PLD + PB * XLD + 64 + 8 + PB) * sizeof(double);
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(trtri_strips_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+  trtri_strips_f64<<<8, 256, smem, s>>>(Ablk, lda, Dinv);
+  agp_count_launch();
+}
+void launch_trsm_sub_f64(double* A21, int64_t lda, int64_t M, const double* Lkk, cudaStream_t s) {
+  if (M <= 0) return;
+  const size_t smem = (size_t)(PB * PLD + PB * TS_XP + TS_R * XLD + 16 * 64 + PB) * sizeof(double);
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(trsm_sub_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+  trsm_sub_f64<<<(unsigned)((M + TS_R - 1) / TS_R), 256, smem, s>>>(A21, lda, M, Lkk);
   agp_count_launch();
 }
