@@ -409,6 +409,74 @@ potrf_diag_kernel_f64(double* __restrict__ A, int64_t lda, double* __restrict__ 
 // only (one CTA, on the critical path) and the inverse is produced by 8 CTAs in parallel, CTA p owning the
 // E row-groups p and 15-p (balanced: the early groups sweep many column groups, the late ones few).
 // ------------------------------------------------------------------------------------------------
+// 8x8 Cholesky of the diagonal block at micro-panel j0, lane-redundant in one warp; publishes Ld / rinv_s
+__device__ __forceinline__ void factor_diag8(const double* arr, int j0, int lane, double* Ld, double* rinv_s, int blk, int* info) {
+  double d[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c <= r; ++c) d[r][c] = arr[(j0 + c) * PLD + j0 + r];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    double piv = d[c][c];
+    if (!(piv > 0.0)) {
+      if (lane == 0) atomicCAS(info, 0, blk * PB + j0 + c + 1);
+      piv = 1.0;
+    }
+    const double r = dev_rsqrt_refined<double>(piv);
+    if (lane == 0) rinv_s[c] = r;
+    d[c][c] = piv * r;
+#pragma unroll
+    for (int r2 = c + 1; r2 < 8; ++r2) d[r2][c] *= r;
+#pragma unroll
+    for (int c2 = c + 1; c2 < 8; ++c2)
+#pragma unroll
+      for (int r2 = c2; r2 < 8; ++r2) d[r2][c2] -= d[r2][c] * d[c2][c];
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c) Ld[r * 8 + c] = d[r][c];
+  }
+}
+
+// rank-8 update of the S tiles of row-group rg against column groups kg_lo..kg_hi (4 tiles per trip)
+__device__ __forceinline__ void s_group_update(double* arr, const double* XS, int rg, int kg_lo, int kg_hi, int gq, int q) {
+  if (kg_hi < kg_lo) return;
+  const int r0 = rg * 8;
+  const double a0 = -XS[(r0 + gq) * XLD + q], a1 = -XS[(r0 + gq) * XLD + 4 + q];
+  for (int kg = kg_lo; kg <= kg_hi; kg += 4) {
+    double b0[4], b1[4], c0[4], c1[4];
+    double* cp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int kgu = min(kg + u, 15);
+      b0[u] = XS[(kgu * 8 + gq) * XLD + q];
+      b1[u] = XS[(kgu * 8 + gq) * XLD + 4 + q];
+      cp[u] = arr + (kgu * 8 + 2 * q) * PLD + r0 + gq;
+      c0[u] = cp[u][0];
+      c1[u] = cp[u][PLD];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) dmma884(c0[u], c1[u], a0, b0[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) dmma884(c0[u], c1[u], a1, b1[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int kgu = kg + u;
+      if (kgu <= kg_hi) {
+        const bool diag_tile = (kgu == rg);
+        if (!diag_tile || 2 * q <= gq) cp[u][0] = c0[u];  // diagonal tile: keep only k <= row
+        if (!diag_tile || 2 * q + 1 <= gq) cp[u][PLD] = c1[u];
+      }
+    }
+  }
+}
+
+// Factor-only kernel with INTRA-KERNEL LOOK-AHEAD: after the substitution of micro-panel J, warp 0 first
+// applies the rank-8 update to the next diagonal 8x8 tile only and immediately factors it (the sqrt chain of
+// micro-panel J+1) while warps 1..7 run the rest of the rank-8 update on the DMMA pipe.
 __global__ void __launch_bounds__(256, 1)
 potrf_factor_only_f64(double* __restrict__ A, int64_t lda, double* __restrict__ logdet_part, int blk, int* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -436,49 +504,18 @@ potrf_factor_only_f64(double* __restrict__ A, int64_t lda, double* __restrict__ 
     }
   }
   __syncthreads();
+  if (warp == 0) factor_diag8(arr, 0, lane, Ld, rinv_s, blk, info);
+  __syncthreads();
   for (int j0 = 0; j0 < PB; j0 += 8) {
     const int J = j0 >> 3;
     const int w = tid;
     const bool is_s = (tid < PB) && (w >= j0 + 8);
     const bool is_diag = (tid < PB) && (w >= j0) && (w < j0 + 8);
-    double a[8];
+    // ---- substitution against the (already factored) 8x8 block of this micro-panel
     if (is_s) {
+      double a[8], x[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) a[c] = arr[(j0 + c) * PLD + w];
-    }
-    if (warp == 0) {
-      double d[8][8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-#pragma unroll
-        for (int c = 0; c <= r; ++c) d[r][c] = arr[(j0 + c) * PLD + j0 + r];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        double piv = d[c][c];
-        if (!(piv > 0.0)) {
-          if (lane == 0) atomicCAS(info, 0, blk * PB + j0 + c + 1);
-          piv = 1.0;
-        }
-        const double r = dev_rsqrt_refined<double>(piv);
-        if (lane == 0) rinv_s[c] = r;
-        d[c][c] = piv * r;
-#pragma unroll
-        for (int r2 = c + 1; r2 < 8; ++r2) d[r2][c] *= r;
-#pragma unroll
-        for (int c2 = c + 1; c2 < 8; ++c2)
-#pragma unroll
-          for (int r2 = c2; r2 < 8; ++r2) d[r2][c2] -= d[r2][c] * d[c2][c];
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-#pragma unroll
-          for (int c = 0; c <= r; ++c) Ld[r * 8 + c] = d[r][c];
-      }
-    }
-    __syncthreads();
-    if (is_s) {
-      double x[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         double sacc = a[c];
@@ -496,40 +533,20 @@ potrf_factor_only_f64(double* __restrict__ A, int64_t lda, double* __restrict__ 
       dinv[w] = rinv_s[cr];
     }
     __syncthreads();
-    {  // rank-8 update of the S rows only: warp wi owns row-groups wi and 15-wi
+    // ---- rank-8 update; warp 0 runs ahead on the next diagonal block
+    if (warp == 0) {
+      if (J < 15) {
+        s_group_update(arr, XS, J + 1, J + 1, J + 1, gq, q);  // the next diagonal 8x8 tile only
+        __syncwarp();
+        factor_diag8(arr, j0 + 8, lane, Ld, rinv_s, blk, info);
+        if (8 > J + 1) s_group_update(arr, XS, 8, J + 1, 8, gq, q);  // then its share of the bulk: row-group 8
+      }
+    } else {
 #pragma unroll
       for (int sel = 0; sel < 2; ++sel) {
-        const int rg = sel ? (15 - warp) : warp;
-        if (rg <= J) continue;
-        const int kg_lo = J + 1, kg_hi = rg;
-        const int r0 = rg * 8;
-        const double a0 = -XS[(r0 + gq) * XLD + q], a1 = -XS[(r0 + gq) * XLD + 4 + q];
-        for (int kg = kg_lo; kg <= kg_hi; kg += 4) {
-          double b0[4], b1[4], c0[4], c1[4];
-          double* cp[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int kgu = min(kg + u, 15);
-            b0[u] = XS[(kgu * 8 + gq) * XLD + q];
-            b1[u] = XS[(kgu * 8 + gq) * XLD + 4 + q];
-            cp[u] = arr + (kgu * 8 + 2 * q) * PLD + r0 + gq;
-            c0[u] = cp[u][0];
-            c1[u] = cp[u][PLD];
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) dmma884(c0[u], c1[u], a0, b0[u]);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) dmma884(c0[u], c1[u], a1, b1[u]);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int kgu = kg + u;
-            if (kgu <= kg_hi) {
-              const bool diag_tile = (kgu == rg);
-              if (!diag_tile || 2 * q <= gq) cp[u][0] = c0[u];
-              if (!diag_tile || 2 * q + 1 <= gq) cp[u][PLD] = c1[u];
-            }
-          }
-        }
+        const int rg = sel ? (16 - warp) : warp;  // warps 1..7 own row-groups (w, 16-w): 1..7 and 9..15
+        if (rg <= J + 1) continue;                // finished groups; group J+1 is only its diagonal tile (warp 0)
+        s_group_update(arr, XS, rg, J + 1, rg, gq, q);
       }
     }
     __syncthreads();
