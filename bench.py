@@ -319,6 +319,7 @@ def run_ours(args, wl):
                                    "DMMA microbenchmark on this pool: 37.0 TFLOP/s",
                     "frac_of_bf16_measured": (fp64_eq / peaks["bf16_tflops"]) if (fp64_eq and "bf16_tflops" in peaks) else None}
     roofline.update({"launches_per_step": len(outer), "alg_flops_per_step": tf, "kernel_ms_per_step": trailing_ms,
+                     "traffic_ncu": ncu_traffic(mode),
                      "kernel_timing": "CUDA events around each launch, look-ahead off (serial), %d steps" % max(2, min(args.steps, 5)),
                      "panel_width": nb, "traffic": None, "cublas_dgemm_tflops": dgemm,
                      "cholesky_third_n3_tflops": chol_tf, "cholesky_frac_of_dgemm": chol_tf / dgemm})
@@ -356,6 +357,23 @@ def run_ours(args, wl):
         # base of the strong-scaling curve, measured here so the N=1 line carries it
         line["scaling_reference"] = c4_single_gpu_reference(eng, L, cabi, C, torch, dev)
     print(json.dumps(line))
+
+
+def ncu_traffic(mode):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/): per launch, for the launch that was captured (the largest trailing update of the C4h step)."""
+    name = "r01_prof_ozaki_v2_c4h.txt" if mode == 1 else "r01_prof_syrk_c4h.txt"
+    try:
+        rd = wr = None
+        for line in open(os.path.join(ROOT, "profiles", name)):
+            parts = line.split()
+            if line.startswith("dram__bytes_read.sum ") and rd is None:
+                rd = float(parts[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3}.get(parts[2], 1.0)
+            if line.startswith("dram__bytes_write.sum ") and wr is None:
+                wr = float(parts[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3}.get(parts[2], 1.0)
+        return {"source": "profiles/" + name, "dram_bytes_per_launch": rd + wr, "read": rd, "write": wr}
+    except Exception:
+        return None
 
 
 def c4_single_gpu_reference(eng, L, cabi, C, torch, dev):
