@@ -303,6 +303,11 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ double ld_cs(const double* p) {
   double v;
   asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
@@ -446,32 +451,42 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
       double* crow = a.C + row;
       mbar_wait(&tmem_full_bar, lt & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < OZ_BN; c += 16) {
-        uint32_t r[S][16];
+      // (1) drain TMEM: Horner-combine the S int32 accumulators of all 64 columns into registers, 8 columns per
+      //     trip (all S loads of a trip in flight before one wait), then hand the accumulators back to the MMA
+      //     warp -- the C read-modify-write below overlaps the next tile's MMAs.
+      double v[OZ_BN];
+#pragma unroll
+      for (int c8 = 0; c8 < OZ_BN; c8 += 8) {
+        uint32_t r[S][8];
 #pragma unroll
         for (int d = 0; d < S; ++d)
-          tmem_ld16_nowait(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(d * OZ_BN + c), r[d]);
-        double cv[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int64_t col = n0 + c + i;
-          cv[i] = (row_ok && col < a.N) ? ld_cs(crow + col * a.ldc) : 0.0;
-        }
+          tmem_ld8_nowait(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(d * OZ_BN + c8), r[d]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c + 16 >= OZ_BN) {  // last TMEM read of this tile: hand the accumulators back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          double acc = (double)(int)r[S - 1][i];
+#pragma unroll
+          for (int d = S - 2; d >= 0; --d) acc = fma(acc, 1.0 / 128.0, (double)(int)r[d][i]);
+          v[c8 + i] = acc;
         }
-        if (row_ok) {
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar);
+      // (2) C -= scale_i * scale_j * v, streamed (.cs) so the int8 slices stay resident in L2
+      if (row_ok) {
+#pragma unroll
+        for (int c = 0; c < OZ_BN; c += 16) {
+          double cv[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            double v = (double)(int)r[S - 1][i];
-#pragma unroll
-            for (int d = S - 2; d >= 0; --d) v = fma(v, 1.0 / 128.0, (double)(int)r[d][i]);
             const int64_t col = n0 + c + i;
-            if (col < a.N) st_cs(crow + col * a.ldc, fma(-v * rs, a.rscale[brow64 + c + i], cv[i]));
+            cv[i] = (col < a.N) ? ld_cs(crow + col * a.ldc) : 0.0;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int64_t col = n0 + c + i;
+            if (col < a.N) st_cs(crow + col * a.ldc, fma(-v[c + i] * rs, a.rscale[brow64 + c + i], cv[i]));
           }
         }
       }
