@@ -880,6 +880,22 @@ int gram_impl(agp_ctx* ctx, const agp_kernel* k, int layout, const void* X, int6
   return AGP_OK;
 }
 
+#define CKN(call)                                                                         \
+  do {                                                                                    \
+    ncclResult_t _r = (call);                                                             \
+    if (_r != ncclSuccess) {                                                              \
+      char _b[512];                                                                       \
+      snprintf(_b, sizeof(_b), "%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(_r)); \
+      ctx->err = _b;                                                                      \
+      return AGP_ERR_NCCL;                                                                \
+    }                                                                                     \
+  } while (0)
+
+template <typename T> struct NcclType;
+template <> struct NcclType<float> { static constexpr ncclDataType_t v = ncclFloat; };
+template <> struct NcclType<double> { static constexpr ncclDataType_t v = ncclDouble; };
+
+
 // ---- VFE (Titsias) : elbo / dtc / approximate posterior --------------------------------------------
 // Follows /root/reference/src/sparse_approximations.jl:289-305 (_compute_intermediates), :248-254 (elbo),
 // :58-75 (posterior), but STREAMS the data dimension: K_zx is generated chunk by chunk, scaled by
@@ -924,8 +940,16 @@ int vfe_core(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
   CK(sc.alloc(&tmp, sizeof(int)));
   int* dinfo = (int*)tmp;
   CK(cudaMemsetAsync(dinfo, 0, sizeof(int), s));
+  // data shard of this rank (multi-GPU: the N dimension is partitioned, ONE all-reduce at the end -- SURVEY s8e)
+  int64_t n_lo = 0, n_hi = N;
+  if (ctx->nccl) {
+    const int64_t per = (N + ctx->nranks - 1) / ctx->nranks;
+    n_lo = (int64_t)ctx->rank * per; if (n_lo > N) n_lo = N;
+    n_hi = n_lo + per; if (n_hi > N) n_hi = N;
+  }
   launch_kdiag<T>(Xt, N, D, k->family, k->variance, k->linear_c, kd, s);
-  launch_vfe_prep<T>(yd, N, mean->kind, mean->c, mean_d, noise->kind, noise->s, noise_d, kd, delta, isn, dscal, s);
+  launch_vfe_prep<T>(yd + n_lo, n_hi - n_lo, mean->kind, mean->c, mean_d ? mean_d + n_lo : nullptr, noise->kind, noise->s,
+                     noise_d ? noise_d + n_lo : nullptr, kd + n_lo, delta + n_lo, isn + n_lo, dscal, s);
 
   // factor buffers
   void *Lzv = nullptr, *Dzv = nullptr, *Lmv = nullptr, *Dlv = nullptr, *mev = nullptr;
@@ -966,8 +990,8 @@ int vfe_core(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
   void* Bv = nullptr;
   CK(sc.alloc(&Bv, (size_t)m_pad * cap * sizeof(T)));
   T* B = (T*)Bv;
-  for (int64_t c0 = 0; c0 < N; c0 += cap) {
-    const int64_t nc = (N - c0 < cap) ? (N - c0) : cap;
+  for (int64_t c0 = n_lo; c0 < n_hi; c0 += cap) {
+    const int64_t nc = (n_hi - c0 < cap) ? (n_hi - c0) : cap;
     const int64_t nc_pad = round_up(nc, TILE);
     GramParams gx{};
     fill_gram_params<T>(gx, k, 0, 0, M, nc, nullptr, nullptr);
@@ -980,6 +1004,11 @@ int vfe_core(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
     launch_gemm<T>(g, s);
     launch_gemv_n_acc<T>(B, m_pad, m_pad, nc, delta + c0, bvec, s);
     launch_sumsq<T>(B, m_pad * nc_pad, dscal + 3, s);
+  }
+  if (ctx->nccl) {  // the one exchange step: D (M x M), b (M) and the three scalars
+    CKN(ncclAllReduce(Lm, Lm, (size_t)lda * m_pad, NcclType<T>::v, ncclSum, ctx->nccl, s));
+    CKN(ncclAllReduce(bvec, bvec, (size_t)m_pad, NcclType<T>::v, ncclSum, ctx->nccl, s));
+    CKN(ncclAllReduce(dscal, dscal, 4, ncclDouble, ncclSum, ctx->nccl, s));
   }
   CK(cudaEventRecord(ctx->ev[2], s));
 
@@ -1076,21 +1105,6 @@ int vfe_mean_var_impl(agp_vfe_post* p, int layout, const void* Xs, int64_t Ms, v
 // replicated points.  (grid_p > 1 is declared in the ABI but not built: on NVSwitch the panel
 // broadcast is ~5 % of the factorisation at C4, so the 2-D row/column split buys nothing yet.)
 // ------------------------------------------------------------------------------------------------
-#define CKN(call)                                                                         \
-  do {                                                                                    \
-    ncclResult_t _r = (call);                                                             \
-    if (_r != ncclSuccess) {                                                              \
-      char _b[512];                                                                       \
-      snprintf(_b, sizeof(_b), "%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(_r)); \
-      ctx->err = _b;                                                                      \
-      return AGP_ERR_NCCL;                                                                \
-    }                                                                                     \
-  } while (0)
-
-template <typename T> struct NcclType;
-template <> struct NcclType<float> { static constexpr ncclDataType_t v = ncclFloat; };
-template <> struct NcclType<double> { static constexpr ncclDataType_t v = ncclDouble; };
-
 template <typename T>
 int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_noise* noise, int layout,
                   const void* X, int64_t N, int D, const void* Y, int S, void* logpdf_out, void* alpha_out) {
@@ -1456,6 +1470,7 @@ int32_t agp_debug_ozaki_syrk(agp_ctx* ctx, void* C_dev, int64_t ldc, const void*
   OzakiWs ws;
   int rc = ozaki_ws_create(&ws, M, K, S, ctx->stream);
   if (rc) { ctx->err = "ozaki_ws_create failed (code " + std::to_string(rc) + ")"; return rc == 1 ? AGP_ERR_INVALID : AGP_ERR_CUDA; }
+  if (!(lower_only && N % 128 == 0 && N >= 128)) ws.bulk = 0;  // the non-persistent kernel reads the row-major slice layout
   ozaki_prepare(ws, (const double*)P_dev, lda, M, ctx->stream);
   ozaki_syrk(ws, (double*)C_dev, ldc, M, N, lower_only, 0, 0, 0, 0, ctx->stream);
   ozaki_ws_destroy(&ws, ctx->stream);

@@ -72,9 +72,6 @@ void launch_trsm_sub_f64(double* A21, int64_t lda, int64_t M, const double* Lkk,
 // v extraction from the border rows + sqmahal: r[s*n_pad + j] = E[s, j], sq[s] = sum_j E[s,j]^2
 template <typename T> void launch_extract_v(const T* A, int64_t lda, int64_t n_pad, int S, T* r, double* sq,
                                             cudaStream_t s);
-// one step of the blocked backward substitution L' alpha = r (in place in r), block k
-template <typename T> void launch_bwd_step(const T* A, int64_t lda, const T* Dinv, int k, T* r,
-                                           cudaStream_t s);
 // whole backward substitution in one persistent launch; flags_and_ticket: nblk+1 ints (zeroed inside)
 template <typename T> void launch_bwd_solve(const T* A, int64_t lda, const T* Dinv, int nblk, T* r,
                                             int* flags_and_ticket, cudaStream_t s);
@@ -82,9 +79,6 @@ template <typename T> void launch_bwd_solve(const T* A, int64_t lda, const T* Di
 template <typename T> void launch_bwd_diag(const T* Dinv_i, const T* r_i, T* alpha_i, cudaStream_t s);
 template <typename T> void launch_bwd_update_local(const T* Lloc, int64_t lda, int i_blk, const T* alpha_i, T* r, int nloc,
                                                    int rank, int nranks, int G, cudaStream_t s);
-// one step of the blocked forward substitution L v = r (in place), block k (used by extend / vfe)
-template <typename T> void launch_fwd_step(const T* A, int64_t lda, const T* Dinv, int k, int nblk, T* r,
-                                           cudaStream_t s);
 template <typename T> void launch_finalize_logpdf(const double* logdet_part, int nblk, const double* sq, int S,
                                                   int64_t n, T* out, double* logdet_out, cudaStream_t s);
 // mu[j] = mean_j + sum_i B[i + j*ldb] * alpha[i]

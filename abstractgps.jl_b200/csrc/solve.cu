@@ -55,10 +55,9 @@ __global__ void extract_v_kernel(const T* __restrict__ A, int64_t lda, int64_t n
   }
 }
 
-// backward step k: every CTA b <= k recomputes alpha_k = Dinv_k' r_k (128x128 mat-vec out of L2);
-// CTA b == k stores it, CTA b < k applies r_b -= L[k-block rows, b-block cols]' alpha_k.
-// Thread (output o = tid>>1, half h = tid&1) streams 64 CONTIGUOUS elements of column o with
-// independent 16-byte loads (all in flight at once), then the two halves meet through one shuffle.
+// 128-term column dot product split over a thread pair: thread (output o = tid>>1, half h = tid&1) streams
+// 64 CONTIGUOUS elements of column o with independent loads (all in flight at once); the two halves meet
+// through one shuffle in the caller.
 template <typename T>
 __device__ __forceinline__ double col_dot_half(const T* __restrict__ col, const T* __restrict__ vec_s, int h) {
   double acc0 = 0.0, acc1 = 0.0;
@@ -70,34 +69,6 @@ __device__ __forceinline__ double col_dot_half(const T* __restrict__ col, const 
     acc1 = fma((double)c[j + 1], (double)v[j + 1], acc1);
   }
   return acc0 + acc1;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) bwd_step_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ Dinv,
-                                                       int k, T* __restrict__ r) {
-  __shared__ T rk[TB];
-  __shared__ T ak[TB];
-  const int b = blockIdx.x;
-  const int tid = threadIdx.x, o = tid >> 1, h = tid & 1;
-  if (tid < TB) rk[tid] = r[(int64_t)k * TB + tid];
-  __syncthreads();
-  const T* Dk = Dinv + (int64_t)k * TB * TB;
-  {  // alpha_k[o] = sum_j Dinv(j, o) r_k[j]  (column o of Dinv, contiguous in j; zero above the diagonal)
-    double acc = col_dot_half<T>(Dk + o * TB, rk, h);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    if (h == 0) ak[o] = (T)acc;
-  }
-  __syncthreads();
-  if (b == k) {
-    if (tid < TB) r[(int64_t)k * TB + tid] = ak[tid];
-    return;
-  }
-  const T* Lkb = A + (int64_t)k * TB + (int64_t)b * TB * lda;  // tile (k, b)
-  {
-    double acc = col_dot_half<T>(Lkb + (int64_t)o * lda, ak, h);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    if (h == 0) r[(int64_t)b * TB + o] -= (T)acc;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -244,45 +215,6 @@ __global__ void __launch_bounds__(256) bwd_update_local_kernel(const T* __restri
   double acc = col_dot_half<T>(tile, ak, h);
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   if (h == 0) r[j * TB + o] -= (T)acc;
-}
-
-// forward step k: v_k = Dinv_k r_k ; r_b -= L[b-block rows, k-block cols] v_k for b > k.
-// thread (row i, half h) accumulates half of the 128-term dot product; rows are consecutive across
-// threads so every global read is coalesced.
-template <typename T>
-__global__ void __launch_bounds__(256) fwd_step_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ Dinv,
-                                                       int k, T* __restrict__ r) {
-  __shared__ T rk[TB];
-  __shared__ T vk[TB];
-  __shared__ double part[2][TB];
-  const int b = k + blockIdx.x;
-  const int tid = threadIdx.x;
-  const int i = tid & (TB - 1), h = tid >> 7;
-  if (tid < TB) rk[tid] = r[(int64_t)k * TB + tid];
-  __syncthreads();
-  const T* Dk = Dinv + (int64_t)k * TB * TB;
-  {
-    double acc = 0.0;
-    const int j0 = h * (TB / 2);
-    for (int j = j0; j < j0 + TB / 2; ++j) acc = fma((double)Dk[i + j * TB], (double)rk[j], acc);
-    part[h][i] = acc;
-  }
-  __syncthreads();
-  if (tid < TB) vk[tid] = (T)(part[0][tid] + part[1][tid]);
-  __syncthreads();
-  if (b == k) {
-    if (tid < TB) r[(int64_t)k * TB + tid] = vk[tid];
-    return;
-  }
-  const T* Lbk = A + (int64_t)b * TB + (int64_t)k * TB * lda;  // tile (b, k)
-  {
-    double acc = 0.0;
-    const int j0 = h * (TB / 2);
-    for (int j = j0; j < j0 + TB / 2; ++j) acc = fma((double)Lbk[i + (int64_t)j * lda], (double)vk[j], acc);
-    part[h][i] = acc;
-  }
-  __syncthreads();
-  if (tid < TB) r[(int64_t)b * TB + tid] -= (T)(part[0][tid] + part[1][tid]);
 }
 
 template <typename T>
@@ -506,11 +438,6 @@ void launch_extract_v(const T* A, int64_t lda, int64_t n_pad, int S, T* r, doubl
   agp_count_launch();
 }
 template <typename T>
-void launch_bwd_step(const T* A, int64_t lda, const T* Dinv, int k, T* r, cudaStream_t s) {
-  bwd_step_kernel<T><<<k + 1, 256, 0, s>>>(A, lda, Dinv, k, r);
-  agp_count_launch();
-}
-template <typename T>
 void launch_bwd_solve(const T* A, int64_t lda, const T* Dinv, int nblk, T* r, int* flags_and_ticket, cudaStream_t s) {
   const size_t smem = (size_t)TB * TB * sizeof(T);
   static bool configured = false;
@@ -520,11 +447,6 @@ void launch_bwd_solve(const T* A, int64_t lda, const T* Dinv, int nblk, T* r, in
   }
   cudaMemsetAsync(flags_and_ticket, 0, (size_t)(nblk + 1) * sizeof(int), s);
   bwd_solve_kernel<T><<<nblk, 256, smem, s>>>(A, lda, Dinv, nblk, r, flags_and_ticket, flags_and_ticket + nblk);
-  agp_count_launch();
-}
-template <typename T>
-void launch_fwd_step(const T* A, int64_t lda, const T* Dinv, int k, int nblk, T* r, cudaStream_t s) {
-  fwd_step_kernel<T><<<nblk - k, 256, 0, s>>>(A, lda, Dinv, k, r);
   agp_count_launch();
 }
 template <typename T>
@@ -690,8 +612,6 @@ template void launch_bwd_solve<float>(const float*, int64_t, const float*, int, 
 template void launch_bwd_solve<double>(const double*, int64_t, const double*, int, double*, int*, cudaStream_t);
 template void launch_border_init<float>(float*, int64_t, int64_t, int64_t, const float*, int64_t, int, int, double, const float*, cudaStream_t);
 template void launch_extract_v<float>(const float*, int64_t, int64_t, int, float*, double*, cudaStream_t);
-template void launch_bwd_step<float>(const float*, int64_t, const float*, int, float*, cudaStream_t);
-template void launch_fwd_step<float>(const float*, int64_t, const float*, int, int, float*, cudaStream_t);
 template void launch_finalize_logpdf<float>(const double*, int, const double*, int, int64_t, float*, double*, cudaStream_t);
 template void launch_gemv_t<float>(const float*, int64_t, int64_t, int64_t, const float*, int, double, const float*, float*, cudaStream_t);
 template void launch_colsumsq_var<float>(const float*, int64_t, int64_t, int64_t, const float*, int, double, const float*, float*, cudaStream_t);
@@ -706,8 +626,6 @@ template void launch_sumsq<float>(const float*, int64_t, double*, cudaStream_t);
 template void launch_vfe_prep<float>(const float*, int64_t, int, double, const float*, int, double, const float*, const float*, float*, float*, double*, cudaStream_t);
 template void launch_border_init<double>(double*, int64_t, int64_t, int64_t, const double*, int64_t, int, int, double, const double*, cudaStream_t);
 template void launch_extract_v<double>(const double*, int64_t, int64_t, int, double*, double*, cudaStream_t);
-template void launch_bwd_step<double>(const double*, int64_t, const double*, int, double*, cudaStream_t);
-template void launch_fwd_step<double>(const double*, int64_t, const double*, int, int, double*, cudaStream_t);
 template void launch_finalize_logpdf<double>(const double*, int, const double*, int, int64_t, double*, double*, cudaStream_t);
 template void launch_gemv_t<double>(const double*, int64_t, int64_t, int64_t, const double*, int, double, const double*, double*, cudaStream_t);
 template void launch_colsumsq_var<double>(const double*, int64_t, int64_t, int64_t, const double*, int, double, const double*, double*, cudaStream_t);

@@ -50,7 +50,7 @@ __global__ void ozaki_rowscale_kernel(const double* __restrict__ P, int64_t lda,
 // pre-pass 2: error-free slicing, 16 consecutive k per thread -> one 16-byte store per slice
 template <int S>
 __global__ void ozaki_slice_kernel(const double* __restrict__ P, int64_t lda, int64_t m, int64_t m_fill, int64_t m_alloc,
-                                   int K, const double* __restrict__ rinv, int8_t* __restrict__ SL) {
+                                   int K, const double* __restrict__ rinv, int8_t* __restrict__ SL, int bulk) {
   const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int k0 = blockIdx.y * 16;
   if (row >= m_fill) return;
@@ -68,7 +68,16 @@ __global__ void ozaki_slice_kernel(const double* __restrict__ P, int64_t lda, in
       r[i] = fma(-q, dn, r[i]);
       pk.b[i] = (int8_t)(int)q;
     }
-    *reinterpret_cast<uint4*>(SL + ((int64_t)s * m_alloc + row) * K + k0) = pk.v;
+    if (bulk) {
+      // UMMA "interleaved" (no-swizzle) K-major layout, written directly: chunk (slice, 128-row block, 32-byte
+      // k-block) = 4096 contiguous bytes = [16 row-groups][2 k-halves][8 rows][16 B]  (SBO 256 B, LBO 128 B)
+      const int64_t rb = row >> 7, g = (row & 127) >> 3, r8 = row & 7;
+      const int kb = k0 >> 5, h = (k0 >> 4) & 1;
+      const int64_t chunk = ((int64_t)s * (m_alloc >> 7) + rb) * (K >> 5) + kb;
+      *reinterpret_cast<uint4*>(SL + chunk * 4096 + ((g * 2 + h) * 8 + r8) * 16) = pk.v;
+    } else {
+      *reinterpret_cast<uint4*>(SL + ((int64_t)s * m_alloc + row) * K + k0) = pk.v;
+    }
     up *= 128.0;
     dn *= (1.0 / 128.0);
   }
@@ -147,6 +156,7 @@ struct OzTileArgs {
   int64_t b_tile_width;          // distribution block width in columns (0 -> 128)
   const int64_t* strip_start;    // v2, block-cyclic: first tile index of every 64-column strip (nbj + 1 entries)
   const int32_t* strip_bimin;    // v2, block-cyclic: first valid 128-row tile of every strip
+  const int8_t* SLb;             // v2 bulk mode: slices in the blocked UMMA layout (nullptr -> tensor-map path)
   int lower_only;
 };
 
@@ -293,6 +303,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
   d |= (uint64_t)6 << 61;           // SWIZZLE_32B
   return d;
 }
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(128 >> 4) << 16;  // LBO: the two 16-byte K halves of a core-matrix pair are 128 B apart
+  d |= (uint64_t)(256 >> 4) << 32;  // SBO: 8-row groups are 256 B apart
+  d |= (uint64_t)1 << 46;           // descriptor version (Blackwell); layout type 0 = interleaved / no swizzle
+  return d;
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -315,21 +337,32 @@ __device__ __forceinline__ double ld_cs(const double* p) {
 }
 __device__ __forceinline__ void st_cs(double* p, double v) { asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 
-// tile index -> (bi, bj): row tile bi (128 rows) owns column tiles 0 .. min(nbj, 2*bi+2)-1
-__device__ __forceinline__ void v2_tile(int64_t t, int nbj, int& bi, int& bj) {
-  const int64_t B = nbj / 2;            // row tiles with the unclipped count 2*bi+2
-  const int64_t t_full = B * (B + 1);
-  if (t < t_full) {
-    int64_t b = (int64_t)((sqrt(4.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((b + 1) * (b + 2) <= t) ++b;
-    while (b * (b + 1) > t) --b;
-    bi = (int)b;
-    bj = (int)(t - b * (b + 1));
+// slot index -> (bi, bj) for the diagonal-anchored lower triangle, L2-BLOCKED: the tile grid is cut into
+// super-blocks of SB row tiles x 2*SB column tiles (2048 x 2048 elements for SB = 16); slots walk one
+// super-block at a time, so the 148 CTAs share ~15 MB of slices at any moment instead of cycling through the
+// whole slice buffer (which is about the size of L2).  Row tile bi owns column tiles 0 .. min(nbj, 2*bi+2)-1;
+// slots outside the triangle (in diagonal / edge super-blocks) are reported invalid and skipped by all roles.
+constexpr int V2_SB = 16;
+__device__ __forceinline__ bool v2_tile(int64_t t, int nbi, int nbj, int& bi, int& bj) {
+  constexpr int64_t PER = (int64_t)V2_SB * 2 * V2_SB;
+  const int64_t sb = t / PER;
+  const int w = (int)(t - sb * PER);
+  const int64_t nJ = (nbj + 2 * V2_SB - 1) / (2 * V2_SB);  // super-block columns
+  const int64_t t_full = nJ * (nJ + 1) / 2;                // super-block rows I < nJ hold I+1 super-blocks
+  int64_t I, Jc;
+  if (sb < t_full) {
+    I = (int64_t)((sqrt(8.0 * (double)sb + 1.0) - 1.0) * 0.5);
+    while ((I + 1) * (I + 2) / 2 <= sb) ++I;
+    while (I * (I + 1) / 2 > sb) --I;
+    Jc = sb - I * (I + 1) / 2;
   } else {
-    const int64_t r = t - t_full;
-    bi = (int)(B + r / nbj);
-    bj = (int)(r % nbj);
+    const int64_t r = sb - t_full;
+    I = nJ + r / nJ;
+    Jc = r % nJ;
   }
+  bi = (int)(I * V2_SB + w / (2 * V2_SB));
+  bj = (int)(Jc * 2 * V2_SB + w % (2 * V2_SB));
+  return bi < nbi && bj < nbj && bj < 2 * bi + 2;
 }
 
 // table-driven variant for the block-cyclic (multi-GPU) trailing update: strips are 64 columns wide,
@@ -344,21 +377,22 @@ __device__ __forceinline__ void v2_tile_tab(int64_t t, int nbj, const int64_t* _
   bj = lo;
   bi = bimin[lo] + (int)(t - start[lo]);
 }
-__device__ __forceinline__ void v2_decode(const OzTileArgs& a, int64_t t, int nbj, int& bi, int& bj, int64_t& brow) {
+__device__ __forceinline__ bool v2_decode(const OzTileArgs& a, int64_t t, int nbi, int nbj, int& bi, int& bj, int64_t& brow) {
   if (a.strip_start) {
     v2_tile_tab(t, nbj, a.strip_start, a.strip_bimin, bi, bj);
     const int64_t n0 = (int64_t)bj * OZ_BN, bw = a.b_tile_width ? a.b_tile_width : 128;
     brow = (n0 / bw) * a.b_tile_stride + (n0 % bw) + a.b_off;
-  } else {
-    v2_tile(t, nbj, bi, bj);
-    brow = (int64_t)bj * OZ_BN + a.b_off;
+    return true;
   }
+  const bool ok = v2_tile(t, nbi, nbj, bi, bj);
+  brow = (int64_t)bj * OZ_BN + a.b_off;
+  return ok;
 }
 
 template <int S>
 __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid_constant__ CUtensorMap tmapA,
                                                                     const __grid_constant__ CUtensorMap tmapB, OzTileArgs a,
-                                                                    int64_t ntiles, int nbj) {
+                                                                    int64_t ntiles, int nbi, int nbj) {
   constexpr int A_BYTES = OZ_BM * V2_KB, B_BYTES = OZ_BN * V2_KB;
   constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
   constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
@@ -392,18 +426,29 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
       for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int bi, bj;
         int64_t brow64;
-        v2_decode(a, t, nbj, bi, bj, brow64);
+        if (!v2_decode(a, t, nbi, nbj, bi, bj, brow64)) continue;
         const int arow = (int)(bi * OZ_BM + a.a_off), brow = (int)brow64;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int st = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[st], ph ^ 1);
           mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+          if (a.SLb) {  // contiguous 4 KB / 2 KB chunks already in the UMMA smem layout: 1-D bulk copies
+            const int64_t nrb = a.m_alloc >> 7, nkb = a.K >> 5;
 #pragma unroll 1
-          for (int sl = 0; sl < S; ++sl) {
-            const int rbase = (int)(sl * a.m_alloc);
-            tma_load_2d(a_tile(st, sl), &tmapA, kb * V2_KB, rbase + arow, &full_bar[st]);
-            tma_load_2d(b_tile(st, sl), &tmapB, kb * V2_KB, rbase + brow, &full_bar[st]);
+            for (int sl = 0; sl < S; ++sl) {
+              const int8_t* ca = a.SLb + (((int64_t)sl * nrb + (arow >> 7)) * nkb + kb) * 4096;
+              const int8_t* cb = a.SLb + (((int64_t)sl * nrb + (brow >> 7)) * nkb + kb) * 4096 + (brow & 64) * 32;
+              bulk_load(a_tile(st, sl), ca, A_BYTES, &full_bar[st]);
+              bulk_load(b_tile(st, sl), cb, B_BYTES, &full_bar[st]);
+            }
+          } else {
+#pragma unroll 1
+            for (int sl = 0; sl < S; ++sl) {
+              const int rbase = (int)(sl * a.m_alloc);
+              tma_load_2d(a_tile(st, sl), &tmapA, kb * V2_KB, rbase + arow, &full_bar[st]);
+              tma_load_2d(b_tile(st, sl), &tmapB, kb * V2_KB, rbase + brow, &full_bar[st]);
+            }
           }
         }
       }
@@ -412,7 +457,12 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
     if (lane == 0) {
       const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
       uint32_t it = 0, lt = 0;
-      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        {
+          int bi_, bj_;
+          int64_t br_;
+          if (!v2_decode(a, t, nbi, nbj, bi_, bj_, br_)) continue;
+        }
         mbar_wait(&tmem_empty_bar, (lt & 1) ^ 1);  // epilogue has drained the previous tile's accumulators
         tc_fence_after();
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -424,10 +474,10 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
 #pragma unroll 1
           for (int sl = 0; sl < S; ++sl) {
             const int Ns = (S - sl) * OZ_BN;
-            const uint64_t adesc = umma_desc_sw32(a0 + sl * A_BYTES);
+            const uint64_t adesc = a.SLb ? umma_desc_nosw(a0 + sl * A_BYTES) : umma_desc_sw32(a0 + sl * A_BYTES);
             for (int c = 0; c < Ns; c += 256) {
               const int nchunk = (Ns - c < 256) ? (Ns - c) : 256;
-              const uint64_t bdesc = umma_desc_sw32(b0 + c * V2_KB);
+              const uint64_t bdesc = a.SLb ? umma_desc_nosw(b0 + c * V2_KB) : umma_desc_sw32(b0 + c * V2_KB);
               const uint32_t idesc = idesc_base | ((uint32_t)(nchunk >> 3) << 17);
               umma_i8(tmem_base + (uint32_t)(sl * OZ_BN + c), adesc, bdesc, idesc, (kb == 0 && sl == 0) ? 0u : 1u);
             }
@@ -435,15 +485,16 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
           umma_commit(&empty_bar[st]);
         }
         umma_commit(&tmem_full_bar);
+        ++lt;
       }
     }
   } else {
     const int quarter = warp & 3;
     uint32_t lt = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
       int bi, bj;
       int64_t brow64;
-      v2_decode(a, t, nbj, bi, bj, brow64);
+      if (!v2_decode(a, t, nbi, nbj, bi, bj, brow64)) continue;
       const int64_t m0 = (int64_t)bi * OZ_BM, n0 = (int64_t)bj * OZ_BN;
       const int64_t row = m0 + 32 * quarter + lane;
       const bool row_ok = row < a.M;
@@ -490,6 +541,7 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
           }
         }
       }
+      ++lt;
     }
   }
   tc_fence_before();
@@ -533,11 +585,13 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
   OzTileArgs a{};
   a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.m_alloc = ws.m_alloc; a.K = ws.K; a.rscale = ws.rscale;
   a.b_tile_stride = b_tile_stride; a.b_tile_width = b_tile_width; a.b_off = b_off; a.a_off = a_off; a.lower_only = 1;
+  a.SLb = ws.bulk ? ws.SL : nullptr;
   const int nbi = (int)((M + OZ_BM - 1) / OZ_BM), nbj = (int)(N / OZ_BN);
   int64_t ntiles = 0;
-  if (b_tile_stride == 0 && a_off == b_off) {  // diagonal-anchored: closed-form enumeration
-    const int64_t B = nbj / 2;
-    ntiles = (nbi <= B) ? (int64_t)nbi * (nbi + 1) : B * (B + 1) + (int64_t)(nbi - B) * nbj;
+  if (b_tile_stride == 0 && a_off == b_off) {  // diagonal-anchored: closed-form, L2-blocked slot enumeration
+    const int64_t nJ = (nbj + 2 * V2_SB - 1) / (2 * V2_SB), nI = (nbi + V2_SB - 1) / V2_SB;
+    const int64_t nsb = (nI <= nJ) ? nI * (nI + 1) / 2 : nJ * (nJ + 1) / 2 + (nI - nJ) * nJ;
+    ntiles = nsb * (int64_t)V2_SB * 2 * V2_SB;  // slots, including the skipped ones of diagonal / edge super-blocks
   } else {  // block-cyclic column map: per-strip table (host -> device, a few KB)
     std::vector<int64_t> start((size_t)nbj + 1);
     std::vector<int32_t> bimin((size_t)nbj);
@@ -562,14 +616,14 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
   }
   if (ntiles <= 0) return;
   const int grid = (int)(ntiles < nsm ? ntiles : nsm);
-  umma_ozaki_syrk_v2_kernel<S><<<grid, 192, smem, s>>>(ws.tmapA32, ws.tmapB32, a, ntiles, nbj);
+  umma_ozaki_syrk_v2_kernel<S><<<grid, 192, smem, s>>>(ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
   agp_count_launch();
 }
 
 template <int S>
 void launch_syrk_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int lower_only, int64_t b_tile_stride,
                    int64_t b_tile_width, int64_t b_off, int64_t a_off, cudaStream_t s) {
-  if (ws.use_v2 && lower_only && N % 128 == 0 && N >= 128 && N / OZ_BN <= ws.tab_cap) {
+  if ((ws.use_v2 || ws.bulk) && lower_only && N % 128 == 0 && N >= 128 && N / OZ_BN <= ws.tab_cap) {
     launch_syrk_v2_S<S>(ws, C, ldc, M, N, b_tile_stride, b_tile_width, b_off, a_off, s);
     return;
   }
@@ -618,6 +672,8 @@ int ozaki_ws_create(OzakiWs* ws, int64_t max_rows, int K, int S, cudaStream_t s)
   if (r != CUDA_SUCCESS) return 4;
   const char* v = getenv("AGP_OZAKI_V2");
   ws->use_v2 = v ? atoi(v) : 1;
+  const char* b = getenv("AGP_OZAKI_BULK");
+  ws->bulk = (ws->use_v2 && (b ? atoi(b) : 1)) ? 1 : 0;
   return 0;
 }
 
@@ -636,10 +692,10 @@ void ozaki_prepare(const OzakiWs& ws, const double* P, int64_t lda, int64_t m, c
   const int64_t m_used = (m + 127) / 128 * 128;  // zero-fill up to the tile edge
   dim3 grid((unsigned)((m_used + 127) / 128), (unsigned)(ws.K / 16));
   switch (ws.S) {
-    case 5: ozaki_slice_kernel<5><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL); break;
-    case 6: ozaki_slice_kernel<6><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL); break;
-    case 7: ozaki_slice_kernel<7><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL); break;
-    default: ozaki_slice_kernel<8><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL); break;
+    case 5: ozaki_slice_kernel<5><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL, ws.bulk); break;
+    case 6: ozaki_slice_kernel<6><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL, ws.bulk); break;
+    case 7: ozaki_slice_kernel<7><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL, ws.bulk); break;
+    default: ozaki_slice_kernel<8><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL, ws.bulk); break;
   }
   agp_count_launch();
 }

@@ -45,6 +45,30 @@ def main():
         if rank == 0:
             print("n=%d %s fam=%d: logpdf %s ref %s  ok=%s" % (n, np.dtype(dtype).name, fam, lp, lp_ref, good), flush=True)
         ok &= bool(good)
+    # VFE elbo with the data dimension sharded over the ranks (one all-reduce): must match the oracle
+    for dtype in (np.float64, np.float32):
+        n, m, d = 3000, 200, 4
+        rng = np.random.default_rng(5)
+        X = rng.random((n, d)).astype(dtype)
+        yv = (np.sin(X.sum(1)) + 0.1 * rng.standard_normal(n)).astype(dtype)
+        Z = X[rng.permutation(n)[:m]].copy()
+        ksr = ref.KernelSpec(ref.SE, 1.0, ref.T_SCALE, scale=1.0)
+        ks = cabi.agp_kernel()
+        ks.family, ks.transform, ks.variance, ks.scale = 0, 1, 1.0, 1.0
+        ns = cabi.agp_noise()
+        ns.kind, ns.s = 0, 0.1
+        js = cabi.agp_noise()
+        js.kind, js.s = 0, (1e-6 if dtype == np.float64 else 1e-3)
+        out = np.zeros(2, dtype=dtype)
+        rc = eng.L.agp_vfe_elbo(eng.h, cabi.dtype_code(dtype), C.byref(ks), None, C.byref(ns), cabi.AGP_POINT_MAJOR,
+                                cabi.ptr(X), n, d, cabi.ptr(Z), m, C.byref(js), cabi.ptr(yv), cabi.ptr(out[0:1]), cabi.ptr(out[1:2]))
+        eng.check(rc)
+        el = ref.elbo(ksr, ref.MeanSpec(), ref.NoiseSpec(0, 0.1), X.astype(np.float64), yv.astype(np.float64),
+                      Z.astype(np.float64), ref.NoiseSpec(0, js.s))
+        good = abs(out[0] - el) <= (1e-8 if dtype == np.float64 else 2e-3) * abs(el)
+        if rank == 0:
+            print("vfe %s: elbo %r ref %r ok=%s" % (np.dtype(dtype).name, out[0], el, good), flush=True)
+        ok &= bool(good)
     # non-PD must surface on every rank, not hang
     n = 200
     X = np.zeros((n, 1))
