@@ -106,3 +106,58 @@ def test_block_cyclic_schedule_world(world):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok, _, _ in res), res
+
+
+def _vfe_worker(rank, world, port, out):
+    """VFE with the data dimension sharded over ranks and ONE all-reduce of (D, b, scalars) -- the schedule of
+    vfe_core in csrc/engine.cu -- must reproduce the oracle's elbo."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import scipy.linalg as sla
+    from oracle import agp_ref as ref
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    rng = np.random.default_rng(1)
+    n, m, d = 501, 40, 3
+    X = rng.random((n, d))
+    y = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(n)
+    Z = X[:m].copy()
+    ks = ref.KernelSpec(ref.SE, 1.2, ref.T_SCALE, scale=1.5)
+    s2, jit = 0.1, 1e-8
+    per = (n + world - 1) // world
+    lo, hi = min(n, rank * per), min(n, rank * per + per)       # same split as vfe_core
+    Kzz = ref.kernelmatrix(ks, Z) + jit * np.eye(m)
+    U = ref.cholesky_upper(Kzz)
+    Xl, yl = X[lo:hi], y[lo:hi]
+    A = sla.solve_triangular(U, (ref.kernelmatrix(ks, Xl, Z) / np.sqrt(s2)).T, trans="T", lower=False)  # M x n_local
+    delta = yl / np.sqrt(s2)
+    D = torch.from_numpy(A @ A.T)
+    b = torch.from_numpy(A @ delta)
+    sc = torch.tensor([len(yl) * np.log(s2), float(delta @ delta), float(ks.variance * len(yl) / s2), float((A * A).sum())])
+    for t in (D, b, sc):
+        dist.all_reduce(t)                                       # the one exchange step
+    Lam = ref.cholesky_upper(D.numpy() + np.eye(m))
+    sq = float((sla.solve_triangular(Lam, b.numpy(), trans="T", lower=False) ** 2).sum())
+    dtc = -0.5 * (n * np.log(2 * np.pi) + sc[0].item() + ref.logdet_chol(Lam) + sc[1].item() - sq)
+    elbo = dtc - 0.5 * (sc[2].item() - sc[3].item())
+    want = ref.elbo(ks, ref.MeanSpec(), ref.NoiseSpec(0, s2), X, y, Z, ref.NoiseSpec(0, jit))
+    out.put((rank, bool(abs(elbo - want) <= 1e-9 * abs(want)), float(elbo), float(want)))
+    dist.destroy_process_group()
+
+
+def test_vfe_data_sharding_world2():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_vfe_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _, _ in res), res
