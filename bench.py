@@ -321,7 +321,10 @@ def run_ours(args, wl):
     roofline.update({"launches_per_step": len(outer), "alg_flops_per_step": tf, "kernel_ms_per_step": trailing_ms,
                      "traffic_ncu": ncu_traffic(mode),
                      "kernel_timing": "CUDA events around each launch, look-ahead off (serial), %d steps" % max(2, min(args.steps, 5)),
-                     "panel_width": nb, "traffic": None, "cublas_dgemm_tflops": dgemm,
+                     "panel_width": nb, "cublas_dgemm_tflops": dgemm,
+                     # dram bytes of ONE launch from the committed `ncu --set full` capture; it was taken on the C4h
+                     # workload, so it is only comparable (per launch) when that workload is benched
+                     "traffic": (ncu_traffic(mode) or {}).get("dram_bytes_per_launch") if wl == "C4h" else None,
                      "cholesky_third_n3_tflops": chol_tf, "cholesky_frac_of_dgemm": chol_tf / dgemm})
 
     # CPU baseline (oracle port of the reference's LAPACK path) on this box's host cores, bounded sample
