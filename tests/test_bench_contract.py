@@ -1,0 +1,30 @@
+"""bench.py contract (CPU part): the reference arm prints ONE JSON line with the required keys, and the
+algorithmic-flop helper matches N^3/3 to leading order."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout + r.stderr
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["higher_is_better"] is False and d["unit"] == "ms" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"] and "C2" in d["config"]["workload"]
+
+
+def test_trailing_flops_close_to_third_n_cubed():
+    sys.path.insert(0, ROOT)
+    import bench
+    for n in (4096, 32768):
+        assert abs(bench.trailing_flops(n) / (n ** 3 / 3.0) - 1.0) < 0.06
