@@ -550,6 +550,18 @@ def _gram(f: GP, pts: _Points, pts2: Optional[_Points], s2, dt):
     return K
 
 
+def kernelmatrix(k: Kernel, x, y=None):
+    """KernelFunctions.kernelmatrix(k, x[, y]) -- what cov(f, x[, y]) forwards to (src/base_gp.jl:70,74)."""
+    pts = _Points(x)
+    dt = np.result_type(pts.a.dtype, np.float32)
+    return _gram(GP(k), pts, None if y is None else _Points(y), None, dt)
+
+
+def kernelmatrix_diag(k: Kernel, x):
+    """KernelFunctions.kernelmatrix_diag(k, x) -- what var(f, x) forwards to (src/base_gp.jl:72)."""
+    return var(GP(k), x)
+
+
 def mean(f, x=None):
     """mean(fx) (src/finite_gp_projection.jl:53) / mean(f, x) (src/abstract_gp.jl:19)."""
     if isinstance(f, FiniteGP):
