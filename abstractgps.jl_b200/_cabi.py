@@ -59,11 +59,13 @@ SIGNATURES = {
                             C.POINTER(_P)]),
     "agp_post_mean_var": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _M, _N, _P, _P]),
     "agp_post_mean_cov": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _M, _P, _P]),
+    "agp_post_logpdf": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _M, _N, _P, C.c_int32, _P]),
+    "agp_post_rand": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _M, _N, _P, C.c_int32, _P]),
     "agp_post_solve_lower": (C.c_int32, [_P, _P, C.c_int64, _P]),
     "agp_post_factor_export": (C.c_int32, [_P, _P]),
     "agp_post_logdet": (C.c_int32, [_P, C.POINTER(C.c_double)]),
     "agp_post_n": (C.c_int64, [_P]),
-    "agp_post_extend": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _P, _M, _N, _P]),
+    "agp_post_extend": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _P, _M, _N, _P, C.POINTER(_P)]),
     "agp_post_free": (C.c_int32, [_P]),
     "agp_rand": (C.c_int32, [_P, C.c_int32, _K, _M, _N, C.c_int32, _P, C.c_int64, C.c_int32, _P, C.c_int32, _P]),
     "agp_vfe_elbo": (C.c_int32, [_P, C.c_int32, _K, _M, _N, C.c_int32, _P, C.c_int64, C.c_int32, _P, C.c_int64, _N,

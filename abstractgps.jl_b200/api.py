@@ -482,8 +482,54 @@ def _fit(fx: FiniteGP, Y, want_post: bool, want_alpha: bool):
 def logpdf(fx: FiniteGP, y):
     """logpdf(fx, y) (src/finite_gp_projection.jl:306-311); matrix y -> per-column values."""
     if isinstance(fx.f, PosteriorGP):
-        raise AGPError(cabi.AGP_ERR_UNSUPPORTED, "logpdf of a posterior FiniteGP is a 'next' row (SURVEY s8f rank 3)")
+        return _post_logpdf(fx, y)
+    if not isinstance(fx.f, GP):
+        raise AGPError(cabi.AGP_ERR_UNSUPPORTED, "logpdf of a FiniteGP over %s is outside the device hot path"
+                       % type(fx.f).__name__)
     return _fit(fx, y, False, False)[0]
+
+
+def _post_args(fx: FiniteGP):
+    p: PosteriorGP = fx.f
+    dt = p.data.C.dtype
+    pts = fx.x.astype(dt)
+    if pts.D != p.data.x.D:
+        raise DimensionMismatch("test points have D=%d, training points D=%d" % (pts.D, p.data.x.D))
+    keep = []
+    ms = _mean_struct(p.prior.mean.spec(pts, dt), keep)
+    ns = _noise_struct(fx.s2, pts.n, dt, keep)
+    return p, dt, pts, ms, ns, keep
+
+
+def _post_logpdf(fx: FiniteGP, y):
+    """logpdf(f_post(x*, s2), y) (src/finite_gp_projection.jl:306-318 over src/exact_gpr_posterior.jl:78-83):
+    posterior covariance, noise add, Cholesky and the quadratic form all on the device (agp_post_logpdf)."""
+    eng = engine()
+    p, dt, pts, ms, ns, keep = _post_args(fx)
+    Y = np.asarray(y, dtype=dt)
+    vec = Y.ndim == 1
+    Yf = Y.reshape(-1, 1) if vec else Y
+    if Yf.shape[0] != pts.n:
+        raise DimensionMismatch("length(fx) = %d but y has %d rows" % (pts.n, Yf.shape[0]))
+    S = Yf.shape[1]
+    lp = np.empty(S, dtype=dt)
+    for s0 in range(0, S, 128):
+        s1 = min(S, s0 + 128)
+        Yc = np.asfortranarray(Yf[:, s0:s1])
+        eng.check(eng.L.agp_post_logpdf(p.data.C.h, cabi.AGP_POINT_MAJOR, cabi.ptr(pts.a), pts.n, C.byref(ms),
+                                        C.byref(ns), cabi.ptr(Yc), s1 - s0, cabi.ptr(lp[s0:s1])))
+    return lp[0] if vec else lp
+
+
+def _post_rand_from_normals(fx: FiniteGP, Z, squeeze=False):
+    """rand(f_post(x*, s2), S) (src/finite_gp_projection.jl:233-240) through agp_post_rand."""
+    eng = engine()
+    p, dt, pts, ms, ns, keep = _post_args(fx)
+    Z = np.asfortranarray(np.asarray(Z, dtype=dt).reshape(pts.n, -1))
+    out = np.empty_like(Z, order="F")
+    eng.check(eng.L.agp_post_rand(p.data.C.h, cabi.AGP_POINT_MAJOR, cabi.ptr(pts.a), pts.n, C.byref(ms), C.byref(ns),
+                                  cabi.ptr(Z), Z.shape[1], cabi.ptr(out)))
+    return out[:, 0] if squeeze else out
 
 
 def loglikelihood(fx: FiniteGP, Y):  # src/finite_gp_projection.jl:304
@@ -661,10 +707,11 @@ def rand(*args):
     rng = args.pop(0) if not isinstance(args[0], FiniteGP) else np.random.default_rng()
     fx = args.pop(0)
     S = args.pop(0) if args else None
-    if not isinstance(fx.f, GP):
-        raise AGPError(cabi.AGP_ERR_UNSUPPORTED, "sampling from a posterior FiniteGP is a 'next' row (SURVEY s8f rank 3)")
+    if not isinstance(fx.f, (GP, PosteriorGP)):
+        raise AGPError(cabi.AGP_ERR_UNSUPPORTED, "sampling from a FiniteGP over %s is outside the device hot path"
+                       % type(fx.f).__name__)
     eng = engine()
-    dt = fx.dtype
+    dt = fx.f.data.C.dtype if isinstance(fx.f, PosteriorGP) else fx.dtype
     pts = fx.x.astype(dt)
     ns_cols = 1 if S is None else int(S)
     Z = np.asfortranarray(rng.standard_normal((pts.n, ns_cols)).astype(dt))
@@ -672,6 +719,8 @@ def rand(*args):
 
 
 def rand_from_normals(fx: FiniteGP, Z, squeeze=False):
+    if isinstance(fx.f, PosteriorGP):
+        return _post_rand_from_normals(fx, Z, squeeze)
     eng = engine()
     f = _prior_of(fx)
     dt = fx.dtype
@@ -700,11 +749,12 @@ def _posterior_sequential(fx: FiniteGP, y):
     ns = _noise_struct(fx.s2, pts.n, dt, keep)
     n1 = p.data.C.n
     alpha = np.empty(n1 + pts.n, dtype=dt)
+    h = C.c_void_p()
     eng.check(eng.L.agp_post_extend(p.data.C.h, cabi.AGP_POINT_MAJOR, cabi.ptr(pts.a), pts.n, cabi.ptr(y), C.byref(ms),
-                                    C.byref(ns), cabi.ptr(alpha)))
+                                    C.byref(ns), cabi.ptr(alpha), C.byref(h)))
     delta = np.concatenate([p.data.delta, y - p.prior.mean.vector(pts, dt)])
-    # the handle was extended in place: the new PosteriorGP takes it over
-    data = DeviceData(alpha=alpha, C=p.data.C, x=vcat(p.data.x, pts), delta=delta)
+    # a NEW device factor: like the reference, the posterior that was conditioned on stays usable
+    data = DeviceData(alpha=alpha, C=DeviceCholesky(eng, h, dt), x=vcat(p.data.x, pts), delta=delta)
     return PosteriorGP(p.prior, data)
 
 

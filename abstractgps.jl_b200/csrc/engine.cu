@@ -625,6 +625,111 @@ int post_mean_cov_impl(agp_post* p, int layout, const void* Xs, int64_t M, const
   return AGP_OK;
 }
 
+// ---- logpdf / rand of a FiniteGP over a posterior: logpdf(f_post(x*, Sigma*), Y) and rand(f_post(x*, Sigma*), S)
+// (/root/reference/src/finite_gp_projection.jl:306-311 and :233-237 applied to f = PosteriorGP, whose
+// mean_and_cov is /root/reference/src/exact_gpr_posterior.jl:78-83).  The M x M posterior covariance never
+// leaves the device: K** + Sigma* is generated straight into a factor buffer, V'V (V = L^-1 K(x, x*)) is
+// subtracted by one GEMM, and the same in-place Cholesky as agp_fit runs with (Y - m*)' in the border tile.
+template <typename T>
+int post_cond_impl(agp_post* p, int layout, const void* Xs, int64_t M, const agp_mean* mean_s,
+                   const agp_noise* noise_s, const void* Y, int S, void* logpdf_out, const void* Z, int Sz,
+                   void* rand_out) {
+  agp_ctx* ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  CK(cudaSetDevice(ctx->device));
+  if (M <= 0) { ctx->err = "M must be positive"; return AGP_ERR_DIM_MISMATCH; }
+  if (!Xs) { ctx->err = "Xs is NULL"; return AGP_ERR_INVALID; }
+  if (S < 0 || S > TILE) { ctx->err = "number of right-hand sides must be in [0,128]"; return AGP_ERR_UNSUPPORTED; }
+  if (S > 0 && (!Y || !logpdf_out)) { ctx->err = "Y/logpdf_out is NULL"; return AGP_ERR_INVALID; }
+  if (Sz > 0 && (!Z || !rand_out)) { ctx->err = "Z/out is NULL"; return AGP_ERR_INVALID; }
+  static const agp_noise default_noise{0, 1e-18, nullptr};  // default_sigma^2, finite_gp_projection.jl:17
+  if (!noise_s) noise_s = &default_noise;
+  if (noise_s->kind == 1 && !noise_s->v) { ctx->err = "noise vector is NULL"; return AGP_ERR_INVALID; }
+  agp_mean mz{p->mean_kind, p->mean_c, nullptr};
+  if (!mean_s) mean_s = &mz;
+  if (mean_s->kind == 2 && !mean_s->v) { ctx->err = "mean vector is NULL"; return AGP_ERR_INVALID; }
+
+  const int64_t m_pad = round_up(M, TILE), ldf = m_pad + TILE;
+  const int nblk = (int)(m_pad / TILE);
+  Scratch sc(ctx);
+  T *Xst = nullptr, *B = nullptr;
+  int rc = post_cross<T>(p, sc, layout, Xs, M, m_pad, &Xst, &B);
+  if (rc) return rc;
+  T *mean_d = nullptr, *noise_d = nullptr, *Yd = nullptr;
+  if (mean_s->kind == 2) { rc = upload<T>(ctx, sc, mean_s->v, M, true, &mean_d); if (rc) return rc; }
+  if (noise_s->kind == 1) { rc = upload<T>(ctx, sc, noise_s->v, M, true, &noise_d); if (rc) return rc; }
+  if (S > 0) { rc = upload<T>(ctx, sc, Y, (size_t)M * S, false, &Yd); if (rc) return rc; }
+  void* tmp = nullptr;
+  CK(sc.alloc(&tmp, (size_t)m_pad * sizeof(T)));
+  T* mu = (T*)tmp;
+  CK(cudaMemsetAsync(mu, 0, (size_t)m_pad * sizeof(T), s));
+  // posterior mean m* = m(x*) + K(x*, x) alpha, then V = L^-1 K(x, x*) in place
+  launch_gemv_t<T>(B, p->n_pad, p->n_pad, M, (const T*)p->alpha, mean_s->kind, mean_s->c, mean_d, mu, s);
+  forward_subst_multi<T>(ctx, (const T*)p->L, p->lda, (const T*)p->Dinv, p->n_pad, B, p->n_pad, m_pad);
+  // C* + Sigma* = K(x*, x*) + Sigma* - V'V, lower triangle, identity padding
+  CK(sc.alloc(&tmp, (size_t)ldf * m_pad * sizeof(T)));
+  T* Lf = (T*)tmp;
+  CK(sc.alloc(&tmp, (size_t)nblk * TILE * TILE * sizeof(T)));
+  T* Dinv = (T*)tmp;
+  GramParams gp{};
+  fill_gram_params<T>(gp, &p->k, 1, 1, M, M, noise_s, noise_d);
+  launch_gram<T>(Xst, Xst, m_pad, m_pad, p->D, Lf, ldf, gp, s);
+  {
+    GemmArgs g{};
+    g.A = B; g.lda = p->n_pad; g.a_kmajor = 1;
+    g.B = B; g.ldb = p->n_pad; g.b_kmajor = 1;
+    g.C = Lf; g.ldc = ldf; g.M = m_pad; g.N = m_pad; g.K = p->n_pad;
+    g.alpha_neg = 1; g.beta_one = 1; g.lower_only = 1;
+    launch_gemm<T>(g, s);
+  }
+  launch_border_init<T>(Lf, ldf, M, m_pad, Yd, M, S, 2, 0.0, (const T*)mu, s);  // border = (Y - m*)'
+  CK(sc.alloc(&tmp, (size_t)(nblk + TILE + 2) * sizeof(double)));
+  double* dscal = (double*)tmp;
+  CK(sc.alloc(&tmp, sizeof(int)));
+  int* dinfo = (int*)tmp;
+  CK(cudaMemsetAsync(dinfo, 0, sizeof(int), s));
+  CK(sc.alloc(&tmp, (size_t)TILE * sizeof(T)));
+  T* lp_d = (T*)tmp;
+  prof_begin(ctx);
+  cholesky_inplace<T>(ctx, Lf, ldf, m_pad, ldf, Dinv, dscal, dinfo);
+  if (S > 0) {
+    CK(sc.alloc(&tmp, (size_t)S * m_pad * sizeof(T)));
+    launch_extract_v<T>(Lf, ldf, m_pad, S, (T*)tmp, dscal + nblk, s);
+    launch_finalize_logpdf<T>(dscal, nblk, dscal + nblk, S, M, lp_d, dscal + nblk + TILE, s);
+  }
+  int h_info = 0;
+  CK(cudaMemcpyAsync(&h_info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  if (h_info != 0) {
+    ctx->info = h_info;
+    char b[128];
+    snprintf(b, sizeof(b), "posterior covariance is not positive definite; Cholesky failed at pivot %d", h_info);
+    ctx->err = b;
+    return AGP_ERR_NOT_POSDEF;
+  }
+  if (S > 0) CK(cudaMemcpyAsync(logpdf_out, lp_d, (size_t)S * sizeof(T), cudaMemcpyDeviceToHost, s));
+  if (Sz > 0) {  // out = m* + L* Z  (C.U' * randn, finite_gp_projection.jl:235)
+    const int64_t s_pad = round_up(Sz, 4);
+    CK(sc.alloc(&tmp, (size_t)m_pad * s_pad * sizeof(T) * 2));
+    T* Zd = (T*)tmp; T* Od = Zd + m_pad * s_pad;
+    CK(cudaMemsetAsync(Zd, 0, (size_t)m_pad * s_pad * sizeof(T), s));
+    cudaMemcpyKind kin = ctx->memspace == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cudaMemcpyKind kout = ctx->memspace == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    CK(cudaMemcpy2DAsync(Zd, (size_t)m_pad * sizeof(T), Z, (size_t)M * sizeof(T), (size_t)M * sizeof(T), (size_t)Sz, kin, s));
+    GemmArgs g{};
+    g.A = Lf; g.lda = ldf; g.a_kmajor = 0;
+    g.B = Zd; g.ldb = m_pad; g.b_kmajor = 1;
+    g.C = Od; g.ldc = m_pad; g.M = m_pad; g.N = s_pad; g.K = m_pad; g.trmm_lower = 1;
+    launch_gemm<T>(g, s);
+    launch_add_mean_cols<T>(Od, m_pad, M, Sz, 2, 0.0, (const T*)mu, s);
+    CK(cudaMemcpy2DAsync(rand_out, (size_t)M * sizeof(T), Od, (size_t)m_pad * sizeof(T), (size_t)M * sizeof(T), (size_t)Sz, kout, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  return AGP_OK;
+}
+
 template <typename T>
 int post_solve_lower_impl(agp_post* p, const void* Bh, int64_t nrhs, void* V_out) {
   agp_ctx* ctx = p->ctx;
@@ -694,7 +799,7 @@ int post_export_impl(agp_post* p, void* U_out) {
 // rows carry [delta1; delta2]' through all of it, so v = L^-1 delta comes out of the same kernels.
 template <typename T>
 int post_extend_impl(agp_post* p, int layout, const void* X2, int64_t N2, const void* y2, const agp_mean* mean2,
-                     const agp_noise* noise2, void* alpha_out) {
+                     const agp_noise* noise2, void* alpha_out, agp_post** post_out) {
   agp_ctx* ctx = p->ctx;
   cudaStream_t s = ctx->stream;
   CK(cudaSetDevice(ctx->device));
@@ -797,10 +902,20 @@ int post_extend_impl(agp_post* p, int layout, const void* X2, int64_t N2, const 
     ctx->err = "extended covariance is not positive definite";
     return AGP_ERR_NOT_POSDEF;
   }
-  // swap the new state in
-  cudaFreeAsync(p->L, s); cudaFreeAsync(p->Dinv, s); cudaFreeAsync(p->Xt, s); cudaFreeAsync(p->alpha, s);
-  cudaFreeAsync(p->delta, s);
-  if (p->valid) cudaFreeAsync(p->valid, s);
+  if (post_out) {  // the reference's semantics: a NEW posterior, the conditioned-on one stays valid
+    agp_post* q = new agp_post(*p);
+    q->ard = nullptr;
+    if (p->ard) {
+      cudaMallocAsync(&q->ard, (size_t)D * sizeof(T), s);
+      cudaMemcpyAsync(q->ard, p->ard, (size_t)D * sizeof(T), cudaMemcpyDeviceToDevice, s);
+    }
+    *post_out = q;
+    p = q;
+  } else {  // in place: the old state is released
+    cudaFreeAsync(p->L, s); cudaFreeAsync(p->Dinv, s); cudaFreeAsync(p->Xt, s); cudaFreeAsync(p->alpha, s);
+    cudaFreeAsync(p->delta, s);
+    if (p->valid) cudaFreeAsync(p->valid, s);
+  }
   p->L = Ln; p->Dinv = Dn; p->Xt = Xn; p->alpha = an; p->delta = dn; p->valid = valid;
   p->segs.push_back({n1p, N2});
   p->n += N2; p->n_pad = np; p->lda = ldn; p->logdet += h_ld;
@@ -1424,6 +1539,22 @@ int32_t agp_post_mean_cov(agp_post* p, int32_t layout, const void* Xs, int64_t M
                   post_mean_cov_impl<double>(p, layout, Xs, M, mean_s, mean_out, cov_out));
 }
 
+int32_t agp_post_logpdf(agp_post* p, int32_t layout, const void* Xs, int64_t M, const agp_mean* mean_s,
+                        const agp_noise* noise_s, const void* Y, int32_t S, void* logpdf_out) {
+  if (!p) return AGP_ERR_INVALID;
+  if (S <= 0) { p->ctx->err = "S must be positive"; return AGP_ERR_INVALID; }
+  return DISPATCH(p->dtype, post_cond_impl<float>(p, layout, Xs, M, mean_s, noise_s, Y, S, logpdf_out, nullptr, 0, nullptr),
+                  post_cond_impl<double>(p, layout, Xs, M, mean_s, noise_s, Y, S, logpdf_out, nullptr, 0, nullptr));
+}
+
+int32_t agp_post_rand(agp_post* p, int32_t layout, const void* Xs, int64_t M, const agp_mean* mean_s,
+                      const agp_noise* noise_s, const void* Z, int32_t S, void* out) {
+  if (!p) return AGP_ERR_INVALID;
+  if (S <= 0) return AGP_OK;
+  return DISPATCH(p->dtype, post_cond_impl<float>(p, layout, Xs, M, mean_s, noise_s, nullptr, 0, nullptr, Z, S, out),
+                  post_cond_impl<double>(p, layout, Xs, M, mean_s, noise_s, nullptr, 0, nullptr, Z, S, out));
+}
+
 int32_t agp_post_solve_lower(agp_post* p, const void* B, int64_t nrhs, void* V_out) {
   if (!p || !B || !V_out) return AGP_ERR_INVALID;
   return DISPATCH(p->dtype, post_solve_lower_impl<float>(p, B, nrhs, V_out), post_solve_lower_impl<double>(p, B, nrhs, V_out));
@@ -1491,10 +1622,11 @@ int64_t agp_bc_local_tiles(int32_t nt, int32_t rank, int32_t P, int32_t Q) {
 
 // ---- multi-GPU entry points are provided by dist.cu ------------------------------------------------
 int32_t agp_post_extend(agp_post* p, int32_t layout, const void* X2, int64_t N2, const void* y2, const agp_mean* mean2,
-                        const agp_noise* noise2, void* alpha_out) {
+                        const agp_noise* noise2, void* alpha_out, agp_post** post_out) {
   if (!p) return AGP_ERR_INVALID;
-  return DISPATCH(p->dtype, post_extend_impl<float>(p, layout, X2, N2, y2, mean2, noise2, alpha_out),
-                  post_extend_impl<double>(p, layout, X2, N2, y2, mean2, noise2, alpha_out));
+  if (post_out) *post_out = nullptr;
+  return DISPATCH(p->dtype, post_extend_impl<float>(p, layout, X2, N2, y2, mean2, noise2, alpha_out, post_out),
+                  post_extend_impl<double>(p, layout, X2, N2, y2, mean2, noise2, alpha_out, post_out));
 }
 int32_t agp_vfe_elbo(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, const agp_mean* mean, const agp_noise* noise,
                      int32_t layout, const void* X, int64_t N, int32_t D, const void* Zind, int64_t M,

@@ -133,6 +133,17 @@ int32_t agp_post_mean_var(agp_post* p, int32_t layout, const void* Xs, int64_t M
  * src/util/common_covmat_ops.jl:54-58).  cov_out M x M column-major. */
 int32_t agp_post_mean_cov(agp_post* p, int32_t layout, const void* Xs, int64_t M,
                           const agp_mean* mean_s, void* mean_out, void* cov_out);
+/* logpdf(f_post(x*, Sigma*), Y): src/finite_gp_projection.jl:306-311 (matrix Y :313-318) for a
+ * FiniteGP over a PosteriorGP -- mean_and_cov(f_post, x*) src/exact_gpr_posterior.jl:78-83 is formed on
+ * the device, Sigma* (noise_s; NULL -> 1e-18) added, factored in place; the M x M covariance never visits
+ * the host.  Y is M x S column-major, S <= 128; logpdf_out[S].  AGP_ERR_NOT_POSDEF as agp_fit. */
+int32_t agp_post_logpdf(agp_post* p, int32_t layout, const void* Xs, int64_t M,
+                        const agp_mean* mean_s, const agp_noise* noise_s, const void* Y, int32_t S,
+                        void* logpdf_out);
+/* rand(f_post(x*, Sigma*), S): src/finite_gp_projection.jl:233-240, out = m* + chol(C* + Sigma*).U' Z with
+ * caller-supplied standard normals Z (M x S column-major) as agp_rand. */
+int32_t agp_post_rand(agp_post* p, int32_t layout, const void* Xs, int64_t M, const agp_mean* mean_s,
+                      const agp_noise* noise_s, const void* Z, int32_t S, void* out);
 /* V = U' \ B (N x nrhs, column-major): backs Xt_invA_X / diag_Xt_invA_X / Xt_invA_Y /
  * tr_Xt_invA_X on a device factor, src/util/common_covmat_ops.jl:54-60,90,101. */
 int32_t agp_post_solve_lower(agp_post* p, const void* B, int64_t nrhs, void* V_out);
@@ -141,10 +152,12 @@ int32_t agp_post_factor_export(agp_post* p, void* U_out);
 int32_t agp_post_logdet(agp_post* p, double* logdet_out); /* logdet(C) = 2 sum log U_ii */
 int64_t agp_post_n(const agp_post* p);
 /* sequential conditioning: posterior(fx::FiniteGP{<:PosteriorGP}, y) src/exact_gpr_posterior.jl:46-56
- * via update_chol src/util/common_covmat_ops.jl:38-42.  Extends the factor in place; alpha_out
- * receives the N1+N2 re-solved weights (or NULL). */
+ * via update_chol src/util/common_covmat_ops.jl:38-42.  alpha_out receives the N1+N2 re-solved weights
+ * (or NULL).  post_out != NULL: a NEW handle is returned and p stays valid (the reference's value
+ * semantics -- both posteriors usable, both to be freed); post_out == NULL: p is extended in place. */
 int32_t agp_post_extend(agp_post* p, int32_t layout, const void* X2, int64_t N2, const void* y2,
-                        const agp_mean* mean2, const agp_noise* noise2, void* alpha_out);
+                        const agp_mean* mean2, const agp_noise* noise2, void* alpha_out,
+                        agp_post** post_out);
 int32_t agp_post_free(agp_post* p);
 
 /* rand(rng, fx, S) / _rand! src/finite_gp_projection.jl:233-237,271-277: out = m + U' Z with the

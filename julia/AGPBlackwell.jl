@@ -153,6 +153,44 @@ function mean_and_var(fx::FiniteGP{<:DevPosterior,<:DevInputs{T},<:Diagonal}) wh
     return μ, v
 end
 
+# FiniteGP over a device posterior: logpdf / rand / sequential conditioning stay on the device
+# (src/finite_gp_projection.jl:306-318, :233-237 and src/exact_gpr_posterior.jl:46-56 for f = PosteriorGP)
+const DevPostFiniteGP{T} = FiniteGP{<:DevPosterior,<:DevInputs{T},<:Diagonal}
+function logpdf(fx::DevPostFiniteGP{T}, Y::AbstractVecOrMat{<:Real}) where {T}
+    p = fx.f; c = ctx(); Xs, layout, D = points(fx.x); M = length(fx)
+    Ym = convert(Matrix{T}, reshape(Y, M, :)); lp = Vector{T}(undef, size(Ym, 2))
+    ms, k2 = mean_spec(p.prior.mean, fx.x, T); ns, k3 = noise_spec(fx.Σy, T)
+    lock(c.lock) do
+        GC.@preserve Xs Ym k2 k3 check(c, ccall((:agp_post_logpdf, libagp), Int32,
+            (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int64, Ref{AgpMean}, Ref{AgpNoise}, Ptr{Cvoid}, Int32, Ptr{Cvoid}),
+            p.data.C.h, layout, Xs, M, ms, ns, Ym, size(Ym, 2), lp))
+    end
+    return Y isa AbstractVector ? lp[1] : lp
+end
+function Random.rand(rng::Random.AbstractRNG, fx::DevPostFiniteGP{T}, S::Int) where {T}
+    p = fx.f; c = ctx(); Xs, layout, D = points(fx.x); M = length(fx)
+    Z = randn(rng, T, M, S); out = similar(Z)
+    ms, k2 = mean_spec(p.prior.mean, fx.x, T); ns, k3 = noise_spec(fx.Σy, T)
+    lock(c.lock) do
+        GC.@preserve Xs k2 k3 check(c, ccall((:agp_post_rand, libagp), Int32,
+            (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int64, Ref{AgpMean}, Ref{AgpNoise}, Ptr{Cvoid}, Int32, Ptr{Cvoid}),
+            p.data.C.h, layout, Xs, M, ms, ns, Z, S, out))
+    end
+    return out
+end
+function posterior(fx::DevPostFiniteGP{T}, y::AbstractVector{<:Real}) where {T}
+    p = fx.f; c = ctx(); X2, layout, D = points(fx.x); N2 = length(fx); N1 = p.data.C.n
+    yv = convert(Vector{T}, y); α = Vector{T}(undef, N1 + N2); post = Ref{Ptr{Cvoid}}(C_NULL)
+    ms, k2 = mean_spec(p.prior.mean, fx.x, T); ns, k3 = noise_spec(fx.Σy, T)
+    lock(c.lock) do
+        GC.@preserve X2 yv k2 k3 check(c, ccall((:agp_post_extend, libagp), Int32,
+            (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ref{AgpMean}, Ref{AgpNoise}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
+            p.data.C.h, layout, X2, N2, yv, ms, ns, α, post))
+    end
+    δ = vcat(p.data.δ, yv - AbstractGPs.mean_vector(p.prior.mean, fx.x))
+    return PosteriorGP(p.prior, (α=α, C=DeviceCholesky{T}(post[], N1 + N2), x=vcat(p.data.x, fx.x), δ=δ))
+end
+
 # replaces rand(rng, fx, S) src/finite_gp_projection.jl:233-237: the normals come from the caller's rng
 function Random.rand(rng::Random.AbstractRNG, fx::DevFiniteGP{T}, S::Int) where {T}
     c = ctx(); X, layout, D = points(fx.x); Z = randn(rng, T, length(fx), S); out = similar(Z)

@@ -278,6 +278,34 @@ def post_mean_and_cov(post, Xs, mean_s=None):
     return m_post, C_post
 
 
+def post_logpdf(post, Xs, noise_s: NoiseSpec, Y, mean_s=None):
+    """logpdf(f_post(x*, Sigma*), Y): the generic FiniteGP method src/finite_gp_projection.jl:306-311
+    (matrix Y :313-318) with f = PosteriorGP, i.e. mean_and_cov from src/exact_gpr_posterior.jl:78-83
+    plus Sigma* (src/finite_gp_projection.jl:133-136)."""
+    dtype = post["x"].dtype
+    Y = np.asarray(Y, dtype=dtype)
+    m, C = post_mean_and_cov(post, Xs, mean_s)
+    n = C.shape[0]
+    C = C.copy()
+    C[np.diag_indices(n)] += noise_s.diag(n, dtype)
+    U = cholesky_upper(C)
+    ld = dtype.type(logdet_chol(U))
+    sq = tr_Xt_invA_X(U, Y - m) if Y.ndim == 1 else diag_Xt_invA_X(U, Y - m[:, None])
+    return -((n * dtype.type(LOG2PI) + ld) + sq) / dtype.type(2)
+
+
+def post_rand_from_Z(post, Xs, noise_s: NoiseSpec, Z, mean_s=None):
+    """rand(rng, f_post(x*, Sigma*), S) src/finite_gp_projection.jl:233-237 with the caller's normals."""
+    dtype = post["x"].dtype
+    m, C = post_mean_and_cov(post, Xs, mean_s)
+    n = C.shape[0]
+    C = C.copy()
+    C[np.diag_indices(n)] += noise_s.diag(n, dtype)
+    U = cholesky_upper(C)
+    Z = np.asarray(Z, dtype=dtype)
+    return m + U.T @ Z if Z.ndim == 1 else m[:, None] + U.T @ Z
+
+
 def rand_from_Z(k, mean, noise, X, Z):
     """rand(rng, fx, S) src/finite_gp_projection.jl:233-237 with the caller's normals Z[N,S]:
     m .+ C.U' * Z."""
