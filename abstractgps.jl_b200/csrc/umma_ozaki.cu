@@ -158,6 +158,7 @@ struct OzTileArgs {
   const int32_t* strip_bimin;    // v2, block-cyclic: first valid 128-row tile of every strip
   const int8_t* SLb;             // v2 bulk mode: slices in the blocked UMMA layout (nullptr -> tensor-map path)
   int lower_only;
+  int epi;                       // v2 epilogue variant: 0 Horner over S fp64 terms, 1 int32 pair pre-combination (K <= 512); >=2 PROBE ONLY
 };
 
 template <int S>
@@ -506,6 +507,10 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
       //     trip (all S loads of a trip in flight before one wait), then hand the accumulators back to the MMA
       //     warp -- the C read-modify-write below overlaps the next tile's MMAs.
       double v[OZ_BN];
+      if (a.epi >= 3) {  // PROBE: no drain at all (3) -- results are garbage, timing only
+#pragma unroll
+        for (int i = 0; i < OZ_BN; ++i) v[i] = 0.0;
+      } else {
 #pragma unroll
       for (int c8 = 0; c8 < OZ_BN; c8 += 8) {
         uint32_t r[S][8];
@@ -513,6 +518,28 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
         for (int d = 0; d < S; ++d)
           tmem_ld8_nowait(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(d * OZ_BN + c8), r[d]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (a.epi == 1) {
+          // adjacent diagonals combined exactly in int32 first: |ACC_d| <= (d+1) * K * 64 * 64, so for K <= 512
+          // t_j = 128 * ACC_2j + ACC_2j+1 stays below 2^31 up to S = 8.  4 int->fp64 conversions and 4 fp64 ops
+          // per element instead of 7 and 6 (S = 7): the drain is bound by the fp64 pipe, not by tcgen05.ld.
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            double acc;
+            if constexpr (S & 1) {
+              acc = (double)(int)r[S - 1][i];
+              acc = fma(acc, 1.0 / 128.0, (double)((int)r[S - 3][i] * 128 + (int)r[S - 2][i]));
+#pragma unroll
+              for (int d = S - 5; d >= 0; d -= 2)
+                acc = fma(acc, 1.0 / 16384.0, (double)((int)r[d][i] * 128 + (int)r[d + 1][i]));
+            } else {
+              acc = (double)((int)r[S - 2][i] * 128 + (int)r[S - 1][i]);
+#pragma unroll
+              for (int d = S - 4; d >= 0; d -= 2)
+                acc = fma(acc, 1.0 / 16384.0, (double)((int)r[d][i] * 128 + (int)r[d + 1][i]));
+            }
+            v[c8 + i] = acc * (1.0 / 128.0);
+          }
+        } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           double acc = (double)(int)r[S - 1][i];
@@ -520,12 +547,14 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
           for (int d = S - 2; d >= 0; --d) acc = fma(acc, 1.0 / 128.0, (double)(int)r[d][i]);
           v[c8 + i] = acc;
         }
+        }
+      }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar);
       // (2) C -= scale_i * scale_j * v, streamed (.cs) so the int8 slices stay resident in L2
-      if (row_ok) {
+      if (row_ok && a.epi != 2 && a.epi != 3) {  // PROBE 2/3: no C read-modify-write
 #pragma unroll
         for (int c = 0; c < OZ_BN; c += 16) {
           double cv[16];
@@ -586,6 +615,14 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
   a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.m_alloc = ws.m_alloc; a.K = ws.K; a.rscale = ws.rscale;
   a.b_tile_stride = b_tile_stride; a.b_tile_width = b_tile_width; a.b_off = b_off; a.a_off = a_off; a.lower_only = 1;
   a.SLb = ws.bulk ? ws.SL : nullptr;
+  {
+    // default: the int32 pair pre-combination where it was measured and validated on the device (S = 7, K <= 512:
+    // +4.4% kernel throughput, sampled output bit-identical to variant 0 -- profiles/r01_ozaki_probe.json);
+    // AGP_OZAKI_EPI=0 restores the plain Horner drain, >= 2 are the timing-only variants of tools/ozaki_probe.py.
+    const char* e = getenv("AGP_OZAKI_EPI");
+    a.epi = e ? atoi(e) : 1;
+    if (a.epi == 1 && (ws.K > 512 || S != 7)) a.epi = 0;  // the int32 pair bound needs K <= 512
+  }
   const int nbi = (int)((M + OZ_BM - 1) / OZ_BM), nbj = (int)(N / OZ_BN);
   int64_t ntiles = 0;
   if (b_tile_stride == 0 && a_off == b_off) {  // diagonal-anchored: closed-form, L2-blocked slot enumeration
