@@ -316,6 +316,26 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// cluster variants (AGP_OZAKI_CLUSTER=2): one copy feeds the same smem offset of every CTA in ctaMask and signals
+// complete_tx on each destination CTA's own mbarrier at the same offset; the MMA warp's commit arrives on the
+// "stage free" barrier of every CTA, because a peer's copy may overwrite this CTA's stage.
+__device__ __forceinline__ void bulk_load_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -390,7 +410,12 @@ __device__ __forceinline__ bool v2_decode(const OzTileArgs& a, int64_t t, int nb
   return ok;
 }
 
-template <int S>
+// CL = CTAs per cluster (1 or 2).  CL = 2: the two CTAs of a cluster take slots 2u and 2u + 1 of the enumeration --
+// the same 128-row tile bi and the two 64-column strips of one 128-column block -- so they read the SAME A slices;
+// each CTA fetches half of every 4 KB A chunk and multicasts it to both (28 KB instead of 43 KB per K chunk and SM
+// from L2).  Validity of the two slots is identical (row bi owns an even number of strips, N is a multiple of 128),
+// so both CTAs run the same sequence of tiles and K chunks in lockstep.
+template <int S, int CL>
 __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid_constant__ CUtensorMap tmapA,
                                                                     const __grid_constant__ CUtensorMap tmapB, OzTileArgs a,
                                                                     int64_t ntiles, int nbi, int nbj) {
@@ -406,7 +431,7 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
   auto b_tile = [&](int st, int sl) { return base + st * STAGE_BYTES + S * A_BYTES + sl * B_BYTES; };
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
     mbar_init(&tmem_full_bar, 1);
     mbar_init(&tmem_empty_bar, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -418,8 +443,10 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (CL > 1) cluster_sync_all();  // every CTA's barriers exist before a peer's copy / commit can hit them
   const uint32_t tmem_base = tmem_base_s;
   const int num_kb = a.K / V2_KB;
+  constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -440,7 +467,13 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
             for (int sl = 0; sl < S; ++sl) {
               const int8_t* ca = a.SLb + (((int64_t)sl * nrb + (arow >> 7)) * nkb + kb) * 4096;
               const int8_t* cb = a.SLb + (((int64_t)sl * nrb + (brow >> 7)) * nkb + kb) * 4096 + (brow & 64) * 32;
-              bulk_load(a_tile(st, sl), ca, A_BYTES, &full_bar[st]);
+              if constexpr (CL > 1) {  // rows [64 r, 64 r + 64) of the A chunk are contiguous (8-row groups of 256 B)
+                constexpr int PART = A_BYTES / CL;
+                const uint32_t r = cluster_ctarank();
+                bulk_load_mc(a_tile(st, sl) + r * PART, ca + r * PART, PART, &full_bar[st], CL_MASK);
+              } else {
+                bulk_load(a_tile(st, sl), ca, A_BYTES, &full_bar[st]);
+              }
               bulk_load(b_tile(st, sl), cb, B_BYTES, &full_bar[st]);
             }
           } else {
@@ -483,7 +516,8 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
               umma_i8(tmem_base + (uint32_t)(sl * OZ_BN + c), adesc, bdesc, idesc, (kb == 0 && sl == 0) ? 0u : 1u);
             }
           }
-          umma_commit(&empty_bar[st]);
+          if constexpr (CL > 1) umma_commit_mc(&empty_bar[st], CL_MASK);
+          else umma_commit(&empty_bar[st]);
         }
         umma_commit(&tmem_full_bar);
         ++lt;
@@ -575,6 +609,7 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while a peer can still copy into it / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -603,13 +638,29 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
   constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
   static bool configured = false;
-  static int nsm = 148;
+  static int nsm = 148, ncl2 = -1;
   if (!configured) {
-    cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
+  }
+  int want_cl = 1;
+  {
+    const char* e = getenv("AGP_OZAKI_CLUSTER");  // EXPERIMENTAL (not yet validated on a device): 2 = A-multicast CTA pairs
+    want_cl = e ? atoi(e) : 1;
+  }
+  if (want_cl == 2 && ncl2 < 0) {  // how many 2-CTA clusters fit at once: the persistent grid must be fully co-resident
+    cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaLaunchConfig_t qc{};
+    qc.gridDim = dim3(2 * (unsigned)nsm); qc.blockDim = dim3(192); qc.dynamicSmemBytes = smem;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa; qc.numAttrs = 1;
+    ncl2 = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl2, umma_ozaki_syrk_v2_kernel<S, 2>, &qc) != cudaSuccess) { ncl2 = 0; cudaGetLastError(); }
   }
   OzTileArgs a{};
   a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.m_alloc = ws.m_alloc; a.K = ws.K; a.rscale = ws.rscale;
@@ -652,8 +703,21 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
     a.strip_bimin = d_bimin;
   }
   if (ntiles <= 0) return;
+  if (want_cl == 2 && ncl2 > 0 && a.SLb && !a.strip_start && ntiles >= 2) {
+    int64_t grid2 = 2 * (int64_t)ncl2;
+    if (grid2 > ntiles) grid2 = ntiles & ~(int64_t)1;  // the closed-form slot count is even
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3((unsigned)grid2); lc.blockDim = dim3(192); lc.dynamicSmemBytes = smem; lc.stream = s;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeClusterDimension;
+    la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+    lc.attrs = la; lc.numAttrs = 1;
+    cudaLaunchKernelEx(&lc, umma_ozaki_syrk_v2_kernel<S, 2>, ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
+    agp_count_launch();
+    return;
+  }
   const int grid = (int)(ntiles < nsm ? ntiles : nsm);
-  umma_ozaki_syrk_v2_kernel<S><<<grid, 192, smem, s>>>(ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
+  umma_ozaki_syrk_v2_kernel<S, 1><<<grid, 192, smem, s>>>(ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
   agp_count_launch();
 }
 

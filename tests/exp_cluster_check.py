@@ -1,0 +1,38 @@
+"""Helper for tests/test_gpu_experimental.py (run as a subprocess so that a device trap in an unvalidated kernel
+cannot poison the pytest process): runs the persistent tcgen05 SYRK with and without AGP_OZAKI_CLUSTER=2 on the same
+inputs and prints the largest difference.  Usage: python tests/exp_cluster_check.py N K S"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import agp_b200 as ag
+    N, K, S = (int(v) for v in sys.argv[1:4])
+    M = N + 128
+    eng = ag.engine()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    P = (torch.rand((K, M), generator=g, device="cuda", dtype=torch.float64) * 2 - 1).t()
+    P = P * torch.logspace(-3, 2, M, device="cuda", dtype=torch.float64)[:, None]
+    Pc = P.t().contiguous()
+    C0 = torch.rand((N, M), generator=g, device="cuda", dtype=torch.float64)
+    outs = []
+    for cl in ("1", "2"):
+        os.environ["AGP_OZAKI_CLUSTER"] = cl
+        Cc = C0.clone()
+        eng.check(eng.L.agp_debug_ozaki_syrk(eng.h, C.c_void_p(Cc.data_ptr()), M, C.c_void_p(Pc.data_ptr()), M, M, N, K, S, 1))
+        torch.cuda.synchronize()
+        outs.append(Cc.cpu().numpy())
+    d = np.abs(outs[0] - outs[1]).max()
+    changed = float(np.abs(outs[1] - C0.cpu().numpy()).max())
+    print("MAXDIFF %.3e CHANGED %.3e" % (d, changed))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,26 @@
+"""Kernels that compile but have NOT been validated on a device yet.  They are opt-in (environment switches, off by
+default) and so are these tests: set AGP_TEST_EXPERIMENTAL=1 to run them.  Each case runs in a subprocess under a
+timeout, so a protocol bug (the mbarrier spin limit traps) fails one test instead of the whole session.
+
+* AGP_OZAKI_CLUSTER=2 -- 2-CTA clusters on one row tile, A slices fetched half each and TMA-multicast
+  (umma_ozaki_syrk_v2_kernel<S, 2>): must be bit-identical to the single-CTA kernel."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("AGP_TEST_EXPERIMENTAL") != "1", reason="opt-in: AGP_TEST_EXPERIMENTAL=1")]
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("N,K,S", [(128, 128, 7), (1024, 256, 7), (4224, 512, 7), (2176, 512, 6), (8192, 512, 7)])
+def test_cluster_multicast_matches_single_cta(N, K, S):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "exp_cluster_check.py"), str(N), str(K), str(S)],
+                       capture_output=True, text=True, timeout=180, cwd=ROOT)
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = [l for l in r.stdout.splitlines() if l.startswith("MAXDIFF")][-1].split()
+    assert float(line[1]) == 0.0, line
+    assert float(line[3]) > 0.0, line  # the update really happened

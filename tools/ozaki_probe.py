@@ -135,8 +135,32 @@ for mode in (1, 3, 2, 4):
     d["fp64_equiv_tflops"] = flops / (d["syrk_ms"] * 1e-3) / 1e12
     out["partA"]["modes"][str(mode)] = d
     save()
-rt.cudaFree(dC)
-rt.cudaFree(dP)
+
+def cluster_part():
+    """EXPERIMENTAL kernel (A-multicast CTA pairs): opt-in with PROBE_CLUSTER=1 and run LAST -- a protocol bug traps and
+    kills the CUDA context, everything above is already saved."""
+    os.environ["AGP_OZAKI_EPI"] = "1"
+    os.environ["AGP_OZAKI_CLUSTER"] = "1"
+    syrk(1, M)
+    _, base = sample()
+    res = {}
+    for epi in (1, 3):
+        os.environ["AGP_OZAKI_CLUSTER"] = "2"
+        t = syrk(epi, M)
+        d = {"ms": t, "syrk_ms": t - fixed, "fp64_equiv_tflops": flops / ((t - fixed) * 1e-3) / 1e12}
+        if epi == 1:
+            _, got = sample()
+            d["max_abs_diff_vs_single_cta"] = float(max(np.max(np.abs(r - w)) for r, w in zip(got, base)))
+        res["cluster2_epi%d" % epi] = d
+        out["partA"]["cluster"] = res
+        save()
+    os.environ["AGP_OZAKI_CLUSTER"] = "1"
+
+
+run_cluster_last = os.environ.get("PROBE_CLUSTER") == "1"
+if not run_cluster_last:
+    rt.cudaFree(dC)
+    rt.cudaFree(dP)
 
 # ---------------- part B: full fit, C4h
 if os.environ.get("PROBE_FIT", "1") == "1":
@@ -171,4 +195,6 @@ if os.environ.get("PROBE_FIT", "1") == "1":
             out["partB"][tag] = {"wall_ms": best * 1e3, "device_ms": tm[0], "cholesky_ms": tm[3], "logpdf": float(lp[0])}
         save()
 save()
+if run_cluster_last:
+    cluster_part()
 print(json.dumps(out, indent=1))
