@@ -1323,6 +1323,31 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
   };
   bool rest_pending = false;
   size_t ev_idx = 0, last_rest = 0;
+  // EXPERIMENTAL schedule (AGP_DIST_SCHED=1, not yet validated on a multi-GPU box; default off).  The persistent
+  // update kernel holds every SM until it ends, so in the default order the next panel's owner factors it only
+  // AFTER its own rest update and every peer's broadcast kernel starts only after theirs: the step costs
+  // rest + factor + broadcast.  Here (1) the owner of panel kk+1 defers its rest update of step kk until panel kk+1
+  // is factored and packed (the broadcast is enqueued right behind), and (2) rest updates run on nsm - reserve
+  // CTAs so that the NCCL kernels of the next broadcast find SMs while the update is still running.
+  bool sched2 = false;
+  int reserve_sms = 16;
+  if (R > 1) {
+    const char* e1 = getenv("AGP_DIST_SCHED");
+    sched2 = e1 && atoi(e1) == 1;
+    const char* e2 = getenv("AGP_DIST_RESERVE_SMS");
+    if (e2) reserve_sms = atoi(e2);
+    if (reserve_sms < 0 || reserve_sms > 64) reserve_sms = 16;
+  }
+  int nsm_dev = 148;
+  cudaDeviceGetAttribute(&nsm_dev, cudaDevAttrMultiProcessorCount, ctx->device);
+  struct DeferredRest { bool on; int kk; T* Pk; int lo, hi; bool use_oz; cudaEvent_t e_rest; };
+  DeferredRest def{false, 0, nullptr, 0, 0, false, nullptr};
+  auto rest_update = [&](int kk, T* Pk, int lo, int hi, bool use_oz, cudaEvent_t e_rest) {
+    if (oz && sched2) oz->max_ctas = nsm_dev - reserve_sms;
+    trailing(kk, Pk, lo, hi, use_oz, s2);
+    if (oz) oz->max_ctas = 0;
+    cudaEventRecord(e_rest, s2);
+  };
   for (int kk = 0; kk < nto; ++kk) {
     const int owner = kk % R;
     const int64_t rows_below = lda - (int64_t)(kk + 1) * W;
@@ -1332,6 +1357,13 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
       T* Lp = L + (int64_t)kk * W + (int64_t)lk * W * lda;
       factor_panel<T>(ctx, Lp, lda, G, lda - (int64_t)kk * W, Dinv + (int64_t)lk * G * TILE * TILE, dscal, kk * G, dinfo, s);
       launch_copy2d<T>(Lp + W, lda, Pk, rows_below, rows_below, W, s);
+    }
+    if (def.on) {  // this rank owns panel kk and still owes step kk-1's rest update: it goes behind the factorisation
+      cudaEvent_t e_fact = dep_event(ctx, ev_idx++);
+      cudaEventRecord(e_fact, s);
+      cudaStreamWaitEvent(s2, e_fact, 0);
+      rest_update(def.kk, def.Pk, def.lo, def.hi, def.use_oz, def.e_rest);
+      def.on = false;
     }
     if (R > 1) CKN(ncclBroadcast(Pk, Pk, (size_t)rows_below * W, NcclType<T>::v, owner, ctx->nccl, s));
     if (kk == nto - 1) break;
@@ -1351,11 +1383,14 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
       trailing(kk, Pk, lj_first, lj_first + 1, use_oz, s);
       lj_bulk = lj_first + 1;
     }
-    cudaStreamWaitEvent(s2, e_panel, 0);
-    trailing(kk, Pk, lj_bulk, nloc, use_oz, s2);
-    cudaEventRecord(e_rest, s2);
     rest_pending = true;
-    last_rest = ev_idx - 1;
+    last_rest = ev_idx - 1;  // index of e_rest
+    if (sched2 && (kk + 1) % R == me) {
+      def = DeferredRest{true, kk, Pk, lj_bulk, nloc, use_oz, e_rest};  // launched at the top of the next iteration
+    } else {
+      cudaStreamWaitEvent(s2, e_panel, 0);
+      rest_update(kk, Pk, lj_bulk, nloc, use_oz, e_rest);
+    }
   }
   if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, last_rest), 0);
   join_inverses(ctx);

@@ -716,7 +716,8 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
     agp_count_launch();
     return;
   }
-  const int grid = (int)(ntiles < nsm ? ntiles : nsm);
+  const int cap = (ws.max_ctas > 0 && ws.max_ctas < nsm) ? ws.max_ctas : nsm;
+  const int grid = (int)(ntiles < cap ? ntiles : cap);
   umma_ozaki_syrk_v2_kernel<S, 1><<<grid, 192, smem, s>>>(ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
   agp_count_launch();
 }

@@ -19,6 +19,8 @@ struct OzakiWs {
   int32_t* tab_bimin;  // consecutive calls (main / side stream) alternate slots
   int tab_cap;
   mutable int tab_slot;
+  mutable int max_ctas;  // persistent (v2) kernel: cap on the grid, 0 = one CTA per SM.  The distributed schedule leaves
+                         // a few SMs to the NCCL broadcast that overlaps the update.
 };
 
 int ozaki_ws_create(OzakiWs* ws, int64_t max_rows, int K, int S, cudaStream_t s);  // 0 = ok
