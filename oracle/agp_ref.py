@@ -244,6 +244,73 @@ def logpdf(k, mean, noise, X, Y):
     return -((n * dtype.type(LOG2PI) + ld) + sq) / dtype.type(2)
 
 
+def _dkappa_r(family: int, d2: np.ndarray) -> np.ndarray:
+    """kappa'(r) * r for the stationary families (r = distance after the transform): the common factor of the
+    derivatives of kappa(s d) with respect to the ScaleTransform s (kappa' r / s) and the ARD weights."""
+    T = d2.dtype.type
+    if family == SE:
+        return -d2 * np.exp(-d2 / T(2))
+    d = np.sqrt(d2)
+    if family == MATERN12:
+        return -d * np.exp(-d)
+    if family == MATERN32:
+        return -T(3) * d2 * np.exp(-T(math.sqrt(3.0)) * d)
+    if family == MATERN52:
+        s5 = T(math.sqrt(5.0)) * d
+        return -(T(5) * d2 / T(3)) * (T(1) + s5) * np.exp(-s5)
+    raise ValueError(family)
+
+
+def logpdf_grad(k, mean, noise, X, y):
+    """Gradient of logpdf(fx, y) (src/finite_gp_projection.jl:306-311) with respect to the hyper-parameters the device
+    path carries -- what Zygote returns through the reference for `logpdf` in test/finite_gp_projection.jl:152-178 and
+    in the training loops of examples/1-mauna-loa/script.jl:200-242.  Closed form:
+    dL/dtheta = 1/2 tr((alpha alpha' - C^-1) dC/dtheta), dL/dm = alpha.  Returns a dict:
+      variance (sigma_f^2), scale (ScaleTransform s) or ard (vector), linear_c, noise (scalar or per-point vector),
+      mean_c (ConstMean) / mean_v (vector mean)."""
+    dtype = X.dtype
+    n = X.shape[0]
+    m, C = mean_and_cov_fx(k, mean, noise, X)
+    U = cholesky_upper(C)
+    delta = np.asarray(y, dtype=dtype) - m
+    alpha = _U_solve(U, _Ut_solve(U, delta))
+    Vinv = _Ut_solve(U, np.eye(n, dtype=dtype))  # U^-T
+    W = np.outer(alpha, alpha) - Vinv.T @ Vinv       # alpha alpha' - C^-1
+    g = {}
+    Kf = kernelmatrix(k, X)
+    g["variance"] = 0.5 * np.sum(W * Kf) / k.variance
+    Xt = k.apply_transform(X)
+    if k.family == LINEAR:
+        G = Xt @ Xt.T  # transformed inner products
+        g["linear_c"] = 0.5 * k.variance * np.sum(W)
+        if k.transform == T_SCALE:
+            g["scale"] = 0.5 * k.variance * np.sum(W * G) * 2.0 / k.scale
+        elif k.transform == T_ARD:
+            v = np.asarray(k.ard, dtype=dtype)
+            g["ard"] = np.array([0.5 * k.variance * 2.0 * v[d] * np.sum(W * np.outer(X[:, d], X[:, d])) for d in range(X.shape[1])])
+    else:
+        d2 = _pairwise_sqdist(Xt, Xt, "direct")
+        np.fill_diagonal(d2, 0)
+        KR = k.variance * _dkappa_r(k.family, d2)      # sigma_f^2 kappa'(r) r
+        if k.transform == T_SCALE:
+            g["scale"] = 0.5 * np.sum(W * KR) / k.scale
+        elif k.transform == T_ARD:
+            v = np.asarray(k.ard, dtype=dtype)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                Q = np.where(d2 > 0, KR / d2, 0.0)       # sigma_f^2 kappa'(r) / r
+            out = np.empty(X.shape[1], dtype=np.float64)
+            for d in range(X.shape[1]):
+                dd = X[:, d][:, None] - X[:, d][None, :]
+                out[d] = 0.5 * np.sum(W * Q * (v[d] * dd * dd))
+            g["ard"] = out
+    g["noise"] = 0.5 * np.trace(W) if noise.kind == 0 else 0.5 * np.diag(W).copy()
+    if mean.kind == 1:
+        g["mean_c"] = np.sum(alpha)
+    elif mean.kind == 2:
+        g["mean_v"] = alpha.copy()
+    return g
+
+
 def posterior(k, mean, noise, X, y):
     """posterior(fx, y) src/exact_gpr_posterior.jl:29-35 -> data = (alpha, C(U), x, delta)."""
     m, C = mean_and_cov_fx(k, mean, noise, X)

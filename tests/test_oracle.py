@@ -156,3 +156,56 @@ def test_c1_readme_toy_and_golden():
     assert np.allclose(post["alpha"], g["alpha"], rtol=1e-9)
     m, v = ref.post_mean_and_var(post, g["Xs"])
     assert np.allclose(m, g["mean_s"], rtol=1e-9) and np.allclose(v, g["var_s"], rtol=1e-7, atol=1e-12)
+
+
+# ---- SURVEY s8(f) rank 1 (next row): the gradient oracle, pinned by central finite differences of the oracle's own
+# logpdf, as the reference pins its AD rules with FiniteDifferences (test/finite_gp_projection.jl:152-178)
+@pytest.mark.parametrize("fam", [ref.SE, ref.MATERN12, ref.MATERN32, ref.MATERN52, ref.LINEAR])
+@pytest.mark.parametrize("transform", [ref.T_SCALE, ref.T_ARD])
+def test_logpdf_grad_matches_finite_differences(fam, transform):
+    import copy
+    rng = np.random.default_rng(7)
+    n, d = 40, 3
+    X = rng.random((n, d))
+    y = np.sin(3 * X[:, 0]) + 0.2 * rng.standard_normal(n)
+    k = ref.KernelSpec(fam, 1.3, transform, scale=1.7, ard=np.array([1.2, 0.7, 2.1]), linear_c=0.4)
+    mean = ref.MeanSpec(1, 0.25)
+    noise = ref.NoiseSpec(1, v=0.05 + 0.1 * rng.random(n))
+    g = ref.logpdf_grad(k, mean, noise, X, y)
+
+    def fd(setter, h=1e-6):
+        kp, mp, npz = copy.deepcopy(k), copy.deepcopy(mean), copy.deepcopy(noise)
+        setter(kp, mp, npz, +h)
+        up = ref.logpdf(kp, mp, npz, X, y)
+        kp, mp, npz = copy.deepcopy(k), copy.deepcopy(mean), copy.deepcopy(noise)
+        setter(kp, mp, npz, -h)
+        return (up - ref.logpdf(kp, mp, npz, X, y)) / (2 * h)
+
+    def chk(got, want):
+        assert abs(got - want) <= 2e-6 * max(1.0, abs(want)), (got, want)
+
+    chk(g["variance"], fd(lambda kp, mp, npz, h: setattr(kp, "variance", kp.variance + h)))
+    chk(g["mean_c"], fd(lambda kp, mp, npz, h: setattr(mp, "c", mp.c + h)))
+    if transform == ref.T_SCALE:
+        chk(g["scale"], fd(lambda kp, mp, npz, h: setattr(kp, "scale", kp.scale + h)))
+    else:
+        for j in range(d):
+            def bump(kp, mp, npz, h, j=j):
+                a = np.array(kp.ard, dtype=np.float64)
+                a[j] += h
+                kp.ard = a
+            chk(g["ard"][j], fd(bump))
+    if fam == ref.LINEAR:
+        chk(g["linear_c"], fd(lambda kp, mp, npz, h: setattr(kp, "linear_c", kp.linear_c + h)))
+    for j in (0, 17):
+        def bumpn(kp, mp, npz, h, j=j):
+            v = np.array(npz.v, dtype=np.float64)
+            v[j] += h
+            npz.v = v
+        chk(g["noise"][j], fd(bumpn))
+    # scalar noise: the trace
+    ns = ref.NoiseSpec(0, 0.1)
+    gs = ref.logpdf_grad(k, mean, ns, X, y)
+    h = 1e-6
+    want = (ref.logpdf(k, mean, ref.NoiseSpec(0, 0.1 + h), X, y) - ref.logpdf(k, mean, ref.NoiseSpec(0, 0.1 - h), X, y)) / (2 * h)
+    chk(gs["noise"], want)
