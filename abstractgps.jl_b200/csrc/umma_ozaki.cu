@@ -415,8 +415,10 @@ __device__ __forceinline__ bool v2_decode(const OzTileArgs& a, int64_t t, int nb
 // each CTA fetches half of every 4 KB A chunk and multicasts it to both (28 KB instead of 43 KB per K chunk and SM
 // from L2).  Validity of the two slots is identical (row bi owns an even number of strips, N is a multiple of 128),
 // so both CTAs run the same sequence of tiles and K chunks in lockstep.
-template <int S, int CL>
-__global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid_constant__ CUtensorMap tmapA,
+// NEPI = epilogue warps (4 or 8).  8: two warps per TMEM lane quarter, 32 of the tile's 64 columns each -- the drain
+// (tcgen05.ld + int->fp64 + Horner) is 12-15 % of the kernel and is issue / latency bound per warp, not TMEM bound.
+template <int S, int CL, int NEPI>
+__global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v2_kernel(const __grid_constant__ CUtensorMap tmapA,
                                                                     const __grid_constant__ CUtensorMap tmapB, OzTileArgs a,
                                                                     int64_t ntiles, int nbi, int nbj) {
   constexpr int A_BYTES = OZ_BM * V2_KB, B_BYTES = OZ_BN * V2_KB;
@@ -433,7 +435,7 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
     mbar_init(&tmem_full_bar, 1);
-    mbar_init(&tmem_empty_bar, 4);
+    mbar_init(&tmem_empty_bar, NEPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -525,12 +527,15 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
     }
   } else {
     const int quarter = warp & 3;
+    constexpr int CB = OZ_BN * 4 / NEPI;                          // columns drained by one epilogue warp
+    const int c0 = (NEPI == 4) ? 0 : ((warp - 2) >> 2) * CB;      // warps 2-5: columns [0, CB), warps 6-9: [CB, 2 CB)
     uint32_t lt = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
       int bi, bj;
       int64_t brow64;
       if (!v2_decode(a, t, nbi, nbj, bi, bj, brow64)) continue;
-      const int64_t m0 = (int64_t)bi * OZ_BM, n0 = (int64_t)bj * OZ_BN;
+      const int64_t m0 = (int64_t)bi * OZ_BM, n0 = (int64_t)bj * OZ_BN + c0;
+      brow64 += c0;
       const int64_t row = m0 + 32 * quarter + lane;
       const bool row_ok = row < a.M;
       const double rs = row_ok ? a.rscale[row + a.a_off] * (1.0 / 4096.0) : 0.0;
@@ -540,17 +545,17 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
       // (1) drain TMEM: Horner-combine the S int32 accumulators of all 64 columns into registers, 8 columns per
       //     trip (all S loads of a trip in flight before one wait), then hand the accumulators back to the MMA
       //     warp -- the C read-modify-write below overlaps the next tile's MMAs.
-      double v[OZ_BN];
+      double v[CB];
       if (a.epi >= 3) {  // PROBE: no drain at all (3) -- results are garbage, timing only
 #pragma unroll
-        for (int i = 0; i < OZ_BN; ++i) v[i] = 0.0;
+        for (int i = 0; i < CB; ++i) v[i] = 0.0;
       } else {
 #pragma unroll
-      for (int c8 = 0; c8 < OZ_BN; c8 += 8) {
+      for (int c8 = 0; c8 < CB; c8 += 8) {
         uint32_t r[S][8];
 #pragma unroll
         for (int d = 0; d < S; ++d)
-          tmem_ld8_nowait(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(d * OZ_BN + c8), r[d]);
+          tmem_ld8_nowait(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(d * OZ_BN + c0 + c8), r[d]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (a.epi == 1) {
           // adjacent diagonals combined exactly in int32 first: |ACC_d| <= (d+1) * K * 64 * 64, so for K <= 512
@@ -590,7 +595,7 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_v2_kernel(const __grid
       // (2) C -= scale_i * scale_j * v, streamed (.cs) so the int8 slices stay resident in L2
       if (row_ok && a.epi != 2 && a.epi != 3) {  // PROBE 2/3: no C read-modify-write
 #pragma unroll
-        for (int c = 0; c < OZ_BN; c += 16) {
+        for (int c = 0; c < CB; c += 16) {
           double cv[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -631,6 +636,36 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+// launch of an experimental variant (cluster size CL, NEPI epilogue warps) through cudaLaunchKernelEx; the persistent
+// grid must be fully co-resident, so with clusters it is capped by cudaOccupancyMaxActiveClusters
+template <int S, int CL, int NEPI>
+void launch_v2_variant(const OzakiWs& ws, const OzTileArgs& a, int64_t ntiles, int nbi, int nbj, int cap, size_t smem,
+                       cudaStream_t s) {
+  static int max_clusters = -1;
+  constexpr unsigned THREADS = 64 + 32 * NEPI;
+  cudaLaunchConfig_t lc{};
+  lc.blockDim = dim3(THREADS); lc.dynamicSmemBytes = smem; lc.stream = s;
+  cudaLaunchAttribute la[1];
+  la[0].id = cudaLaunchAttributeClusterDimension;
+  la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+  lc.attrs = la; lc.numAttrs = 1;
+  if (max_clusters < 0) {
+    cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S, CL, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lc.gridDim = dim3((unsigned)(cap / CL * CL));
+    max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, umma_ozaki_syrk_v2_kernel<S, CL, NEPI>, &lc) != cudaSuccess) {
+      max_clusters = 0;
+      cudaGetLastError();
+    }
+  }
+  int64_t grid = (int64_t)max_clusters * CL;
+  if (grid > cap) grid = cap / CL * CL;
+  if (grid > ntiles) grid = ntiles / CL * CL;  // the closed-form slot count is even
+  if (grid <= 0) return;
+  lc.gridDim = dim3((unsigned)grid);
+  cudaLaunchKernelEx(&lc, umma_ozaki_syrk_v2_kernel<S, CL, NEPI>, ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
+}
+
 template <int S>
 void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int64_t b_tile_stride,
                       int64_t b_tile_width, int64_t b_off, int64_t a_off, cudaStream_t s) {
@@ -638,29 +673,22 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
   constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
   static bool configured = false;
-  static int nsm = 148, ncl2 = -1;
+  static int nsm = 148;
   if (!configured) {
-    cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
-  int want_cl = 1;
+  // EXPERIMENTAL switches (the variants compile, none has run on a device yet; the default <S, 1, 4> kernel is the
+  // validated one): AGP_OZAKI_CLUSTER=2 -> A-multicast CTA pairs, AGP_OZAKI_EPIWARPS=8 -> two epilogue warps per quarter
+  int want_cl = 1, want_ew = 4;
   {
-    const char* e = getenv("AGP_OZAKI_CLUSTER");  // EXPERIMENTAL (not yet validated on a device): 2 = A-multicast CTA pairs
-    want_cl = e ? atoi(e) : 1;
-  }
-  if (want_cl == 2 && ncl2 < 0) {  // how many 2-CTA clusters fit at once: the persistent grid must be fully co-resident
-    cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaLaunchConfig_t qc{};
-    qc.gridDim = dim3(2 * (unsigned)nsm); qc.blockDim = dim3(192); qc.dynamicSmemBytes = smem;
-    cudaLaunchAttribute qa[1];
-    qa[0].id = cudaLaunchAttributeClusterDimension;
-    qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-    qc.attrs = qa; qc.numAttrs = 1;
-    ncl2 = 0;
-    if (cudaOccupancyMaxActiveClusters(&ncl2, umma_ozaki_syrk_v2_kernel<S, 2>, &qc) != cudaSuccess) { ncl2 = 0; cudaGetLastError(); }
+    const char* e = getenv("AGP_OZAKI_CLUSTER");
+    want_cl = (e && atoi(e) == 2) ? 2 : 1;
+    const char* f = getenv("AGP_OZAKI_EPIWARPS");
+    want_ew = (f && atoi(f) == 8) ? 8 : 4;
   }
   OzTileArgs a{};
   a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.m_alloc = ws.m_alloc; a.K = ws.K; a.rscale = ws.rscale;
@@ -703,22 +731,18 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
     a.strip_bimin = d_bimin;
   }
   if (ntiles <= 0) return;
-  if (want_cl == 2 && ncl2 > 0 && a.SLb && !a.strip_start && ntiles >= 2) {
-    int64_t grid2 = 2 * (int64_t)ncl2;
-    if (grid2 > ntiles) grid2 = ntiles & ~(int64_t)1;  // the closed-form slot count is even
-    cudaLaunchConfig_t lc{};
-    lc.gridDim = dim3((unsigned)grid2); lc.blockDim = dim3(192); lc.dynamicSmemBytes = smem; lc.stream = s;
-    cudaLaunchAttribute la[1];
-    la[0].id = cudaLaunchAttributeClusterDimension;
-    la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
-    lc.attrs = la; lc.numAttrs = 1;
-    cudaLaunchKernelEx(&lc, umma_ozaki_syrk_v2_kernel<S, 2>, ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
+  const int cap = (ws.max_ctas > 0 && ws.max_ctas < nsm) ? ws.max_ctas : nsm;
+  if (want_cl == 2 || want_ew == 8) {
+    const bool cl2 = want_cl == 2 && a.SLb && !a.strip_start && ntiles >= 2;
+    if (cl2 && want_ew == 8) launch_v2_variant<S, 2, 8>(ws, a, ntiles, nbi, nbj, cap, smem, s);
+    else if (cl2) launch_v2_variant<S, 2, 4>(ws, a, ntiles, nbi, nbj, cap, smem, s);
+    else if (want_ew == 8) launch_v2_variant<S, 1, 8>(ws, a, ntiles, nbi, nbj, cap, smem, s);
+    else launch_v2_variant<S, 1, 4>(ws, a, ntiles, nbi, nbj, cap, smem, s);
     agp_count_launch();
     return;
   }
-  const int cap = (ws.max_ctas > 0 && ws.max_ctas < nsm) ? ws.max_ctas : nsm;
   const int grid = (int)(ntiles < cap ? ntiles : cap);
-  umma_ozaki_syrk_v2_kernel<S, 1><<<grid, 192, smem, s>>>(ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
+  umma_ozaki_syrk_v2_kernel<S, 1, 4><<<grid, 192, smem, s>>>(ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
   agp_count_launch();
 }
 

@@ -1,6 +1,7 @@
 """Helper for tests/test_gpu_experimental.py (run as a subprocess so that a device trap in an unvalidated kernel
-cannot poison the pytest process): runs the persistent tcgen05 SYRK with and without AGP_OZAKI_CLUSTER=2 on the same
-inputs and prints the largest difference.  Usage: python tests/exp_cluster_check.py N K S"""
+cannot poison the pytest process): runs the persistent tcgen05 SYRK with the default kernel and with the given
+environment switches on the same inputs and prints the largest difference.
+Usage: python tests/exp_variant_check.py N K S AGP_OZAKI_CLUSTER=2 [AGP_OZAKI_EPIWARPS=8 ...]"""
 import ctypes as C
 import os
 import sys
@@ -23,8 +24,13 @@ def main():
     Pc = P.t().contiguous()
     C0 = torch.rand((N, M), generator=g, device="cuda", dtype=torch.float64)
     outs = []
-    for cl in ("1", "2"):
-        os.environ["AGP_OZAKI_CLUSTER"] = cl
+    switches = dict(a.split("=", 1) for a in sys.argv[4:])
+    for on in (False, True):
+        for k_, v_ in switches.items():
+            if on:
+                os.environ[k_] = v_
+            else:
+                os.environ.pop(k_, None)
         Cc = C0.clone()
         eng.check(eng.L.agp_debug_ozaki_syrk(eng.h, C.c_void_p(Cc.data_ptr()), M, C.c_void_p(Pc.data_ptr()), M, M, N, K, S, 1))
         torch.cuda.synchronize()

@@ -137,24 +137,25 @@ for mode in (1, 3, 2, 4):
     save()
 
 def cluster_part():
-    """EXPERIMENTAL kernel (A-multicast CTA pairs): opt-in with PROBE_CLUSTER=1 and run LAST -- a protocol bug traps and
+    """EXPERIMENTAL kernels (A-multicast CTA pairs, 8 epilogue warps): opt-in with PROBE_CLUSTER=1 and run LAST -- a protocol bug traps and
     kills the CUDA context, everything above is already saved."""
     os.environ["AGP_OZAKI_EPI"] = "1"
     os.environ["AGP_OZAKI_CLUSTER"] = "1"
     syrk(1, M)
     _, base = sample()
     res = {}
-    for epi in (1, 3):
-        os.environ["AGP_OZAKI_CLUSTER"] = "2"
-        t = syrk(epi, M)
-        d = {"ms": t, "syrk_ms": t - fixed, "fp64_equiv_tflops": flops / ((t - fixed) * 1e-3) / 1e12}
-        if epi == 1:
-            _, got = sample()
-            d["max_abs_diff_vs_single_cta"] = float(max(np.max(np.abs(r - w)) for r, w in zip(got, base)))
-        res["cluster2_epi%d" % epi] = d
-        out["partA"]["cluster"] = res
-        save()
-    os.environ["AGP_OZAKI_CLUSTER"] = "1"
+    for tag, cl, ew in (("epiwarps8", "1", "8"), ("cluster2", "2", "4"), ("cluster2_epiwarps8", "2", "8")):
+        for epi in (1, 3):
+            os.environ["AGP_OZAKI_CLUSTER"], os.environ["AGP_OZAKI_EPIWARPS"] = cl, ew
+            t = syrk(epi, M)
+            d = {"ms": t, "syrk_ms": t - fixed, "fp64_equiv_tflops": flops / ((t - fixed) * 1e-3) / 1e12}
+            if epi == 1:
+                _, got = sample()
+                d["max_abs_diff_vs_validated"] = float(max(np.max(np.abs(r - w)) for r, w in zip(got, base)))
+            res["%s_epi%d" % (tag, epi)] = d
+            out["partA"]["variants"] = res
+            save()
+    os.environ["AGP_OZAKI_CLUSTER"], os.environ["AGP_OZAKI_EPIWARPS"] = "1", "4"
 
 
 run_cluster_last = os.environ.get("PROBE_CLUSTER") == "1"
