@@ -61,6 +61,7 @@ SIGNATURES = {
     "agp_post_mean_cov": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _M, _P, _P]),
     "agp_post_logpdf": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _M, _N, _P, C.c_int32, _P]),
     "agp_post_rand": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _M, _N, _P, C.c_int32, _P]),
+    "agp_post_logpdf_grad": (C.c_int32, [_P, C.POINTER(C.c_double), _P]),
     "agp_post_solve_lower": (C.c_int32, [_P, _P, C.c_int64, _P]),
     "agp_post_factor_export": (C.c_int32, [_P, _P]),
     "agp_post_logdet": (C.c_int32, [_P, C.POINTER(C.c_double)]),

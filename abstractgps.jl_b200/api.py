@@ -552,6 +552,36 @@ def fit(fx: FiniteGP, y):
     return _fit(fx, y, True, True)
 
 
+def logpdf_grad(fx: FiniteGP, y):
+    """EXPERIMENTAL (device path not yet validated): (logpdf, gradient dict) of logpdf(fx, y) w.r.t. the kernel variance,
+    ScaleTransform s / ARDTransform v, LinearKernel c, the noise (scalar or per-point) and the mean (constant or vector)
+    -- the cotangents Zygote returns through the reference (test/finite_gp_projection.jl:152-178).  One fit, then
+    agp_post_logpdf_grad on its factor."""
+    lp, post = _fit(fx, y, True, True)
+    eng = engine()
+    f = post.prior
+    dt = post.data.C.dtype
+    D = post.data.x.D
+    g = np.zeros(5 + D, dtype=np.float64)
+    per_point = np.ndim(fx.s2) != 0
+    nd = np.empty(len(fx), dtype=dt) if (per_point or isinstance(f.mean, CustomMean)) else None
+    eng.check(eng.L.agp_post_logpdf_grad(post.data.C.h, g.ctypes.data_as(C.POINTER(C.c_double)), cabi.ptr(nd)))
+    k = f.kernel
+    out = {"variance": g[0]}
+    if isinstance(k.transform, ScaleTransform):
+        out["scale"] = g[1]
+    elif isinstance(k.transform, ARDTransform):
+        out["ard"] = g[5:5 + D].copy()
+    if k.family == LINEAR:
+        out["linear_c"] = g[2]
+    out["noise"] = nd.astype(np.float64) if per_point else g[3]
+    if isinstance(f.mean, ConstMean):
+        out["mean_c"] = g[4]
+    elif isinstance(f.mean, CustomMean):
+        out["mean_v"] = post.data.alpha.astype(np.float64)
+    return lp, out
+
+
 def _post_call(p: PosteriorGP, pts: _Points, s2, want_var=True, want_cov=False):
     eng = engine()
     dt = p.data.C.dtype

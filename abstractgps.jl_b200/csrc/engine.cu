@@ -730,6 +730,61 @@ int post_cond_impl(agp_post* p, int layout, const void* Xs, int64_t M, const agp
   return AGP_OK;
 }
 
+// ---- EXPERIMENTAL (compiles, not yet run on a device): gradient of logpdf(fx, y) w.r.t. the hyper-parameters from the
+// factor agp_fit left in the handle.  V = L^-1 by the blocked forward
+// substitution on the identity, C^-1 = V'V by the lower-only GEMM (both validated kernels), then grad.cu's fused
+// reduction 1/2 sum (alpha alpha' - C^-1) o dC/dtheta.  Extra cost ~ 2 N^3 flop and two N^2 buffers.
+template <typename T>
+int post_logpdf_grad_impl(agp_post* p, double* grad_out, void* noise_diag_out) {
+  agp_ctx* ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  CK(cudaSetDevice(ctx->device));
+  if (p->valid || p->segs.size() > 1) { ctx->err = "gradient of an extended (sequentially conditioned) posterior is unsupported"; return AGP_ERR_UNSUPPORTED; }
+  const int64_t n = p->n, n_pad = p->n_pad;
+  const int D = p->D;
+  Scratch sc(ctx);
+  void* tmp = nullptr;
+  CK(sc.alloc(&tmp, (size_t)n_pad * n_pad * sizeof(T)));
+  T* V = (T*)tmp;
+  CK(sc.alloc(&tmp, (size_t)n_pad * n_pad * sizeof(T)));
+  T* Cinv = (T*)tmp;
+  CK(sc.alloc(&tmp, (size_t)(5 + D) * sizeof(double)));
+  double* sums = (double*)tmp;
+  T* noise_d = nullptr;
+  if (noise_diag_out) { CK(sc.alloc(&tmp, (size_t)n_pad * sizeof(T))); noise_d = (T*)tmp; }
+  CK(cudaMemsetAsync(V, 0, (size_t)n_pad * n_pad * sizeof(T), s));
+  CK(cudaMemsetAsync(sums, 0, (size_t)(5 + D) * sizeof(double), s));
+  launch_add_diag<T>(V, n_pad, n_pad, 1.0, s);
+  forward_subst_multi<T>(ctx, (const T*)p->L, p->lda, (const T*)p->Dinv, n_pad, V, n_pad, n_pad);
+  {
+    GemmArgs g{};  // C^-1 = V'V, lower tiles
+    g.A = V; g.lda = n_pad; g.a_kmajor = 1;
+    g.B = V; g.ldb = n_pad; g.b_kmajor = 1;
+    g.C = Cinv; g.ldc = n_pad; g.M = n_pad; g.N = n_pad; g.K = n_pad; g.lower_only = 1;
+    launch_gemm<T>(g, s);
+  }
+  const int want_ard = (p->k.transform == AGP_T_ARD) ? 1 : 0;
+  launch_grad_reduce<T>((const T*)p->Xt, D, n, n_pad, Cinv, n_pad, (const T*)p->alpha, p->k.family, p->k.linear_c, want_ard,
+                        sums, noise_d, s);
+  std::vector<double> h((size_t)5 + D);
+  std::vector<T> ard_h((size_t)(D > 0 ? D : 1));
+  CK(cudaMemcpyAsync(h.data(), sums, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (want_ard && p->ard) CK(cudaMemcpyAsync(ard_h.data(), p->ard, (size_t)D * sizeof(T), cudaMemcpyDeviceToHost, s));
+  if (noise_diag_out) { int rc = download<T>(ctx, noise_diag_out, noise_d, (size_t)n, false); if (rc) return rc; }
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  const bool linear = p->k.family == AGP_LINEAR;
+  const double var = p->k.variance, sc_ = p->k.scale;
+  grad_out[0] = 0.5 * h[0];
+  grad_out[1] = (p->k.transform == AGP_T_SCALE) ? (linear ? var * h[1] / sc_ : 0.5 * var * h[1] / sc_) : 0.0;
+  grad_out[2] = linear ? 0.5 * var * h[2] : 0.0;
+  grad_out[3] = 0.5 * h[3];
+  grad_out[4] = h[4];
+  for (int d = 0; d < D; ++d)
+    grad_out[5 + d] = want_ard ? (linear ? var : 0.5 * var) * h[(size_t)5 + d] / (double)ard_h[(size_t)d] : 0.0;
+  return AGP_OK;
+}
+
 template <typename T>
 int post_solve_lower_impl(agp_post* p, const void* Bh, int64_t nrhs, void* V_out) {
   agp_ctx* ctx = p->ctx;
@@ -1588,6 +1643,12 @@ int32_t agp_post_rand(agp_post* p, int32_t layout, const void* Xs, int64_t M, co
   if (S <= 0) return AGP_OK;
   return DISPATCH(p->dtype, post_cond_impl<float>(p, layout, Xs, M, mean_s, noise_s, nullptr, 0, nullptr, Z, S, out),
                   post_cond_impl<double>(p, layout, Xs, M, mean_s, noise_s, nullptr, 0, nullptr, Z, S, out));
+}
+
+int32_t agp_post_logpdf_grad(agp_post* p, double* grad_out, void* noise_diag_out) {
+  if (!p || !grad_out) return AGP_ERR_INVALID;
+  return DISPATCH(p->dtype, post_logpdf_grad_impl<float>(p, grad_out, noise_diag_out),
+                  post_logpdf_grad_impl<double>(p, grad_out, noise_diag_out));
 }
 
 int32_t agp_post_solve_lower(agp_post* p, const void* B, int64_t nrhs, void* V_out) {

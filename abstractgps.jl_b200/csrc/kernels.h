@@ -111,6 +111,11 @@ template <typename T> void launch_copy2d(const T* src, int64_t lds, T* dst, int6
 // generic small helpers for VFE
 template <typename T> void launch_scale_cols(T* B, int64_t ldb, int64_t rows, int64_t cols, const T* colscale,
                                              cudaStream_t s);  // B[:,j] *= colscale[j]
+// EXPERIMENTAL (grad.cu): fused reduction of the logpdf gradient over the lower triangle; sums has 5 + D doubles (zeroed
+// by the caller), noise_diag (n, optional) receives 1/2 W_ii
+template <typename T> void launch_grad_reduce(const T* Xt, int D, int64_t n, int64_t n_pad, const T* Cinv, int64_t ldc,
+                                              const T* alpha, int family, double linear_c, int want_ard, double* sums,
+                                              T* noise_diag, cudaStream_t s);
 template <typename T> void launch_add_diag(T* A, int64_t lda, int64_t n, double v, cudaStream_t s);
 template <typename T> void launch_sumsq(const T* p, int64_t n, double* out, cudaStream_t s);  // out += sum p^2
 template <typename T> void launch_vfe_prep(const T* y, int64_t n, int mean_kind, double mean_c, const T* mean_v,

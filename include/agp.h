@@ -144,6 +144,14 @@ int32_t agp_post_logpdf(agp_post* p, int32_t layout, const void* Xs, int64_t M,
  * caller-supplied standard normals Z (M x S column-major) as agp_rand. */
 int32_t agp_post_rand(agp_post* p, int32_t layout, const void* Xs, int64_t M, const agp_mean* mean_s,
                       const agp_noise* noise_s, const void* Z, int32_t S, void* out);
+/* EXPERIMENTAL -- compiled, not yet validated on a device.  Gradient of logpdf(fx, y) with
+ * respect to the hyper-parameters, from the factor and alpha that agp_fit left in the handle: what reverse-mode AD
+ * returns through the reference's logpdf (test/finite_gp_projection.jl:152-178, examples/1-mauna-loa/script.jl:200-242).
+ * grad_out (double, 5 + D entries): [0] d/d variance, [1] d/d ScaleTransform s, [2] d/d LinearKernel c,
+ * [3] d/d sigma^2 (scalar noise; = 1/2 tr W), [4] d/d ConstMean c, [5 + d] d/d ARDTransform v_d.
+ * noise_diag_out (N elements of the handle's dtype, or NULL): d/d sigma_i^2 for per-point noise, and -- via
+ * d/d m_i = alpha_i -- the caller already holds the gradient w.r.t. a vector mean. */
+int32_t agp_post_logpdf_grad(agp_post* p, double* grad_out, void* noise_diag_out);
 /* V = U' \ B (N x nrhs, column-major): backs Xt_invA_X / diag_Xt_invA_X / Xt_invA_Y /
  * tr_Xt_invA_X on a device factor, src/util/common_covmat_ops.jl:54-60,90,101. */
 int32_t agp_post_solve_lower(agp_post* p, const void* B, int64_t nrhs, void* V_out);

@@ -28,3 +28,31 @@ def test_variant_matches_validated_kernel(N, K, S, switches):
     line = [l for l in r.stdout.splitlines() if l.startswith("MAXDIFF")][-1].split()
     assert float(line[1]) == 0.0, line
     assert float(line[3]) > 0.0, line  # the update really happened
+
+
+# ---- gradient of logpdf on the device (agp_post_logpdf_grad, csrc/grad.cu) vs the gradient oracle
+@pytest.mark.parametrize("dtype_name", ["float64", "float32"])
+@pytest.mark.parametrize("transform", ["scale", "ard"])
+@pytest.mark.parametrize("fam", [0, 1, 2, 3, 4])
+def test_logpdf_grad_matches_oracle(ag, fam, transform, dtype_name):
+    import numpy as np
+    from oracle import agp_ref as ref
+    from test_gpu_parity import FAM_CTOR
+    dtype = np.dtype(dtype_name).type
+    rng = np.random.default_rng(5)
+    n, D = 333, 5
+    X = rng.random((n, D)).astype(dtype)
+    y = (np.sin(3 * X[:, 0]) + 0.2 * rng.standard_normal(n)).astype(dtype)
+    ard = (0.6 + rng.random(D)).astype(dtype)
+    ks = ref.KernelSpec(fam, 1.3, ref.T_SCALE if transform == "scale" else ref.T_ARD, scale=1.7, ard=ard, linear_c=0.4)
+    nv = (0.05 + 0.1 * rng.random(n)).astype(dtype)
+    k = getattr(ag, FAM_CTOR[fam])() if fam != ref.LINEAR else ag.LinearKernel(c=0.4)
+    k = 1.3 * k.compose(ag.ScaleTransform(1.7) if transform == "scale" else ag.ARDTransform(ard))
+    f = ag.GP(0.25, k)
+    lp, g = ag.logpdf_grad(f(ag.RowVecs(X), nv), y)
+    want = ref.logpdf_grad(ks, ref.MeanSpec(1, 0.25), ref.NoiseSpec(1, v=nv), X.astype(np.float64), y.astype(np.float64))
+    rt = 1e-7 if dtype == np.float64 else 2e-2
+    scale_of = lambda a: max(1.0, float(np.max(np.abs(a))))
+    for key in ("variance", "mean_c", "noise") + (("scale",) if transform == "scale" else ("ard",)) + (("linear_c",) if fam == 4 else ()):
+        np.testing.assert_allclose(g[key], want[key], rtol=rt, atol=rt * scale_of(want[key]), err_msg=key)
+    assert np.isclose(lp, ref.logpdf(ks, ref.MeanSpec(1, 0.25), ref.NoiseSpec(1, v=nv), X, y), rtol=1e-8 if dtype == np.float64 else 1e-4)
