@@ -158,6 +158,7 @@ struct OzTileArgs {
   const int32_t* strip_bimin;    // v2, block-cyclic: first valid 128-row tile of every strip
   const int8_t* SLb;             // v2 bulk mode: slices in the blocked UMMA layout (nullptr -> tensor-map path)
   int lower_only;
+  int gs_shift;                  // v2 <.., GE = 1> only: the tables describe GROUPS of 2^gs_shift strips, tiles row-major inside
   int epi;                       // v2 epilogue variant: 0 Horner over S fp64 terms, 1 int32 pair pre-combination (K <= 512); >=2 PROBE ONLY
 };
 
@@ -398,9 +399,25 @@ __device__ __forceinline__ void v2_tile_tab(int64_t t, int nbj, const int64_t* _
   bj = lo;
   bi = bimin[lo] + (int)(t - start[lo]);
 }
+// GE = 1 (EXPERIMENTAL, block-cyclic path): the tables hold one entry per GROUP of 2^gs_shift strips (one local
+// distribution block); inside a group tiles run row-major -- 2^gs_shift consecutive slots share one 128-row A tile and
+// the group's B strips (~2 MB) stay in L2, instead of every slot of a wave asking for a different A tile.
+template <int GE>
 __device__ __forceinline__ bool v2_decode(const OzTileArgs& a, int64_t t, int nbi, int nbj, int& bi, int& bj, int64_t& brow) {
   if (a.strip_start) {
-    v2_tile_tab(t, nbj, a.strip_start, a.strip_bimin, bi, bj);
+    if constexpr (GE == 1) {
+      const int ng = nbj >> a.gs_shift;
+      int lo = 0, hi = ng;  // last group with start[g] <= t
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (a.strip_start[mid] <= t) lo = mid; else hi = mid;
+      }
+      const int64_t tl = t - a.strip_start[lo];
+      bi = a.strip_bimin[lo] + (int)(tl >> a.gs_shift);
+      bj = (lo << a.gs_shift) + (int)(tl & ((1 << a.gs_shift) - 1));
+    } else {
+      v2_tile_tab(t, nbj, a.strip_start, a.strip_bimin, bi, bj);
+    }
     const int64_t n0 = (int64_t)bj * OZ_BN, bw = a.b_tile_width ? a.b_tile_width : 128;
     brow = (n0 / bw) * a.b_tile_stride + (n0 % bw) + a.b_off;
     return true;
@@ -417,7 +434,7 @@ __device__ __forceinline__ bool v2_decode(const OzTileArgs& a, int64_t t, int nb
 // so both CTAs run the same sequence of tiles and K chunks in lockstep.
 // NEPI = epilogue warps (4 or 8).  8: two warps per TMEM lane quarter, 32 of the tile's 64 columns each -- the drain
 // (tcgen05.ld + int->fp64 + Horner) is 12-15 % of the kernel and is issue / latency bound per warp, not TMEM bound.
-template <int S, int CL, int NEPI>
+template <int S, int CL, int NEPI, int GE>
 __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v2_kernel(const __grid_constant__ CUtensorMap tmapA,
                                                                     const __grid_constant__ CUtensorMap tmapB, OzTileArgs a,
                                                                     int64_t ntiles, int nbi, int nbj) {
@@ -456,7 +473,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v2_kernel(c
       for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int bi, bj;
         int64_t brow64;
-        if (!v2_decode(a, t, nbi, nbj, bi, bj, brow64)) continue;
+        if (!v2_decode<GE>(a, t, nbi, nbj, bi, bj, brow64)) continue;
         const int arow = (int)(bi * OZ_BM + a.a_off), brow = (int)brow64;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int st = it % STAGES;
@@ -497,7 +514,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v2_kernel(c
         {
           int bi_, bj_;
           int64_t br_;
-          if (!v2_decode(a, t, nbi, nbj, bi_, bj_, br_)) continue;
+          if (!v2_decode<GE>(a, t, nbi, nbj, bi_, bj_, br_)) continue;
         }
         mbar_wait(&tmem_empty_bar, (lt & 1) ^ 1);  // epilogue has drained the previous tile's accumulators
         tc_fence_after();
@@ -533,7 +550,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v2_kernel(c
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
       int bi, bj;
       int64_t brow64;
-      if (!v2_decode(a, t, nbi, nbj, bi, bj, brow64)) continue;
+      if (!v2_decode<GE>(a, t, nbi, nbj, bi, bj, brow64)) continue;
       const int64_t m0 = (int64_t)bi * OZ_BM, n0 = (int64_t)bj * OZ_BN + c0;
       brow64 += c0;
       const int64_t row = m0 + 32 * quarter + lane;
@@ -638,7 +655,7 @@ EncodeTiledFn get_encode() {
 
 // launch of an experimental variant (cluster size CL, NEPI epilogue warps) through cudaLaunchKernelEx; the persistent
 // grid must be fully co-resident, so with clusters it is capped by cudaOccupancyMaxActiveClusters
-template <int S, int CL, int NEPI>
+template <int S, int CL, int NEPI, int GE>
 void launch_v2_variant(const OzakiWs& ws, const OzTileArgs& a, int64_t ntiles, int nbi, int nbj, int cap, size_t smem,
                        cudaStream_t s) {
   static int max_clusters = -1;
@@ -650,10 +667,10 @@ void launch_v2_variant(const OzakiWs& ws, const OzTileArgs& a, int64_t ntiles, i
   la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
   lc.attrs = la; lc.numAttrs = 1;
   if (max_clusters < 0) {
-    cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S, CL, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S, CL, NEPI, GE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     lc.gridDim = dim3((unsigned)(cap / CL * CL));
     max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, umma_ozaki_syrk_v2_kernel<S, CL, NEPI>, &lc) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, umma_ozaki_syrk_v2_kernel<S, CL, NEPI, GE>, &lc) != cudaSuccess) {
       max_clusters = 0;
       cudaGetLastError();
     }
@@ -663,7 +680,7 @@ void launch_v2_variant(const OzakiWs& ws, const OzTileArgs& a, int64_t ntiles, i
   if (grid > ntiles) grid = ntiles / CL * CL;  // the closed-form slot count is even
   if (grid <= 0) return;
   lc.gridDim = dim3((unsigned)grid);
-  cudaLaunchKernelEx(&lc, umma_ozaki_syrk_v2_kernel<S, CL, NEPI>, ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
+  cudaLaunchKernelEx(&lc, umma_ozaki_syrk_v2_kernel<S, CL, NEPI, GE>, ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
 }
 
 template <int S>
@@ -675,20 +692,23 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
   static bool configured = false;
   static int nsm = 148;
   if (!configured) {
-    cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S, 1, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
-  // EXPERIMENTAL switches (the variants compile, none has run on a device yet; the default <S, 1, 4> kernel is the
-  // validated one): AGP_OZAKI_CLUSTER=2 -> A-multicast CTA pairs, AGP_OZAKI_EPIWARPS=8 -> two epilogue warps per quarter
-  int want_cl = 1, want_ew = 4;
+  // EXPERIMENTAL switches (the variants compile, none has run on a device yet; the default <S, 1, 4, 0> kernel is the
+  // validated one): AGP_OZAKI_CLUSTER=2 -> A-multicast CTA pairs, AGP_OZAKI_EPIWARPS=8 -> two epilogue warps per quarter,
+  // AGP_OZAKI_GROUPED=1 -> block-cyclic (multi-GPU) tile order grouped by distribution block, row-major inside
+  int want_cl = 1, want_ew = 4, want_ge = 0;
   {
     const char* e = getenv("AGP_OZAKI_CLUSTER");
     want_cl = (e && atoi(e) == 2) ? 2 : 1;
     const char* f = getenv("AGP_OZAKI_EPIWARPS");
     want_ew = (f && atoi(f) == 8) ? 8 : 4;
+    const char* g = getenv("AGP_OZAKI_GROUPED");
+    want_ge = (g && atoi(g) == 1) ? 1 : 0;
   }
   OzTileArgs a{};
   a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.m_alloc = ws.m_alloc; a.K = ws.K; a.rscale = ws.rscale;
@@ -712,6 +732,29 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
     std::vector<int64_t> start((size_t)nbj + 1);
     std::vector<int32_t> bimin((size_t)nbj);
     const int64_t bw = b_tile_width ? b_tile_width : 128;
+    // grouped order: one table entry per distribution block (bw / 64 strips, a power of two), its first strip's bimin for
+    // all of them -- inside the block on the diagonal that computes a few tiles above the diagonal (harmless: they land
+    // in the unused upper triangle of the local block) in exchange for a uniform row-major walk
+    int gs_shift = 0;
+    if (want_ge) {
+      const int64_t gs = bw / OZ_BN;
+      while ((1ll << gs_shift) < gs) ++gs_shift;
+      if ((1ll << gs_shift) != gs || gs < 2 || nbj % gs != 0 || !b_tile_stride) want_ge = 0;
+    }
+    if (want_ge) {
+      const int gs = 1 << gs_shift, ng = nbj / gs;
+      for (int g = 0; g < ng; ++g) {
+        const int64_t n0 = (int64_t)g * gs * OZ_BN;
+        const int64_t nsrc = (n0 / bw) * b_tile_stride + (n0 % bw) + b_off;
+        int64_t bm = (nsrc - a_off) >= 0 ? (nsrc - a_off) / OZ_BM : 0;
+        if (bm > nbi) bm = nbi;
+        bimin[g] = (int32_t)bm;
+        start[g] = ntiles;
+        ntiles += (nbi - bm) * gs;
+      }
+      start[ng] = ntiles;
+      a.gs_shift = gs_shift;
+    } else
     for (int j = 0; j < nbj; ++j) {
       const int64_t n0 = (int64_t)j * OZ_BN;
       const int64_t nsrc = (b_tile_stride ? (n0 / bw) * b_tile_stride + (n0 % bw) : n0) + b_off;
@@ -732,17 +775,20 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
   }
   if (ntiles <= 0) return;
   const int cap = (ws.max_ctas > 0 && ws.max_ctas < nsm) ? ws.max_ctas : nsm;
-  if (want_cl == 2 || want_ew == 8) {
+  const bool ge = want_ge && a.strip_start;
+  if (want_cl == 2 || want_ew == 8 || ge) {
     const bool cl2 = want_cl == 2 && a.SLb && !a.strip_start && ntiles >= 2;
-    if (cl2 && want_ew == 8) launch_v2_variant<S, 2, 8>(ws, a, ntiles, nbi, nbj, cap, smem, s);
-    else if (cl2) launch_v2_variant<S, 2, 4>(ws, a, ntiles, nbi, nbj, cap, smem, s);
-    else if (want_ew == 8) launch_v2_variant<S, 1, 8>(ws, a, ntiles, nbi, nbj, cap, smem, s);
-    else launch_v2_variant<S, 1, 4>(ws, a, ntiles, nbi, nbj, cap, smem, s);
+    if (ge && want_ew == 8) launch_v2_variant<S, 1, 8, 1>(ws, a, ntiles, nbi, nbj, cap, smem, s);
+    else if (ge) launch_v2_variant<S, 1, 4, 1>(ws, a, ntiles, nbi, nbj, cap, smem, s);
+    else if (cl2 && want_ew == 8) launch_v2_variant<S, 2, 8, 0>(ws, a, ntiles, nbi, nbj, cap, smem, s);
+    else if (cl2) launch_v2_variant<S, 2, 4, 0>(ws, a, ntiles, nbi, nbj, cap, smem, s);
+    else if (want_ew == 8) launch_v2_variant<S, 1, 8, 0>(ws, a, ntiles, nbi, nbj, cap, smem, s);
+    else launch_v2_variant<S, 1, 4, 0>(ws, a, ntiles, nbi, nbj, cap, smem, s);
     agp_count_launch();
     return;
   }
   const int grid = (int)(ntiles < cap ? ntiles : cap);
-  umma_ozaki_syrk_v2_kernel<S, 1, 4><<<grid, 192, smem, s>>>(ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
+  umma_ozaki_syrk_v2_kernel<S, 1, 4, 0><<<grid, 192, smem, s>>>(ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
   agp_count_launch();
 }
 

@@ -101,3 +101,61 @@ def test_block_cyclic_strip_table(R, me, W, kk, nto):
             if prow < bi * 128 + 128:                # tile touches the lower triangle (incl. diagonal-crossing)
                 want.add((bi, bj))
     assert seen == want
+
+
+# ---- EXPERIMENTAL grouped order of the block-cyclic path (AGP_OZAKI_GROUPED=1; umma_ozaki.cu: v2_decode<1> and the
+# want_ge branch of launch_syrk_v2_S): one table entry per distribution block, tiles row-major inside the block
+def group_table(nbi, nbj, b_tile_stride, bw, b_off, a_off):
+    gs = bw // 64
+    shift = gs.bit_length() - 1
+    assert (1 << shift) == gs and gs >= 2 and nbj % gs == 0 and b_tile_stride
+    start, bimin, n = [], [], 0
+    for g in range(nbj // gs):
+        n0 = g * gs * 64
+        nsrc = (n0 // bw) * b_tile_stride + n0 % bw + b_off
+        bm = (nsrc - a_off) // 128 if nsrc - a_off >= 0 else 0
+        bm = min(bm, nbi)
+        bimin.append(bm)
+        start.append(n)
+        n += (nbi - bm) * gs
+    start.append(n)
+    return start, bimin, n, shift
+
+
+def group_decode(t, start, bimin, nbj, shift):
+    ng = nbj >> shift
+    lo, hi = 0, ng
+    while hi - lo > 1:
+        mid = (lo + hi) >> 1
+        if start[mid] <= t:
+            lo = mid
+        else:
+            hi = mid
+    tl = t - start[lo]
+    return bimin[lo] + (tl >> shift), (lo << shift) + (tl & ((1 << shift) - 1))
+
+
+@pytest.mark.parametrize("R,me,W,kk,nto", [(2, 0, 256, 0, 7), (2, 1, 256, 1, 7), (4, 3, 512, 2, 16), (8, 5, 512, 0, 20), (3, 0, 128, 4, 11)])
+def test_block_cyclic_grouped_table(R, me, W, kk, nto):
+    local = [j for j in range(nto) if j % R == me and j > kk]
+    if not local:
+        pytest.skip("no local trailing blocks")
+    rows_below = (nto - (kk + 1)) * W + 128
+    nbi, nbj = (rows_below + 127) // 128, len(local) * W // 64
+    b_off = (local[0] - (kk + 1)) * W
+    start, bimin, n, shift = group_table(nbi, nbj, R * W, W, b_off, 0)
+    seq = [group_decode(t, start, bimin, nbj, shift) for t in range(n)]
+    assert len(seq) == len(set(seq)), "a tile is visited twice"
+    # every tile of the strip-major (validated) enumeration is covered ...
+    s_start, s_bimin, s_n = strip_table(nbi, nbj, R * W, W, b_off, 0)
+    want = {tab_decode(t, s_start, s_bimin, nbj) for t in range(s_n)}
+    assert want <= set(seq)
+    # ... and the extras lie strictly above the diagonal inside the block that crosses it (the unused upper triangle)
+    for (bi, bj) in set(seq) - want:
+        prow = (bj * 64 // W) * R * W + (bj * 64) % W + b_off
+        assert prow >= bi * 128 + 128 and bi < nbi
+    assert len(seq) - len(want) <= len(local) * (W // 64) * (W // 128)
+    # row-major inside a group: 2^shift consecutive slots share the A row tile
+    gs = 1 << shift
+    for t0 in range(0, n, gs):
+        assert len({bi for bi, _ in seq[t0:t0 + gs]}) == 1

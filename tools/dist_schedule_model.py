@@ -39,8 +39,8 @@ def build(n, R, W, sched2, reserve, eff_narrow):
         flops = sum(2.0 * W * W * (lda - j * W) for j in blocks)
         return flops / (upd_rate * eff_narrow * sms / NSM) + 15e-6
 
-    def t_factor(rows):
-        return 0.28e-3 + rows * 262144.0 / fact_rate
+    def t_factor(rows):  # W/128 inner steps of ~70 us latency-bound chain + rows * W^2 flop of TRSM / rank-128 updates
+        return (W / 128) * 0.07e-3 + rows * float(W) * W / fact_rate
 
     for r in range(R):
         S, S2 = ops[(r, "s")], ops[(r, "s2")]
