@@ -777,8 +777,11 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
   const int cap = (ws.max_ctas > 0 && ws.max_ctas < nsm) ? ws.max_ctas : nsm;
   const bool ge = want_ge && a.strip_start;
   if (want_cl == 2 || want_ew == 8 || ge) {
-    const bool cl2 = want_cl == 2 && a.SLb && !a.strip_start && ntiles >= 2;
-    if (ge && want_ew == 8) launch_v2_variant<S, 1, 8, 1>(ws, a, ntiles, nbi, nbj, cap, smem, s);
+    // CTA pairs need slots 2u, 2u + 1 on the same row tile: the closed-form order and the grouped table order give that
+    const bool cl2 = want_cl == 2 && a.SLb && (!a.strip_start || ge) && ntiles >= 2;
+    if (ge && cl2 && want_ew == 8) launch_v2_variant<S, 2, 8, 1>(ws, a, ntiles, nbi, nbj, cap, smem, s);
+    else if (ge && cl2) launch_v2_variant<S, 2, 4, 1>(ws, a, ntiles, nbi, nbj, cap, smem, s);
+    else if (ge && want_ew == 8) launch_v2_variant<S, 1, 8, 1>(ws, a, ntiles, nbi, nbj, cap, smem, s);
     else if (ge) launch_v2_variant<S, 1, 4, 1>(ws, a, ntiles, nbi, nbj, cap, smem, s);
     else if (cl2 && want_ew == 8) launch_v2_variant<S, 2, 8, 0>(ws, a, ntiles, nbi, nbj, cap, smem, s);
     else if (cl2) launch_v2_variant<S, 2, 4, 0>(ws, a, ntiles, nbi, nbj, cap, smem, s);
