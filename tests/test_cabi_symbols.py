@@ -57,3 +57,28 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, fn), errors="ignore").read()
                 assert "oracle" not in txt.replace("# oracle-free", ""), fn
+
+
+def test_header_is_plain_c_and_a_c_client_links(tmp_path):
+    """include/agp.h is the boundary a C / Julia / Go host binds: it must compile as C99 (no C++-isms), and a C client
+    (examples/c_abi_demo.c) must link against libagp.so; without a CUDA device the client reports the failure of
+    agp_init and exits 2 -- no silent CPU path."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(inc, "agp.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exe = str(tmp_path / "c_abi_demo")
+    libdir = os.path.join(ROOT, "abstractgps.jl_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-I" + inc, os.path.join(ROOT, "examples", "c_abi_demo.c"), "-o", exe,
+                        "-L" + libdir, "-l:libagp.so", "-lm", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode in (0, 2), (r.returncode, r.stdout, r.stderr)
+    if r.returncode == 2:
+        assert "agp_init" in r.stderr
+    else:
+        assert "logpdf" in r.stdout
