@@ -1,0 +1,158 @@
+"""The host mirror (abstractgps.jl_b200/api.py) driven end to end on the CPU against tests/fake_libagp.py, a stand-in for
+libagp.so that answers the C ABI with the oracle.  What this pins: argument marshalling and layouts (point-major vs
+RowVecs/ColVecs, column-major outputs), struct filling, dtype propagation, handle ownership (sequential conditioning
+returns a new handle), chunking of > 128 right-hand sides, the error mapping (PosDefException / DimensionMismatch) -- and
+the LOGIC of the GPU test files themselves: the replay of the reference's jldoctests and of its TestUtils suites, and
+the posterior-FiniteGP cases, run here unchanged with the fake engine installed.  Nothing here exercises CUDA."""
+import inspect
+
+import numpy as np
+import pytest
+
+from oracle import agp_ref as ref
+import fake_libagp
+import test_gpu_posterior_finitegp as pf
+import test_gpu_reference_doctests as doc
+
+
+@pytest.fixture()
+def fag(ag, monkeypatch):
+    import ctypes as C
+    eng = ag.api.Engine.__new__(ag.api.Engine)
+    eng.L, eng.h, eng.device = fake_libagp.FakeLib(), C.c_void_p(1), 0
+    monkeypatch.setattr(ag.api, "_engine", eng)
+    yield ag
+
+
+def _call(fn, fag, **extra):
+    kw = {}
+    for name in inspect.signature(fn).parameters:
+        if name == "ag":
+            kw[name] = fag
+        elif name == "rng":
+            kw[name] = np.random.default_rng(20240924)
+        else:
+            kw[name] = extra[name]
+    return fn(**kw)
+
+
+DOC_TESTS = [n for n in dir(doc) if n.startswith("test_")]
+
+
+@pytest.mark.parametrize("name", DOC_TESTS)
+def test_reference_doctest_replays(fag, name):
+    _call(getattr(doc, name), fag)
+
+
+def test_reference_testutils_suites(fag):
+    pf.test_reference_base_gp_suite(fag)
+    pf.test_reference_exact_gpr_posterior_suite(fag)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_posterior_finitegp_cases(fag, dtype):
+    pf.test_posterior_finitegp_logpdf_and_rand(fag, dtype, 129, 40, 3, ref.MATERN52)
+    if dtype == np.float64:
+        pf.test_posterior_logpdf_is_the_chain_rule_increment(fag)
+        pf.test_sequential_conditioning_has_value_semantics(fag)
+        pf.test_posterior_finitegp_not_posdef(fag)
+
+
+def test_fit_matches_oracle_through_every_input_wrapper(fag):
+    ag = fag
+    rng = np.random.default_rng(0)
+    n, d = 60, 3
+    X = rng.random((n, d))
+    y = np.sin(X.sum(1))
+    ks = ref.KernelSpec(ref.MATERN32, 1.7, ref.T_ARD, ard=np.array([1.0, 2.0, 0.5]))
+    k = 1.7 * ag.Matern32Kernel().compose(ag.ARDTransform([1.0, 2.0, 0.5]))
+    want = ref.logpdf(ks, ref.MeanSpec(1, 0.3), ref.NoiseSpec(0, 0.1), X, y)
+    f = ag.GP(0.3, k)
+    for x in (ag.RowVecs(X), ag.ColVecs(np.ascontiguousarray(X.T)), ag.ColVecs(np.asfortranarray(X.T))):
+        assert np.isclose(ag.logpdf(f(x, 0.1), y), want, rtol=1e-12)
+    lp, p = ag.fit(f(ag.RowVecs(X), 0.1), y)
+    pr = ref.posterior(ks, ref.MeanSpec(1, 0.3), ref.NoiseSpec(0, 0.1), X, y)
+    assert np.allclose(p.data.alpha, pr["alpha"]) and np.allclose(p.data.C.U, pr["U"]) and np.allclose(p.data.delta, pr["delta"])
+    assert np.isclose(p.data.C.logdet(), ref.logdet_chol(pr["U"]))
+    # the operator API on the factor handle
+    B = rng.standard_normal((n, 4))
+    assert np.allclose(ag.Xt_invA_X(p.data.C, B), ref.Xt_invA_X(pr["U"], B))
+    assert np.allclose(ag.diag_Xt_invA_X(p.data.C, B), ref.diag_Xt_invA_X(pr["U"], B))
+    assert np.isclose(ag.tr_Xt_invA_X(p.data.C, B[:, 0]), ref.tr_Xt_invA_X(pr["U"], B[:, 0]))
+    # 1-D inputs are D = 1 points; float32 inputs stay float32 end to end
+    x1 = rng.random(20).astype(np.float32)
+    y1 = np.cos(x1).astype(np.float32)
+    lp32 = ag.logpdf(ag.GP(ag.SqExponentialKernel())(x1, 0.1), y1)
+    assert lp32.dtype == np.float32
+
+
+def test_more_than_128_right_hand_sides_are_chunked(fag):
+    ag = fag
+    rng = np.random.default_rng(1)
+    X = rng.random((30, 2))
+    Y = rng.standard_normal((30, 300))
+    fx = ag.GP(ag.SqExponentialKernel())(ag.RowVecs(X), 0.2)
+    lps = ag.logpdf(fx, Y)
+    want = ref.logpdf(ref.KernelSpec(ref.SE, 1.0), ref.MeanSpec(), ref.NoiseSpec(0, 0.2), X, Y)
+    assert lps.shape == (300,) and np.allclose(lps, want)
+    assert fag.api.engine().L.calls.count("agp_fit") == 3  # 128 + 128 + 44 columns
+    assert np.isclose(ag.loglikelihood(fx, Y), want.sum())
+
+
+def test_error_mapping(fag):
+    ag = fag
+    f = ag.GP(ag.SqExponentialKernel())
+    x = np.linspace(0, 1, 5)
+    with pytest.raises(ag.PosDefException) as e:
+        ag.logpdf(f(np.array([0.0, 0.0, 1.0]), -1.0), np.zeros(3))  # K - I is indefinite
+    assert e.value.info >= 1
+    with pytest.raises(ag.DimensionMismatch):
+        ag.logpdf(f(x, 0.1), np.zeros(4))
+    p = ag.posterior(f(x, 0.1), np.zeros(5))
+    with pytest.raises(ag.DimensionMismatch):
+        ag.mean_and_var(p(ag.RowVecs(np.zeros((3, 2)))))
+    with pytest.raises(ag.DimensionMismatch):
+        ag.elbo(ag.VFE(f(x[:2])), f(x, 0.1), np.zeros(4))
+
+
+def test_vfe_wrappers(fag):
+    ag = fag
+    rng = np.random.default_rng(2)
+    X, Z = rng.random((80, 2)), rng.random((9, 2))
+    y = np.sin(3 * X[:, 0])
+    ks = ref.KernelSpec(ref.MATERN52, 1.0, ref.T_SCALE, scale=2.0)
+    f = ag.GP(ag.Matern52Kernel().compose(ag.ScaleTransform(2.0)))
+    fx = f(ag.RowVecs(X), 0.1)
+    vfe = ag.VFE(f(ag.RowVecs(Z), 1e-6))
+    jit = ref.NoiseSpec(0, 1e-6)
+    el, dtc = ag.approx_log_evidence(vfe, fx, y, return_dtc=True)
+    assert np.isclose(el, ref.elbo(ks, ref.MeanSpec(), ref.NoiseSpec(0, 0.1), X, y, Z, jit))
+    assert np.isclose(dtc, ref.dtc(ks, ref.MeanSpec(), ref.NoiseSpec(0, 0.1), X, y, Z, jit))
+    post = ag.posterior(vfe, fx, y)
+    Xs = rng.random((7, 2))
+    m, v = ag.mean_and_var(post(ag.RowVecs(Xs), 0.05))
+    mr, vr = ref.vfe_mean_and_var(ref.vfe_posterior(ks, ref.MeanSpec(), ref.NoiseSpec(0, 0.1), X, y, Z, jit), Xs)
+    assert np.allclose(m, mr) and np.allclose(v, vr + 0.05)
+
+
+@pytest.mark.parametrize("transform", ["scale", "ard"])
+@pytest.mark.parametrize("fam", [ref.SE, ref.LINEAR])
+def test_logpdf_grad_mapping(fag, fam, transform):
+    """the dict ag.logpdf_grad builds from the ABI's 5 + D vector (variance / scale|ard / linear_c / noise / mean)"""
+    ag = fag
+    rng = np.random.default_rng(3)
+    n, D = 40, 3
+    X = rng.random((n, D))
+    y = np.sin(X[:, 0])
+    ard = np.array([1.2, 0.7, 2.1])
+    ks = ref.KernelSpec(fam, 1.3, ref.T_SCALE if transform == "scale" else ref.T_ARD, scale=1.7, ard=ard, linear_c=0.4)
+    k = ag.SqExponentialKernel() if fam == ref.SE else ag.LinearKernel(c=0.4)
+    k = 1.3 * k.compose(ag.ScaleTransform(1.7) if transform == "scale" else ag.ARDTransform(ard))
+    nv = 0.05 + 0.1 * rng.random(n)
+    lp, g = ag.logpdf_grad(ag.GP(0.25, k)(ag.RowVecs(X), nv), y)
+    want = ref.logpdf_grad(ks, ref.MeanSpec(1, 0.25), ref.NoiseSpec(1, v=nv), X, y)
+    assert set(g) == set(want)
+    for key in want:
+        assert np.allclose(g[key], want[key]), key
+    lp2, g2 = ag.logpdf_grad(ag.GP(lambda r: np.sin(r[0]), k)(ag.RowVecs(X), 0.1), y)  # scalar noise, vector mean
+    assert np.ndim(g2["noise"]) == 0 and g2["mean_v"].shape == (n,) and "mean_c" not in g2
