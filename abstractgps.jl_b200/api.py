@@ -338,7 +338,7 @@ class GP(AbstractGP):
             mean, kernel = ZeroMean(), args[0]
         else:
             mean, kernel = args
-            if isinstance(mean, (int, float)):
+            if isinstance(mean, (int, float, np.integer, np.floating)):  # GP(c::Real, kernel), src/base_gp.jl:64
                 mean = ConstMean(mean)
             elif not isinstance(mean, MeanFunction):
                 mean = CustomMean(mean)
@@ -792,8 +792,20 @@ def _posterior_sequential(fx: FiniteGP, y):
 # VFE (src/sparse_approximations.jl)
 # ---------------------------------------------------------------------------------------------
 class VFE:
+    """VFE(fz) (src/sparse_approximations.jl:1-12)."""
+
     def __init__(self, fz: FiniteGP):
         self.fz = fz
+
+
+class DTC(VFE):
+    """DTC(fz) (src/sparse_approximations.jl:14-23): the same optimal approximate posterior as VFE (`posterior(::Union{VFE,DTC}, ...)`
+    :58), but `approx_log_evidence` is the DTC objective (:282-286) -- the second output of agp_vfe_elbo."""
+
+
+def inducing_points(p):
+    """inducing_points(f_post_approx) (src/sparse_approximations.jl:219)."""
+    return p.approx.fz.x
 
 
 class ApproxPosteriorGP(AbstractGP):
@@ -835,10 +847,16 @@ def approx_log_evidence(vfe: VFE, fx: FiniteGP, y, return_dtc=False):
     eng.check(eng.L.agp_vfe_elbo(eng.h, cabi.dtype_code(dt), C.byref(ks), C.byref(ms), C.byref(ns), cabi.AGP_POINT_MAJOR,
                                  cabi.ptr(pts.a), pts.n, pts.D, cabi.ptr(z.a), z.n, C.byref(js), cabi.ptr(y),
                                  cabi.ptr(out[0:1]), cabi.ptr(out[1:2])))
-    return (out[0], out[1]) if return_dtc else out[0]
+    if return_dtc:
+        return out[0], out[1]
+    return out[1] if isinstance(vfe, DTC) else out[0]
 
 
-elbo = approx_log_evidence
+def elbo(vfe: VFE, fx: FiniteGP, y):
+    """elbo(vfe::VFE, fx, y) = approx_log_evidence(vfe, fx, y) (src/sparse_approximations.jl:254); VFE only."""
+    if isinstance(vfe, DTC):
+        raise TypeError("elbo is defined for VFE; use approx_log_evidence for DTC")
+    return approx_log_evidence(vfe, fx, y)
 
 
 def _vfe_posterior(vfe: VFE, fx: FiniteGP, y):
@@ -856,4 +874,6 @@ def _vfe_mean_var(p: ApproxPosteriorGP, pts: _Points):
     m = np.empty(pts.n, dtype=p.dtype)
     v = np.empty(pts.n, dtype=p.dtype)
     eng.check(eng.L.agp_vfe_mean_var(p.h, cabi.AGP_POINT_MAJOR, cabi.ptr(pts.a), pts.n, cabi.ptr(m), cabi.ptr(v)))
+    if isinstance(p.prior.mean, CustomMean):  # the handle carries Zero/Const means only: a closure is evaluated here
+        m = m + p.prior.mean.vector(pts, p.dtype)
     return m, v

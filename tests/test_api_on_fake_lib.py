@@ -156,3 +156,24 @@ def test_logpdf_grad_mapping(fag, fam, transform):
         assert np.allclose(g[key], want[key]), key
     lp2, g2 = ag.logpdf_grad(ag.GP(lambda r: np.sin(r[0]), k)(ag.RowVecs(X), 0.1), y)  # scalar noise, vector mean
     assert np.ndim(g2["noise"]) == 0 and g2["mean_v"].shape == (n,) and "mean_c" not in g2
+
+
+# ---- the reference's own test sets for the hot path (tests/ref_suite_replays.py), on the fake library
+import ref_suite_replays as rs  # noqa: E402
+
+
+def test_reference_finite_gp_testsets(fag):
+    rs.finite_gp_statistics(fag)
+    rs.finite_gp_rand_statistical(fag, S=100_000)
+    rs.finite_gp_logpdf(fag)
+    for T in (np.float64, np.float32):
+        rs.finite_gp_type_stability(fag, T)
+
+
+@pytest.mark.parametrize("approx_name", ["VFE", "DTC"])
+def test_reference_sparse_testsets(fag, approx_name):
+    A = getattr(fag, approx_name)
+    rs.sparse_approx_log_evidence(fag, A)
+    rs.sparse_posterior_matches_exact(fag, A)
+    for T in (np.float64, np.float32):
+        rs.sparse_type_stability(fag, A, T)

@@ -56,3 +56,26 @@ def test_logpdf_grad_matches_oracle(ag, fam, transform, dtype_name):
     for key in ("variance", "mean_c", "noise") + (("scale",) if transform == "scale" else ("ard",)) + (("linear_c",) if fam == 4 else ()):
         np.testing.assert_allclose(g[key], want[key], rtol=rt, atol=rt * scale_of(want[key]), err_msg=key)
     assert np.isclose(lp, ref.logpdf(ks, ref.MeanSpec(1, 0.25), ref.NoiseSpec(1, v=nv), X, y), rtol=1e-8 if dtype == np.float64 else 1e-4)
+
+
+# ---- the reference's own test sets for the hot path (tests/ref_suite_replays.py) on the device; their logic already
+# runs on the CPU against the fake library (tests/test_api_on_fake_lib.py) -- promote to the default GPU suite once green
+def test_reference_finite_gp_testsets_on_device(ag):
+    import numpy as np
+    import ref_suite_replays as rs
+    rs.finite_gp_statistics(ag)
+    rs.finite_gp_rand_statistical(ag)
+    rs.finite_gp_logpdf(ag)
+    for T in (np.float64, np.float32):
+        rs.finite_gp_type_stability(ag, T)
+
+
+@pytest.mark.parametrize("approx_name", ["VFE", "DTC"])
+def test_reference_sparse_testsets_on_device(ag, approx_name):
+    import numpy as np
+    import ref_suite_replays as rs
+    A = getattr(ag, approx_name)
+    rs.sparse_approx_log_evidence(ag, A)
+    rs.sparse_posterior_matches_exact(ag, A)
+    for T in (np.float64, np.float32):
+        rs.sparse_type_stability(ag, A, T)
