@@ -326,7 +326,15 @@ default_s2 = 1e-18  # src/finite_gp_projection.jl:17
 
 
 class AbstractGP:
-    def __call__(self, x, s2=default_s2):  # (f::AbstractGP)(x...) src/finite_gp_projection.jl:32
+    def __call__(self, x, s2=default_s2, obsdim=None):
+        """(f::AbstractGP)(x...) src/finite_gp_projection.jl:32; (f)(X::AbstractMatrix, args...; obsdim) :33-37 --
+        obsdim = 1: rows are points (RowVecs), obsdim = 2: columns are points (ColVecs); a bare matrix without obsdim
+        is ambiguous (the reference deprecated its default) and is rejected."""
+        if obsdim is not None:
+            X = np.asarray(x)
+            if X.ndim != 2 or obsdim not in (1, 2):
+                raise TypeError("obsdim applies to a matrix of inputs and is 1 (rows) or 2 (columns)")
+            x = RowVecs(X) if obsdim == 1 else ColVecs(X)
         return FiniteGP(self, x, s2)
 
 
@@ -638,10 +646,25 @@ def kernelmatrix_diag(k: Kernel, x):
     return var(GP(k), x)
 
 
+def mean_vector(m: "MeanFunction", x):
+    """mean_vector(m, x) (src/mean_function.jl:27,40,52-55)."""
+    pts = _Points(x)
+    return m.vector(pts, np.result_type(pts.a.dtype, np.float32))
+
+
+def _need_x(f, x, name):
+    """`mean(f::AbstractGP)` & co. are not defined on purpose (src/abstract_gp.jl:66-87): Julia's ErrorException."""
+    if x is None and isinstance(f, AbstractGP):
+        raise RuntimeError("`%s(f::AbstractGP)` is not defined (on purpose!).\nPlease provide an `AbstractVector` of locations "
+                           "`x` at which you wish to compute your %s vector%s, and call `%s(f(x))`" %
+                           (name, name, "s" if name.startswith("mean_and") else "", name))
+
+
 def mean(f, x=None):
     """mean(fx) (src/finite_gp_projection.jl:53) / mean(f, x) (src/abstract_gp.jl:19)."""
     if isinstance(f, FiniteGP):
         return mean(f.f, f.x)
+    _need_x(f, x, "mean")
     pts = _Points(x)
     if isinstance(f, GP):
         return f.mean.vector(pts, np.result_type(pts.a.dtype, np.float32))
@@ -661,6 +684,7 @@ def cov(f, x=None, z=None):
         if isinstance(f.f, GP):
             return _gram(f.f, f.x, None, f.s2, f.dtype)
         return mean_and_cov(f)[1]
+    _need_x(f, x, "cov")
     pts = _Points(x)
     if isinstance(f, GP):
         dt = np.result_type(pts.a.dtype, np.float32)
@@ -678,6 +702,7 @@ def var(f, x=None):
     """var(fx) (src/finite_gp_projection.jl:114-117) / var(f, x) (src/base_gp.jl:72)."""
     if isinstance(f, FiniteGP):
         return mean_and_var(f)[1]
+    _need_x(f, x, "var")
     pts = _Points(x)
     if isinstance(f, GP):
         dt = np.result_type(pts.a.dtype, np.float32)
@@ -707,6 +732,7 @@ def mean_and_var(f, x=None):
             m, v = _vfe_mean_var(f.f, f.x)
             return m, v + f.Sigma_y_diag.astype(v.dtype)
         return mean(f), var(f.f, f.x) + f.Sigma_y_diag
+    _need_x(f, x, "mean_and_var")
     return mean(f, x), var(f, x)
 
 
@@ -716,6 +742,7 @@ def mean_and_cov(f, x=None):
         if isinstance(f.f, PosteriorGP):
             return _post_call(f.f, f.x, f.Sigma_y_diag, want_cov=True)
         return mean(f), cov(f)
+    _need_x(f, x, "mean_and_cov")
     if isinstance(f, PosteriorGP):
         return _post_call(f, _Points(x), None, want_cov=True)
     return mean(f, x), cov(f, x)

@@ -177,3 +177,34 @@ def test_reference_sparse_testsets(fag, approx_name):
     rs.sparse_posterior_matches_exact(fag, A)
     for T in (np.float64, np.float32):
         rs.sparse_type_stability(fag, A, T)
+
+
+# ---- the host-side usage of the GPU parity suite (tests/test_gpu_parity.py), re-run against the fake library: a
+# regression net for api.py that needs no device (numerics are the oracle's on both sides, so only the plumbing is tested)
+import test_gpu_parity as gp  # noqa: E402
+
+PARITY_CASES = [
+    (gp.test_gram, dict(fam=ref.MATERN52, dtype=np.float64, n=63, m=70, d=3)),
+    (gp.test_gram, dict(fam=ref.LINEAR, dtype=np.float32, n=129, m=5, d=8)),
+    (gp.test_logpdf_posterior, dict(dtype=np.float64, n=129, d=3, fam=ref.SE)),
+    (gp.test_logpdf_posterior, dict(dtype=np.float32, n=10, d=1, fam=ref.MATERN32)),
+    (gp.test_multicolumn_and_noise_and_mean_variants, dict(dtype=np.float64)),
+    (gp.test_multicolumn_and_noise_and_mean_variants, dict(dtype=np.float32)),
+    (gp.test_mean_and_var_and_cov, dict(dtype=np.float64, n=200, m=77, d=3, fam=ref.SE)),
+    (gp.test_posterior_collapses_on_data, {}),
+    (gp.test_operator_api_on_device_factor, {}),
+    (gp.test_rand, dict(dtype=np.float64)),
+    (gp.test_not_posdef_maps_to_exception, {}),
+    (gp.test_dimension_mismatch, {}),
+    (gp.test_golden_fixtures, dict(name="c1.npz")),
+    (gp.test_golden_fixtures, dict(name="c3_n500_f32.npz")),
+    (gp.test_sequential_conditioning_equals_batch, dict(dtype=np.float64, n1=40, n2=30)),
+    (gp.test_vfe_elbo_and_posterior, dict(dtype=np.float64, n=200, m=20, d=2, fam=ref.SE)),
+    (gp.test_vfe_with_z_equal_x_reproduces_exact, {}),
+]
+
+
+@pytest.mark.parametrize("case", range(len(PARITY_CASES)))
+def test_gpu_parity_suite_plumbing(fag, case):
+    fn, kw = PARITY_CASES[case]
+    _call(fn, fag, **kw)

@@ -52,3 +52,36 @@ def test_finite_gp_construction(ag):
         f(np.linspace(0, 1, 3), np.eye(3))  # dense Sigma_y is outside the device path
     assert np.array_equal(ag.mean(fx), np.zeros(7))
     assert np.allclose(ag.var(f, np.zeros(3)), 1.0)
+
+
+def test_reference_mean_function_testset(ag):
+    """/root/reference/test/mean_function.jl:1-34: mean_vector for Zero / Const / Custom means on vectors, ColVecs, RowVecs."""
+    rng = np.random.default_rng(123456)
+    N, D = 5, 3
+    x1 = rng.standard_normal(N)
+    xc, xr = ag.ColVecs(rng.standard_normal((D, N))), ag.RowVecs(rng.standard_normal((N, D)))
+    c = rng.standard_normal()
+    foo = lambda x: np.sum(np.square(x))
+    for x in (x1, xc, xr):
+        assert np.array_equal(ag.mean_vector(ag.ZeroMean(), x), np.zeros(N))
+        assert np.array_equal(ag.mean_vector(ag.ConstMean(c), x), np.full(N, c))
+    assert np.allclose(ag.mean_vector(ag.CustomMean(foo), x1), [foo(v) for v in x1])
+    assert np.allclose(ag.mean_vector(ag.CustomMean(foo), xc), [foo(col) for col in xc.X.T])   # eachcol
+    assert np.allclose(ag.mean_vector(ag.CustomMean(foo), xr), [foo(row) for row in xr.X])     # eachrow
+
+
+def test_reference_abstract_gp_testset_and_obsdim(ag):
+    """/root/reference/test/abstract_gp.jl:1-9: mean(f) & co. without locations raise (ErrorException);
+    /root/reference/test/finite_gp_projection.jl:38-43: f(Xmat; obsdim) == f(RowVecs / ColVecs)."""
+    f = ag.GP(ag.SqExponentialKernel())
+    for fn in (ag.mean, ag.var, ag.cov, ag.mean_and_var, ag.mean_and_cov):
+        with pytest.raises(RuntimeError, match="not defined"):
+            fn(f)
+    Xmat = np.random.default_rng(0).standard_normal((1, 9))
+    for x, obsdim in ((ag.RowVecs(Xmat), 1), (ag.ColVecs(Xmat), 2)):
+        a, b = f(Xmat, obsdim=obsdim), f(x)
+        assert np.array_equal(a.x.a, b.x.a) and a.s2 == b.s2
+        a, b = f(Xmat, 1e-3, obsdim=obsdim), f(x, 1e-3)
+        assert np.array_equal(a.x.a, b.x.a) and a.s2 == b.s2 == 1e-3
+    with pytest.raises(TypeError):
+        f(Xmat)  # ambiguous without obsdim
