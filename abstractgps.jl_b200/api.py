@@ -836,8 +836,12 @@ def inducing_points(p):
 
 
 class ApproxPosteriorGP(AbstractGP):
-    def __init__(self, approx, prior, handle, dtype):
+    """ApproxPosteriorGP(approx, prior, data) (src/sparse_approximations.jl:25-29); `data` lives on the device behind
+    the handle, the observations are kept host-side for `update_posterior`."""
+
+    def __init__(self, approx, prior, handle, dtype, x=None, y=None, s2=None):
         self.approx, self.prior, self.h, self.dtype = approx, prior, handle, dtype
+        self.x, self.y, self.s2 = x, y, s2
 
     def __del__(self):
         try:
@@ -892,7 +896,28 @@ def _vfe_posterior(vfe: VFE, fx: FiniteGP, y):
     h = C.c_void_p()
     eng.check(eng.L.agp_vfe_fit(eng.h, cabi.dtype_code(dt), C.byref(ks), C.byref(ms), C.byref(ns), cabi.AGP_POINT_MAJOR,
                                 cabi.ptr(pts.a), pts.n, pts.D, cabi.ptr(z.a), z.n, C.byref(js), cabi.ptr(y), C.byref(h)))
-    return ApproxPosteriorGP(vfe, f, h, dt)
+    return ApproxPosteriorGP(vfe, f, h, dt, x=fx.x, y=np.array(y), s2=fx.s2)
+
+
+def update_posterior(p: ApproxPosteriorGP, a: FiniteGP, y=None):
+    """update_posterior(f_post_approx, fx, y) -- new observations, same pseudo-points (src/sparse_approximations.jl:87-119)
+    -- and update_posterior(f_post_approx, fz) -- pseudo-points appended (:130-176).  The reference patches its host
+    factors with rank-1 / block updates; here the posterior is re-formed by the streamed device fit on the concatenated
+    observations / inducing set (one pass over the data, O(N M^2) like the first fit), which yields the same posterior
+    (test/sparse_approximations.jl:27-85 compares the two routes to atol 1e-5)."""
+    if a.f is not p.prior:
+        raise AssertionError("f_post_approx.prior === fx.f")  # :92 / :131
+    if y is not None:
+        y = np.asarray(y, dtype=p.dtype)
+        if y.shape[0] != len(a):
+            raise DimensionMismatch("length(fx) != length(y)")
+        old_fx = FiniteGP(p.prior, p.x, p.s2)
+        s2 = np.concatenate([old_fx.Sigma_y_diag.astype(p.dtype), a.Sigma_y_diag.astype(p.dtype)])
+        return _vfe_posterior(p.approx, FiniteGP(p.prior, vcat(p.x, a.x), s2), np.concatenate([p.y, y]))
+    fz_old = p.approx.fz
+    fz_new = FiniteGP(p.prior, vcat(fz_old.x, a.x), fz_old.s2 if np.ndim(fz_old.s2) == 0 else
+                      np.concatenate([np.asarray(fz_old.s2), a.Sigma_y_diag]))
+    return _vfe_posterior(type(p.approx)(fz_new), FiniteGP(p.prior, p.x, p.s2), p.y)
 
 
 def _vfe_mean_var(p: ApproxPosteriorGP, pts: _Points):

@@ -122,3 +122,29 @@ def sparse_posterior_matches_exact(ag, Approx):
     xt = rng.standard_normal(100)
     assert approx(ag.mean(f_post, xt), ag.mean(f_approx, xt), rtol=1e-6)
     assert approx(ag.var(f_post, xt), ag.var(f_approx, xt), rtol=1e-6, atol=1e-9)
+
+
+def sparse_update_posterior(ag, Approx):
+    """test/sparse_approximations.jl:27-85: online (update_posterior) vs batch, new observations and new pseudo-points.
+    The reference compares its host caches field by field (atol 1e-5); the device handle exposes predictions, so the two
+    routes are compared there, plus the inducing points."""
+    rng = np.random.default_rng(1)
+    X, y = rng.random(10), rng.random(10)
+    Z = rng.random(4)
+    f = ag.GP(ag.SqExponentialKernel())
+    xt = np.linspace(-0.2, 1.2, 23)
+    p1 = ag.posterior(Approx(f(Z)), f(X[:7], 0.1), y[:7])
+    u1 = ag.update_posterior(p1, f(X[7:], 0.1), y[7:])
+    p2 = ag.posterior(Approx(f(Z)), f(X, 0.1), y)
+    assert approx(ag.inducing_points(u1).a, ag.inducing_points(p2).a, atol=1e-5)
+    for a, b in zip(ag.mean_and_var(u1, xt), ag.mean_and_var(p2, xt)):
+        assert approx(a, b, rtol=1e-6, atol=1e-5)
+    assert isinstance(u1.approx, Approx)
+    Z1, Z2 = rng.random(4), rng.random(3)
+    q1 = ag.posterior(Approx(f(Z1)), f(X, 0.1), y)
+    v1 = ag.update_posterior(q1, f(Z2))
+    q2 = ag.posterior(Approx(f(np.concatenate([Z1, Z2]))), f(X, 0.1), y)
+    assert approx(ag.inducing_points(v1).a, ag.inducing_points(q2).a, atol=1e-5)
+    for a, b in zip(ag.mean_and_var(v1, xt), ag.mean_and_var(q2, xt)):
+        assert approx(a, b, rtol=1e-6, atol=1e-5)
+    assert isinstance(v1.approx, Approx)

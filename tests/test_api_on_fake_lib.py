@@ -175,6 +175,7 @@ def test_reference_sparse_testsets(fag, approx_name):
     A = getattr(fag, approx_name)
     rs.sparse_approx_log_evidence(fag, A)
     rs.sparse_posterior_matches_exact(fag, A)
+    rs.sparse_update_posterior(fag, A)
     for T in (np.float64, np.float32):
         rs.sparse_type_stability(fag, A, T)
 

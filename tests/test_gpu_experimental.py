@@ -77,5 +77,6 @@ def test_reference_sparse_testsets_on_device(ag, approx_name):
     A = getattr(ag, approx_name)
     rs.sparse_approx_log_evidence(ag, A)
     rs.sparse_posterior_matches_exact(ag, A)
+    rs.sparse_update_posterior(ag, A)
     for T in (np.float64, np.float32):
         rs.sparse_type_stability(ag, A, T)
