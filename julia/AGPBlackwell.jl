@@ -13,7 +13,7 @@
 module AGPBlackwell
 
 using AbstractGPs, KernelFunctions, LinearAlgebra, FillArrays
-import AbstractGPs: posterior, mean_and_var, elbo, approx_log_evidence, FiniteGP, PosteriorGP, VFE
+import AbstractGPs: posterior, mean_and_var, elbo, approx_log_evidence, FiniteGP, PosteriorGP, VFE, DTC
 import AbstractGPs: Xt_invA_X, Xt_invA_Y, diag_Xt_invA_X, tr_Xt_invA_X
 import Distributions: logpdf
 import Random
@@ -217,6 +217,23 @@ function approx_log_evidence(vfe::VFE, fx::DevFiniteGP{T}, y::AbstractVector{<:R
             c.h, agp_dtype(T), ks, ms, ns, layout, X, length(fx), D, Z, length(vfe.fz), js, yv, pointer(out, 1), pointer(out, 2)))
     end
     return out[1]
+end
+
+# replaces approx_log_evidence(::DTC, fx, y) src/sparse_approximations.jl:282-286: the DTC objective is the second
+# output of the same call
+function approx_log_evidence(dtc::DTC, fx::DevFiniteGP{T}, y::AbstractVector{<:Real}) where {T}
+    @assert dtc.fz.f === fx.f
+    c = ctx(); X, layout, D = points(fx.x); Z, _, _ = points(dtc.fz.x)
+    ks, k1 = kernel_spec(fx.f.kernel, T); ms, k2 = mean_spec(fx.f.mean, fx.x, T)
+    ns, k3 = noise_spec(fx.Σy, T); js, k4 = noise_spec(dtc.fz.Σy, T)
+    yv = convert(Vector{T}, y); out = Vector{T}(undef, 2)
+    lock(c.lock) do
+        GC.@preserve X Z yv k1 k2 k3 k4 check(c, ccall((:agp_vfe_elbo, libagp), Int32,
+            (Ptr{Cvoid}, Int32, Ref{AgpKernel}, Ref{AgpMean}, Ref{AgpNoise}, Int32, Ptr{Cvoid}, Int64, Int32, Ptr{Cvoid}, Int64,
+             Ref{AgpNoise}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+            c.h, agp_dtype(T), ks, ms, ns, layout, X, length(fx), D, Z, length(dtc.fz), js, yv, pointer(out, 1), pointer(out, 2)))
+    end
+    return out[2]
 end
 
 end # module
