@@ -209,3 +209,11 @@ PARITY_CASES = [
 def test_gpu_parity_suite_plumbing(fag, case):
     fn, kw = PARITY_CASES[case]
     _call(fn, fag, **kw)
+
+
+def test_smoke_entry_plumbing(fag, capsys):
+    """__graft_entry__.smoke() end to end with the fake engine installed: its host calls stay valid as api.py evolves
+    (the real smoke runs the same body on cuda:0)."""
+    import __graft_entry__ as ge
+    ge.smoke()
+    assert "smoke ok" in capsys.readouterr().out
