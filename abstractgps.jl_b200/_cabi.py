@@ -74,6 +74,9 @@ SIGNATURES = {
     "agp_vfe_fit": (C.c_int32, [_P, C.c_int32, _K, _M, _N, C.c_int32, _P, C.c_int64, C.c_int32, _P, C.c_int64, _N,
                                 _P, C.POINTER(_P)]),
     "agp_vfe_mean_var": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _P, _P]),
+    "agp_vfe_mean_cov": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _P, _P]),
+    "agp_vfe_post_logpdf": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _N, _P, C.c_int32, _P]),
+    "agp_vfe_post_rand": (C.c_int32, [_P, C.c_int32, _P, C.c_int64, _N, _P, C.c_int32, _P]),
     "agp_vfe_post_free": (C.c_int32, [_P]),
     "agp_debug_ozaki_syrk": (C.c_int32, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                          C.c_int32]),

@@ -319,6 +319,58 @@ def _noise_struct(s2, n, dt, keep):
     return ns
 
 
+def _vfe_mean_cov(p: "ApproxPosteriorGP", pts: _Points):
+    """mean_and_cov(::ApproxPosteriorGP, x*) (src/sparse_approximations.jl:205-210) through agp_vfe_mean_cov (EXPERIMENTAL)."""
+    eng = engine()
+    pts = pts.astype(p.dtype)
+    m = np.empty(pts.n, dtype=p.dtype)
+    Cv = np.empty((pts.n, pts.n), dtype=p.dtype, order="F")
+    eng.check(eng.L.agp_vfe_mean_cov(p.h, cabi.AGP_POINT_MAJOR, cabi.ptr(pts.a), pts.n, cabi.ptr(m), cabi.ptr(Cv)))
+    if isinstance(p.prior.mean, CustomMean):
+        m = m + p.prior.mean.vector(pts, p.dtype)
+    return m, Cv
+
+
+def _vfe_post_logpdf(fx: "FiniteGP", y):
+    """logpdf(f_approx_post(x*, s2), y) on the device (agp_vfe_post_logpdf, EXPERIMENTAL)."""
+    eng = engine()
+    p = fx.f
+    dt = p.dtype
+    pts = fx.x.astype(dt)
+    Y = np.asarray(y, dtype=dt)
+    vec = Y.ndim == 1
+    Yf = Y.reshape(-1, 1) if vec else Y
+    if Yf.shape[0] != pts.n:
+        raise DimensionMismatch("length(fx) = %d but y has %d rows" % (pts.n, Yf.shape[0]))
+    if isinstance(p.prior.mean, CustomMean):  # the handle knows Zero/Const means: a closure mean is removed here
+        Yf = Yf - p.prior.mean.vector(pts, dt)[:, None]
+    keep = []
+    ns = _noise_struct(fx.s2, pts.n, dt, keep)
+    lp = np.empty(Yf.shape[1], dtype=dt)
+    for s0 in range(0, Yf.shape[1], 128):
+        s1 = min(Yf.shape[1], s0 + 128)
+        Yc = np.asfortranarray(Yf[:, s0:s1])
+        eng.check(eng.L.agp_vfe_post_logpdf(p.h, cabi.AGP_POINT_MAJOR, cabi.ptr(pts.a), pts.n, C.byref(ns), cabi.ptr(Yc),
+                                            s1 - s0, cabi.ptr(lp[s0:s1])))
+    return lp[0] if vec else lp
+
+
+def _vfe_post_rand_from_normals(fx: "FiniteGP", Z, squeeze=False):
+    eng = engine()
+    p = fx.f
+    dt = p.dtype
+    pts = fx.x.astype(dt)
+    Z = np.asfortranarray(np.asarray(Z, dtype=dt).reshape(pts.n, -1))
+    keep = []
+    ns = _noise_struct(fx.s2, pts.n, dt, keep)
+    out = np.empty_like(Z, order="F")
+    eng.check(eng.L.agp_vfe_post_rand(p.h, cabi.AGP_POINT_MAJOR, cabi.ptr(pts.a), pts.n, C.byref(ns), cabi.ptr(Z), Z.shape[1],
+                                      cabi.ptr(out)))
+    if isinstance(p.prior.mean, CustomMean):
+        out = out + p.prior.mean.vector(pts, dt)[:, None]
+    return out[:, 0] if squeeze else out
+
+
 # ---------------------------------------------------------------------------------------------
 # GP / FiniteGP / PosteriorGP  (src/base_gp.jl, src/finite_gp_projection.jl, src/exact_gpr_posterior.jl)
 # ---------------------------------------------------------------------------------------------
@@ -491,6 +543,8 @@ def logpdf(fx: FiniteGP, y):
     """logpdf(fx, y) (src/finite_gp_projection.jl:306-311); matrix y -> per-column values."""
     if isinstance(fx.f, PosteriorGP):
         return _post_logpdf(fx, y)
+    if isinstance(fx.f, ApproxPosteriorGP):
+        return _vfe_post_logpdf(fx, y)
     if not isinstance(fx.f, GP):
         raise AGPError(cabi.AGP_ERR_UNSUPPORTED, "logpdf of a FiniteGP over %s is outside the device hot path"
                        % type(fx.f).__name__)
@@ -695,6 +749,13 @@ def cov(f, x=None, z=None):
         Cx = cov(f.prior, f.data.x, pts)
         Cz = cov(f.prior, f.data.x, _Points(z))
         return cov(f.prior, pts, _Points(z)) - Xt_invA_Y(Cx, f.data.C, Cz)
+    if isinstance(f, ApproxPosteriorGP):
+        if z is None:  # cov(f_approx_post, x) src/sparse_approximations.jl:187-190
+            return _vfe_mean_cov(f, pts)[1]
+        # cov(f_approx_post, x, z) (:197-203): the off-diagonal block of the covariance at [x; z]
+        zp = _Points(z)
+        Cxz = _vfe_mean_cov(f, vcat(pts, zp))[1]
+        return np.asfortranarray(Cxz[:pts.n, pts.n:])
     raise TypeError(type(f))
 
 
@@ -741,10 +802,16 @@ def mean_and_cov(f, x=None):
     if isinstance(f, FiniteGP):
         if isinstance(f.f, PosteriorGP):
             return _post_call(f.f, f.x, f.Sigma_y_diag, want_cov=True)
+        if isinstance(f.f, ApproxPosteriorGP):
+            m, Cv = _vfe_mean_cov(f.f, f.x)
+            Cv[np.diag_indices(len(f))] += f.Sigma_y_diag.astype(Cv.dtype)
+            return m, Cv
         return mean(f), cov(f)
     _need_x(f, x, "mean_and_cov")
     if isinstance(f, PosteriorGP):
         return _post_call(f, _Points(x), None, want_cov=True)
+    if isinstance(f, ApproxPosteriorGP):
+        return _vfe_mean_cov(f, _Points(x))
     return mean(f, x), cov(f, x)
 
 
@@ -764,11 +831,11 @@ def rand(*args):
     rng = args.pop(0) if not isinstance(args[0], FiniteGP) else np.random.default_rng()
     fx = args.pop(0)
     S = args.pop(0) if args else None
-    if not isinstance(fx.f, (GP, PosteriorGP)):
+    if not isinstance(fx.f, (GP, PosteriorGP, ApproxPosteriorGP)):
         raise AGPError(cabi.AGP_ERR_UNSUPPORTED, "sampling from a FiniteGP over %s is outside the device hot path"
                        % type(fx.f).__name__)
     eng = engine()
-    dt = fx.f.data.C.dtype if isinstance(fx.f, PosteriorGP) else fx.dtype
+    dt = fx.f.data.C.dtype if isinstance(fx.f, PosteriorGP) else (fx.f.dtype if isinstance(fx.f, ApproxPosteriorGP) else fx.dtype)
     pts = fx.x.astype(dt)
     ns_cols = 1 if S is None else int(S)
     Z = np.asfortranarray(rng.standard_normal((pts.n, ns_cols)).astype(dt))
@@ -778,6 +845,8 @@ def rand(*args):
 def rand_from_normals(fx: FiniteGP, Z, squeeze=False):
     if isinstance(fx.f, PosteriorGP):
         return _post_rand_from_normals(fx, Z, squeeze)
+    if isinstance(fx.f, ApproxPosteriorGP):
+        return _vfe_post_rand_from_normals(fx, Z, squeeze)
     eng = engine()
     f = _prior_of(fx)
     dt = fx.dtype

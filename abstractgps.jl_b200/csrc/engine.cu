@@ -1275,6 +1275,128 @@ int vfe_mean_var_impl(agp_vfe_post* p, int layout, const void* Xs, int64_t Ms, v
 // replicated points.  (grid_p > 1 is declared in the ABI but not built: on NVSwitch the panel
 // broadcast is ~5 % of the factorisation at C4, so the 2-D row/column split buys nothing yet.)
 // ------------------------------------------------------------------------------------------------
+// ---- EXPERIMENTAL (composed of validated launches, not yet run on a device): full predictive covariance of the
+// approximate posterior, and logpdf / rand of a FiniteGP over it.
+//   mean_and_cov(::ApproxPosteriorGP, x*)  /root/reference/src/sparse_approximations.jl:205-210 (cov :187-190):
+//   A = U' \ K(z, x*),  m* = m(x*) + A' m_e,  C* = K** - A'A + (Lam' \ A)'(Lam' \ A)
+// mode "cov": C* (no noise) is returned.  mode "factor": K** + Sigma* is generated with the noise fused, C* + Sigma* is
+// factored in place with (Y - m*)' in the border tile (logpdf, src/finite_gp_projection.jl:306-318) and / or multiplied
+// into the caller's normals (rand, :233-240) -- the same tail as post_cond_impl.
+template <typename T>
+int vfe_cond_impl(agp_vfe_post* p, int layout, const void* Xs, int64_t M, const agp_noise* noise_s, void* mean_out,
+                  void* cov_out, const void* Y, int S, void* logpdf_out, const void* Z, int Sz, void* rand_out) {
+  agp_ctx* ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  CK(cudaSetDevice(ctx->device));
+  if (M <= 0) { ctx->err = "M must be positive"; return AGP_ERR_DIM_MISMATCH; }
+  if (!Xs) { ctx->err = "Xs is NULL"; return AGP_ERR_INVALID; }
+  if (S < 0 || S > TILE) { ctx->err = "number of right-hand sides must be in [0,128]"; return AGP_ERR_UNSUPPORTED; }
+  if (S > 0 && (!Y || !logpdf_out)) { ctx->err = "Y/logpdf_out is NULL"; return AGP_ERR_INVALID; }
+  if (Sz > 0 && (!Z || !rand_out)) { ctx->err = "Z/out is NULL"; return AGP_ERR_INVALID; }
+  const bool factor = (S > 0 || Sz > 0);
+  static const agp_noise default_noise{0, 1e-18, nullptr};
+  if (factor && !noise_s) noise_s = &default_noise;
+  if (factor && noise_s->kind == 1 && !noise_s->v) { ctx->err = "noise vector is NULL"; return AGP_ERR_INVALID; }
+  const int64_t c_pad = round_up(M, TILE), ldf = c_pad + TILE;
+  const int nblk = (int)(c_pad / TILE);
+  Scratch sc(ctx);
+  T* Xst = nullptr;
+  int rc = prep_points<T>(ctx, sc, &p->k, (const T*)p->ard, layout, Xs, M, c_pad, p->D, &Xst, false);
+  if (rc) return rc;
+  T *noise_d = nullptr, *Yd = nullptr;
+  if (factor && noise_s->kind == 1) { rc = upload<T>(ctx, sc, noise_s->v, M, true, &noise_d); if (rc) return rc; }
+  if (S > 0) { rc = upload<T>(ctx, sc, Y, (size_t)M * S, false, &Yd); if (rc) return rc; }
+  void* tmp = nullptr;
+  CK(sc.alloc(&tmp, (size_t)p->m_pad * c_pad * sizeof(T)));
+  T* B = (T*)tmp;
+  CK(sc.alloc(&tmp, (size_t)c_pad * sizeof(T)));
+  T* mu = (T*)tmp;
+  CK(cudaMemsetAsync(mu, 0, (size_t)c_pad * sizeof(T), s));
+  CK(sc.alloc(&tmp, (size_t)ldf * c_pad * sizeof(T)));
+  T* Lf = (T*)tmp;
+  GramParams gp{};
+  fill_gram_params<T>(gp, &p->k, 0, 0, p->m, M, nullptr, nullptr);
+  launch_gram<T>((const T*)p->Zt, Xst, p->m_pad, c_pad, p->D, B, p->m_pad, gp, s);
+  forward_subst_multi<T>(ctx, (const T*)p->U, p->lda, (const T*)p->Udinv, p->m_pad, B, p->m_pad, c_pad);  // A
+  launch_gemv_t<T>(B, p->m_pad, p->m_pad, M, (const T*)p->m_e, p->mean_kind, p->mean_c, (const T*)nullptr, mu, s);
+  GramParams gs{};  // K** (+ Sigma* when factoring), full square: the covariance is returned whole
+  fill_gram_params<T>(gs, &p->k, 1, 0, M, M, factor ? noise_s : nullptr, noise_d);
+  launch_gram<T>(Xst, Xst, c_pad, c_pad, p->D, Lf, ldf, gs, s);
+  {
+    GemmArgs g{};  // -= A'A
+    g.A = B; g.lda = p->m_pad; g.a_kmajor = 1;
+    g.B = B; g.ldb = p->m_pad; g.b_kmajor = 1;
+    g.C = Lf; g.ldc = ldf; g.M = c_pad; g.N = c_pad; g.K = p->m_pad; g.alpha_neg = 1; g.beta_one = 1;
+    launch_gemm<T>(g, s);
+  }
+  forward_subst_multi<T>(ctx, (const T*)p->Lam, p->lda, (const T*)p->Ldinv, p->m_pad, B, p->m_pad, c_pad);  // Lam' \ A
+  {
+    GemmArgs g{};  // += (Lam' \ A)'(Lam' \ A)
+    g.A = B; g.lda = p->m_pad; g.a_kmajor = 1;
+    g.B = B; g.ldb = p->m_pad; g.b_kmajor = 1;
+    g.C = Lf; g.ldc = ldf; g.M = c_pad; g.N = c_pad; g.K = p->m_pad; g.beta_one = 1;
+    launch_gemm<T>(g, s);
+  }
+  if (mean_out) { rc = download<T>(ctx, mean_out, mu, (size_t)M, false); if (rc) return rc; }
+  if (!factor) {
+    if (cov_out) {
+      cudaMemcpyKind kind = ctx->memspace == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+      CK(cudaMemcpy2DAsync(cov_out, (size_t)M * sizeof(T), Lf, (size_t)ldf * sizeof(T), (size_t)M * sizeof(T), (size_t)M, kind, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return AGP_OK;
+  }
+  CK(sc.alloc(&tmp, (size_t)nblk * TILE * TILE * sizeof(T)));
+  T* Dinv = (T*)tmp;
+  CK(sc.alloc(&tmp, (size_t)(nblk + TILE + 2) * sizeof(double)));
+  double* dscal = (double*)tmp;
+  CK(sc.alloc(&tmp, sizeof(int)));
+  int* dinfo = (int*)tmp;
+  CK(cudaMemsetAsync(dinfo, 0, sizeof(int), s));
+  CK(sc.alloc(&tmp, (size_t)TILE * sizeof(T)));
+  T* lp_d = (T*)tmp;
+  launch_border_init<T>(Lf, ldf, M, c_pad, Yd, M, S, 2, 0.0, (const T*)mu, s);  // border = (Y - m*)'
+  prof_begin(ctx);
+  cholesky_inplace<T>(ctx, Lf, ldf, c_pad, ldf, Dinv, dscal, dinfo);
+  if (S > 0) {
+    CK(sc.alloc(&tmp, (size_t)S * c_pad * sizeof(T)));
+    launch_extract_v<T>(Lf, ldf, c_pad, S, (T*)tmp, dscal + nblk, s);
+    launch_finalize_logpdf<T>(dscal, nblk, dscal + nblk, S, M, lp_d, dscal + nblk + TILE, s);
+  }
+  int h_info = 0;
+  CK(cudaMemcpyAsync(&h_info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  if (h_info != 0) {
+    ctx->info = h_info;
+    char b[128];
+    snprintf(b, sizeof(b), "approximate posterior covariance is not positive definite; Cholesky failed at pivot %d", h_info);
+    ctx->err = b;
+    return AGP_ERR_NOT_POSDEF;
+  }
+  if (S > 0) CK(cudaMemcpyAsync(logpdf_out, lp_d, (size_t)S * sizeof(T), cudaMemcpyDeviceToHost, s));
+  if (Sz > 0) {
+    const int64_t s_pad = round_up(Sz, 4);
+    CK(sc.alloc(&tmp, (size_t)c_pad * s_pad * sizeof(T) * 2));
+    T* Zd = (T*)tmp; T* Od = Zd + c_pad * s_pad;
+    CK(cudaMemsetAsync(Zd, 0, (size_t)c_pad * s_pad * sizeof(T), s));
+    cudaMemcpyKind kin = ctx->memspace == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cudaMemcpyKind kout = ctx->memspace == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    CK(cudaMemcpy2DAsync(Zd, (size_t)c_pad * sizeof(T), Z, (size_t)M * sizeof(T), (size_t)M * sizeof(T), (size_t)Sz, kin, s));
+    GemmArgs g{};
+    g.A = Lf; g.lda = ldf; g.a_kmajor = 0;
+    g.B = Zd; g.ldb = c_pad; g.b_kmajor = 1;
+    g.C = Od; g.ldc = c_pad; g.M = c_pad; g.N = s_pad; g.K = c_pad; g.trmm_lower = 1;
+    launch_gemm<T>(g, s);
+    launch_add_mean_cols<T>(Od, c_pad, M, Sz, 2, 0.0, (const T*)mu, s);
+    CK(cudaMemcpy2DAsync(rand_out, (size_t)M * sizeof(T), Od, (size_t)c_pad * sizeof(T), (size_t)M * sizeof(T), (size_t)Sz, kout, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  return AGP_OK;
+}
+
 template <typename T>
 int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_noise* noise, int layout,
                   const void* X, int64_t N, int D, const void* Y, int S, void* logpdf_out, void* alpha_out) {
@@ -1743,6 +1865,25 @@ int32_t agp_vfe_mean_var(agp_vfe_post* p, int32_t layout, const void* Xs, int64_
   if (!p) return AGP_ERR_INVALID;
   return DISPATCH(p->dtype, vfe_mean_var_impl<float>(p, layout, Xs, Ms, mean_out, var_out),
                   vfe_mean_var_impl<double>(p, layout, Xs, Ms, mean_out, var_out));
+}
+int32_t agp_vfe_mean_cov(agp_vfe_post* p, int32_t layout, const void* Xs, int64_t M, void* mean_out, void* cov_out) {
+  if (!p) return AGP_ERR_INVALID;
+  return DISPATCH(p->dtype, vfe_cond_impl<float>(p, layout, Xs, M, nullptr, mean_out, cov_out, nullptr, 0, nullptr, nullptr, 0, nullptr),
+                  vfe_cond_impl<double>(p, layout, Xs, M, nullptr, mean_out, cov_out, nullptr, 0, nullptr, nullptr, 0, nullptr));
+}
+int32_t agp_vfe_post_logpdf(agp_vfe_post* p, int32_t layout, const void* Xs, int64_t M, const agp_noise* noise_s,
+                            const void* Y, int32_t S, void* logpdf_out) {
+  if (!p) return AGP_ERR_INVALID;
+  if (S <= 0) { p->ctx->err = "S must be positive"; return AGP_ERR_INVALID; }
+  return DISPATCH(p->dtype, vfe_cond_impl<float>(p, layout, Xs, M, noise_s, nullptr, nullptr, Y, S, logpdf_out, nullptr, 0, nullptr),
+                  vfe_cond_impl<double>(p, layout, Xs, M, noise_s, nullptr, nullptr, Y, S, logpdf_out, nullptr, 0, nullptr));
+}
+int32_t agp_vfe_post_rand(agp_vfe_post* p, int32_t layout, const void* Xs, int64_t M, const agp_noise* noise_s,
+                          const void* Z, int32_t S, void* out) {
+  if (!p) return AGP_ERR_INVALID;
+  if (S <= 0) return AGP_OK;
+  return DISPATCH(p->dtype, vfe_cond_impl<float>(p, layout, Xs, M, noise_s, nullptr, nullptr, nullptr, 0, nullptr, Z, S, out),
+                  vfe_cond_impl<double>(p, layout, Xs, M, noise_s, nullptr, nullptr, nullptr, 0, nullptr, Z, S, out));
 }
 int32_t agp_vfe_post_free(agp_vfe_post* p) {
   if (!p) return AGP_OK;

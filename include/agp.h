@@ -190,6 +190,17 @@ int32_t agp_vfe_fit(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, const agp_
 /* mean_and_var(::ApproxPosteriorGP, x*) src/sparse_approximations.jl:212-217 */
 int32_t agp_vfe_mean_var(agp_vfe_post* p, int32_t layout, const void* Xs, int64_t Ms,
                          void* mean_out, void* var_out);
+/* EXPERIMENTAL -- composed of validated kernels, not yet run on a device.
+ * mean_and_cov(::ApproxPosteriorGP, x*) src/sparse_approximations.jl:205-210 (cov :187-190); cov_out M x M column-major,
+ * no observation noise.  The prior mean at x* is the handle's Zero/Const mean (a closure mean is added by the host). */
+int32_t agp_vfe_mean_cov(agp_vfe_post* p, int32_t layout, const void* Xs, int64_t M, void* mean_out,
+                         void* cov_out);
+/* logpdf(f_approx_post(x*, Sigma*), Y) and rand(f_approx_post(x*, Sigma*), S): src/finite_gp_projection.jl:306-318,
+ * :233-240 over the approximate posterior -- C* + Sigma* is formed and factored on the device like agp_post_logpdf. */
+int32_t agp_vfe_post_logpdf(agp_vfe_post* p, int32_t layout, const void* Xs, int64_t M, const agp_noise* noise_s,
+                            const void* Y, int32_t S, void* logpdf_out);
+int32_t agp_vfe_post_rand(agp_vfe_post* p, int32_t layout, const void* Xs, int64_t M, const agp_noise* noise_s,
+                          const void* Z, int32_t S, void* out);
 int32_t agp_vfe_post_free(agp_vfe_post* p);
 
 /* ---- test hook for the tcgen05 int8-sliced fp64 trailing update (csrc/umma_ozaki.cu): DEVICE pointers;

@@ -484,6 +484,24 @@ def vfe_mean_and_var(vp, Xs):
     return m_post, c_post
 
 
+def vfe_mean_and_cov(vp, Xs):
+    """mean_and_cov(::ApproxPosteriorGP, x*) src/sparse_approximations.jl:205-210 (cov :187-190)."""
+    k = vp["k"]
+    Xs = np.asarray(Xs, dtype=vp["z"].dtype)
+    A = _Ut_solve(vp["U"], kernelmatrix(k, vp["z"], Xs))
+    m_post = vp["mean"].vector(Xs.shape[0], Xs.dtype) + A.T @ vp["m_e"]
+    C_post = kernelmatrix(k, Xs) - A.T @ A + Xt_invA_X(vp["Lam_U"], A)
+    return m_post, C_post
+
+
+def vfe_cov_cross(vp, Xs, Ys):
+    """cov(::ApproxPosteriorGP, x, y) src/sparse_approximations.jl:197-203."""
+    k = vp["k"]
+    A_zx = _Ut_solve(vp["U"], kernelmatrix(k, vp["z"], Xs))
+    A_zy = _Ut_solve(vp["U"], kernelmatrix(k, vp["z"], Ys))
+    return kernelmatrix(k, Xs, Ys) - A_zx.T @ A_zy + Xt_invA_Y(A_zx, vp["Lam_U"], A_zy)
+
+
 # ---------------------------------------------------------------------------
 # Synthetic workloads of SURVEY.md s8(d) -- identical bytes go to oracle and GPU
 # ---------------------------------------------------------------------------

@@ -312,6 +312,52 @@ class FakeLib:
         _arr(var_out, (Ms,), dt)[...] = v
         return OK
 
+    def _vp(self, p):
+        vp = self.vposts[self._h(p)]
+        if vp["mean"].kind == 2:  # like the device handle: Zero/Const means only
+            vp = dict(vp, mean=ref.MeanSpec())
+        return vp
+
+    def agp_vfe_mean_cov(self, p, layout, Xs, M, mean_out, cov_out):
+        self.calls.append("agp_vfe_mean_cov")
+        vp = self._vp(p)
+        dt, D = vp["z"].dtype, vp["z"].shape[1]
+        m, Cv = ref.vfe_mean_and_cov(vp, self._points(layout, Xs, M, D, dt))
+        if _addr(mean_out) is not None:
+            _arr(mean_out, (M,), dt)[...] = m
+        if _addr(cov_out) is not None:
+            _arr(cov_out, (M, M), dt, "F")[...] = Cv
+        return OK
+
+    def _vfe_factor(self, p, layout, Xs, M, ns):
+        vp = self._vp(p)
+        dt, D = vp["z"].dtype, vp["z"].shape[1]
+        m, Cv = ref.vfe_mean_and_cov(vp, self._points(layout, Xs, M, D, dt))
+        Cv = Cv.copy()
+        Cv[np.diag_indices(M)] += self._noise(ns, M, dt).diag(M, dt)
+        return dt, m, ref.cholesky_upper(Cv)
+
+    def agp_vfe_post_logpdf(self, p, layout, Xs, M, ns, Y, S, lp_out):
+        self.calls.append("agp_vfe_post_logpdf")
+        try:
+            dt, m, U = self._vfe_factor(p, layout, Xs, M, ns)
+        except np.linalg.LinAlgError:
+            return self._fail(NOT_POSDEF, "approximate posterior covariance is not positive definite", 1)
+        Ya = np.array(_arr(Y, (M, S), dt, "F"))
+        sq = ref.diag_Xt_invA_X(U, Ya - m[:, None])
+        _arr(lp_out, (S,), dt)[...] = -((M * ref.LOG2PI + ref.logdet_chol(U)) + sq) / 2.0
+        return OK
+
+    def agp_vfe_post_rand(self, p, layout, Xs, M, ns, Z, S, out):
+        self.calls.append("agp_vfe_post_rand")
+        try:
+            dt, m, U = self._vfe_factor(p, layout, Xs, M, ns)
+        except np.linalg.LinAlgError:
+            return self._fail(NOT_POSDEF, "approximate posterior covariance is not positive definite", 1)
+        Za = np.array(_arr(Z, (M, S), dt, "F"))
+        _arr(out, (M, S), dt, "F")[...] = m[:, None] + U.T @ Za
+        return OK
+
     def agp_vfe_post_free(self, p):
         self.vposts.pop(self._h(p), None)
         return OK

@@ -148,3 +148,23 @@ def sparse_update_posterior(ag, Approx):
     for a, b in zip(ag.mean_and_var(v1, xt), ag.mean_and_var(q2, xt)):
         assert approx(a, b, rtol=1e-6, atol=1e-5)
     assert isinstance(v1.approx, Approx)
+
+
+def sparse_internal_interface(ag, Approx, testutils):
+    """test/sparse_approximations.jl:12-25: the optimal approximate posterior with z = x equals the exact posterior (mean AND
+    full covariance at 100 inputs), and TestUtils.test_internal_abstractgps_interface runs on it.  `testutils` is the
+    module holding the TestUtils mirror (tests/test_gpu_posterior_finitegp.py).  Exact conditioning ON TOP of an
+    approximate posterior (`posterior(f_approx(x, s2), y)`, the last line of the primary interface) is outside the device
+    path and is skipped."""
+    rng = np.random.default_rng(123456)
+    f = ag.GP(np.sin, ag.Matern32Kernel())
+    x = np.linspace(-1.0, 1.0, 3)
+    fx = f(x, 1e-15)
+    y = ag.rand(rng, fx)
+    f_post = ag.posterior(fx, y)
+    f_approx = ag.posterior(Approx(f(x, 1e-12)), fx, y)
+    xt = rng.standard_normal(100)
+    assert approx(ag.mean(f_post, xt), ag.mean(f_approx, xt), rtol=1e-6)
+    assert approx(ag.cov(f_post, xt), ag.cov(f_approx, xt), rtol=1e-6, atol=1e-8)
+    a, b = np.linspace(-1.0, 1.0, 5), rng.standard_normal(6)
+    testutils.internal_abstractgps_interface(ag, rng, f_approx, a, b, vfe=False, conditioning=False)

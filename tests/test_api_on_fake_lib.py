@@ -133,6 +133,12 @@ def test_vfe_wrappers(fag):
     m, v = ag.mean_and_var(post(ag.RowVecs(Xs), 0.05))
     mr, vr = ref.vfe_mean_and_var(ref.vfe_posterior(ks, ref.MeanSpec(), ref.NoiseSpec(0, 0.1), X, y, Z, jit), Xs)
     assert np.allclose(m, mr) and np.allclose(v, vr + 0.05)
+    vp = ref.vfe_posterior(ks, ref.MeanSpec(), ref.NoiseSpec(0, 0.1), X, y, Z, jit)
+    Zs = rng.random((5, 2))
+    assert np.allclose(ag.cov(post, ag.RowVecs(Xs)), ref.vfe_mean_and_cov(vp, Xs)[1])
+    assert np.allclose(ag.cov(post, ag.RowVecs(Xs), ag.RowVecs(Zs)), ref.vfe_cov_cross(vp, Xs, Zs))
+    mc, Cc = ag.mean_and_cov(post(ag.RowVecs(Xs), 0.05))
+    assert np.allclose(mc, mr) and np.allclose(Cc, ref.vfe_mean_and_cov(vp, Xs)[1] + 0.05 * np.eye(7))
 
 
 @pytest.mark.parametrize("transform", ["scale", "ard"])
@@ -176,6 +182,7 @@ def test_reference_sparse_testsets(fag, approx_name):
     rs.sparse_approx_log_evidence(fag, A)
     rs.sparse_posterior_matches_exact(fag, A)
     rs.sparse_update_posterior(fag, A)
+    rs.sparse_internal_interface(fag, A, pf)
     for T in (np.float64, np.float32):
         rs.sparse_type_stability(fag, A, T)
 

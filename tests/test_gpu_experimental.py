@@ -78,5 +78,39 @@ def test_reference_sparse_testsets_on_device(ag, approx_name):
     rs.sparse_approx_log_evidence(ag, A)
     rs.sparse_posterior_matches_exact(ag, A)
     rs.sparse_update_posterior(ag, A)
+    import test_gpu_posterior_finitegp as pf
+    rs.sparse_internal_interface(ag, A, pf)
     for T in (np.float64, np.float32):
         rs.sparse_type_stability(ag, A, T)
+
+
+@pytest.mark.parametrize("dtype_name", ["float64", "float32"])
+def test_vfe_cov_logpdf_rand_match_oracle(ag, dtype_name):
+    """agp_vfe_mean_cov / agp_vfe_post_logpdf / agp_vfe_post_rand (full covariance of the approximate posterior and a
+    FiniteGP over it) against the oracle."""
+    import numpy as np
+    from oracle import agp_ref as ref
+    dtype = np.dtype(dtype_name).type
+    rng = np.random.default_rng(8)
+    n, m, d, M = 900, 140, 3, 200
+    X, Zi, Xs = rng.random((n, d)).astype(dtype), rng.random((m, d)).astype(dtype), rng.random((M, d)).astype(dtype)
+    y = (np.sin(3 * X[:, 0]) + 0.1 * rng.standard_normal(n)).astype(dtype)
+    ks = ref.KernelSpec(ref.MATERN52, 1.2, ref.T_SCALE, scale=2.0)
+    f = ag.GP(0.2, 1.2 * ag.Matern52Kernel().compose(ag.ScaleTransform(2.0)))
+    jit = 1e-6 if dtype == np.float64 else 1e-4
+    post = ag.posterior(ag.VFE(f(ag.RowVecs(Zi), jit)), f(ag.RowVecs(X), 0.1), y)
+    vp = ref.vfe_posterior(ks, ref.MeanSpec(1, 0.2), ref.NoiseSpec(0, 0.1), X, y, Zi, ref.NoiseSpec(0, jit))
+    mr, Cr = ref.vfe_mean_and_cov(vp, Xs)
+    m_, C_ = ag.mean_and_cov(post, ag.RowVecs(Xs))
+    tol = dict(rtol=1e-6, atol=1e-7) if dtype == np.float64 else dict(rtol=2e-2, atol=2e-3)
+    assert np.allclose(m_, mr, **tol) and np.allclose(C_, Cr, **tol)
+    assert np.allclose(ag.cov(post, ag.RowVecs(Xs[:50]), ag.RowVecs(Xs[50:90])), ref.vfe_cov_cross(vp, Xs[:50], Xs[50:90]), **tol)
+    Cn = Cr.astype(np.float64) + 0.05 * np.eye(M)
+    U = ref.cholesky_upper(Cn)
+    Ys = rng.standard_normal((M, 2)).astype(dtype)
+    want = -0.5 * (M * ref.LOG2PI + ref.logdet_chol(U) + ref.diag_Xt_invA_X(U, Ys.astype(np.float64) - mr[:, None]))
+    got = ag.logpdf(post(ag.RowVecs(Xs), 0.05), Ys)
+    assert np.allclose(got, want, rtol=1e-8 if dtype == np.float64 else 2e-3)
+    Zn = rng.standard_normal((M, 3)).astype(dtype)
+    got_r = ag.rand_from_normals(post(ag.RowVecs(Xs), 0.05), Zn)
+    assert np.allclose(got_r, mr[:, None] + U.T @ Zn, **(dict(rtol=0, atol=1e-7) if dtype == np.float64 else dict(rtol=0, atol=5e-3)))
