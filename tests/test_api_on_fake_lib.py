@@ -224,3 +224,93 @@ def test_smoke_entry_plumbing(fag, capsys):
     import __graft_entry__ as ge
     ge.smoke()
     assert "smoke ok" in capsys.readouterr().out
+
+
+# ---- randomized differential test of the marshalling: kernel algebra -> agp_kernel, means, noise, wrappers, dtypes
+def _random_case(rng):
+    fam = int(rng.integers(0, 5))
+    D = int(rng.integers(1, 5))
+    n = int(rng.integers(5, 40))
+    dtype = [np.float64, np.float32][int(rng.integers(0, 2))]
+    X = rng.random((n, D))
+    var = float(0.5 + rng.random())
+    c = float(rng.random())
+    tkind = int(rng.integers(0, 5))
+    scale, ard = 1.0, None
+    return dict(fam=fam, D=D, n=n, dtype=dtype, X=X, var=var, c=c, tkind=tkind, scale=scale, ard=ard)
+
+
+def _build(ag, rng, cs):
+    """build the kernel through a random but equivalent sequence of the reference's constructors; return (ag kernel, KernelSpec)"""
+    fam, D = cs["fam"], cs["D"]
+    base = {ref.SE: ag.SqExponentialKernel, ref.MATERN12: ag.Matern12Kernel, ref.MATERN32: ag.Matern32Kernel,
+            ref.MATERN52: ag.Matern52Kernel}.get(fam)
+    k = base() if base else ag.LinearKernel(c=cs["c"])
+    tk = cs["tkind"]
+    spec = dict(transform=ref.T_NONE, scale=1.0, ard=None)
+    if tk == 1:      # ScaleTransform
+        s = float(0.5 + rng.random())
+        k = k.compose(ag.ScaleTransform(s))
+        spec = dict(transform=ref.T_SCALE, scale=s, ard=None)
+    elif tk == 2:    # with_lengthscale scalar, then another ScaleTransform composed on top (applied first)
+        ell, s2 = float(0.5 + rng.random()), float(0.5 + rng.random())
+        k = ag.TransformedKernel(ag.with_lengthscale(k, ell), ag.ScaleTransform(s2))
+        spec = dict(transform=ref.T_SCALE, scale=s2 / ell, ard=None)
+    elif tk == 3:    # ARD
+        v = 0.5 + rng.random(D)
+        k = k @ ag.ARDTransform(v)
+        spec = dict(transform=ref.T_ARD, scale=1.0, ard=v)
+    elif tk == 4:    # vector lengthscale then a scalar scale
+        ell, s2 = 0.5 + rng.random(D), float(0.5 + rng.random())
+        k = ag.with_lengthscale(k, ell).compose(ag.ScaleTransform(s2))
+        spec = dict(transform=ref.T_ARD, scale=1.0, ard=s2 / ell)
+    # variance through a random split of ScaledKernel / scalar products
+    a = float(0.5 + rng.random())
+    k = ag.ScaledKernel(a * k, cs["var"] / a) if rng.random() < 0.5 else (cs["var"] / a) * (k * a)
+    ks = ref.KernelSpec(fam, cs["var"], spec["transform"], scale=spec["scale"], ard=spec["ard"], linear_c=cs["c"])
+    return k, ks
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_randomized_marshalling(fag, seed):
+    ag = fag
+    rng = np.random.default_rng(1000 + seed)
+    cs = _random_case(rng)
+    k, ks = _build(ag, rng, cs)
+    n, D, dt = cs["n"], cs["D"], cs["dtype"]
+    X = cs["X"].astype(dt)
+    mk = int(rng.integers(0, 3))
+    if mk == 0:
+        f, mean = ag.GP(k), ref.MeanSpec()
+    elif mk == 1:
+        cm = dt(rng.standard_normal())
+        f, mean = ag.GP(cm, k), ref.MeanSpec(1, float(cm))
+    else:
+        fn = (lambda r: float(np.sum(r)) ** 2) if D > 1 else (lambda r: float(r) ** 2)
+        f = ag.GP(fn, k)
+        mean = ref.MeanSpec(2, v=np.array([fn(r) for r in (X if D > 1 else X[:, 0])], dtype=dt))
+    if rng.random() < 0.5:
+        s2 = float(0.05 + rng.random())
+        noise = ref.NoiseSpec(0, s2)
+    else:
+        s2 = (0.05 + rng.random(n)).astype(dt)
+        noise = ref.NoiseSpec(1, v=s2)
+    wrap = int(rng.integers(0, 3)) if D > 1 else int(rng.integers(0, 4))
+    x = [ag.RowVecs(X), ag.ColVecs(np.ascontiguousarray(X.T)), ag.ColVecs(np.asfortranarray(X.T)), X[:, 0]][wrap]
+    fx = f(x, s2)
+    y = rng.standard_normal(n).astype(dt)
+    tol = dict(rtol=1e-10, atol=1e-12) if dt == np.float64 else dict(rtol=1e-4, atol=1e-5)
+    assert np.allclose(ag.logpdf(fx, y), ref.logpdf(ks, mean, noise, X, y), **tol)
+    assert np.allclose(ag.cov(fx), ref.mean_and_cov_fx(ks, mean, noise, X)[1], **tol)
+    assert ag.logpdf(fx, y).dtype == dt
+    p = ag.posterior(fx, y)
+    pr = ref.posterior(ks, mean, noise, X, y)
+    m = int(rng.integers(1, 9))
+    Xs = rng.random((m, D)).astype(dt)
+    xs = ag.RowVecs(Xs) if D > 1 else Xs[:, 0]
+    mean_s = None if mk != 2 else ref.MeanSpec(2, v=np.array([fn(r) for r in (Xs if D > 1 else Xs[:, 0])], dtype=dt))
+    mm, vv = ag.mean_and_var(p, xs)
+    mr, vr = ref.post_mean_and_var(pr, Xs, mean_s)
+    assert np.allclose(mm, mr, **tol) and np.allclose(vv, vr, **tol) and mm.dtype == dt
+    Z = rng.standard_normal((n, 2)).astype(dt)
+    assert np.allclose(ag.rand_from_normals(fx, Z), ref.rand_from_Z(ks, mean, noise, X, Z), **tol)
