@@ -286,8 +286,9 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
     }
   }
   const bool la = ctx->cfg.lookahead != 0 && nblk > 2 * G;
-  bool rest_pending = false;
-  size_t ev_idx = 0, last_rest = 0;
+  const bool la2 = la && ctx->cfg.lookahead >= 2;
+  bool rest_pending = false, restA_pending = false;
+  size_t ev_idx = 0, last_rest = 0, last_restA = 0;
   for (int ko = 0; ko < nblk; ko += G) {
     const int g_end = (ko + G < nblk) ? ko + G : nblk;  // inner blocks [ko, g_end)
     factor_panel<T>(ctx, L + (int64_t)ko * TILE + (int64_t)ko * TILE * lda, lda, g_end - ko, rows_total - (int64_t)ko * TILE,
@@ -304,6 +305,35 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
     if (!la) {
       if constexpr (std::is_same<T, double>::value) { if (oz) ozaki_prepare(*oz, L + t0 + kc0 * lda, lda, rows_total - t0, s); }
       trailing_update<T>(ctx, L, lda, t0, t0, kc0, K, rows_total - t0, cols_trail, s, oz, t0);
+      continue;
+    }
+    if (la2 && !oz) {
+      // EXPERIMENTAL look-ahead depth 2 (cfg.lookahead = 2 / AGP_LOOKAHEAD=2, DMMA path only -- the tcgen05 path would
+      // need a second slice buffer; not yet run on a device).  The rest update is split: restA = the panel after next,
+      // restB = everything beyond.  The next-panel update of step k+1 needs only restA(k), so the latency-bound chain
+      // (potrf -> TRSM -> next-panel update) no longer waits for the bulk of the previous rest update; restB(k) has two
+      // chain steps to finish instead of one (it is serialised behind restB(k-1) and restA(k) on the side stream).
+      cudaEvent_t e_panel = dep_event(ctx, ev_idx++), e_restA = dep_event(ctx, ev_idx++), e_restB = dep_event(ctx, ev_idx++);
+      if (restA_pending) cudaStreamWaitEvent(s, dep_event(ctx, last_restA), 0);
+      cudaEventRecord(e_panel, s);
+      const int64_t next_cols = (cols_trail < (int64_t)G * TILE) ? cols_trail : (int64_t)G * TILE;
+      trailing_update<T>(ctx, L, lda, t0, t0, kc0, K, rows_total - t0, next_cols, s, nullptr, t0);
+      restA_pending = false;
+      rest_pending = false;
+      if (cols_trail > next_cols) {
+        const int64_t r0 = t0 + next_cols;
+        const int64_t colsA = (n_pad - r0 < (int64_t)G * TILE) ? (n_pad - r0) : (int64_t)G * TILE;
+        cudaStreamWaitEvent(s2, e_panel, 0);
+        trailing_update<T>(ctx, L, lda, r0, r0, kc0, K, rows_total - r0, colsA, s2, nullptr, t0);
+        cudaEventRecord(e_restA, s2);
+        restA_pending = true;
+        last_restA = ev_idx - 2;
+        const int64_t r1 = r0 + colsA;
+        if (n_pad > r1) trailing_update<T>(ctx, L, lda, r1, r1, kc0, K, rows_total - r1, n_pad - r1, s2, nullptr, t0);
+        cudaEventRecord(e_restB, s2);
+        rest_pending = true;
+        last_rest = ev_idx - 1;
+      }
       continue;
     }
     cudaEvent_t e_panel = dep_event(ctx, ev_idx++), e_rest = dep_event(ctx, ev_idx++);

@@ -11,6 +11,18 @@ echo "== 1. baseline GPU tests (ozaki + posterior + doctests)";
 timeout 300 python -m pytest tests/test_gpu_ozaki.py tests/test_gpu_posterior_finitegp.py tests/test_gpu_reference_doctests.py -q -m gpu -x 2>&1 | tail -3 | tee gpurun_out/r02_tests_baseline.log
 echo "== 2. experimental variants: bit-identical to the validated kernel?"
 AGP_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -q -m gpu 2>&1 | tail -25 | tee gpurun_out/r02_tests_experimental.log
+echo "== 2b. look-ahead depth 2 (DMMA path): parity + C2 bench, default vs AGP_LOOKAHEAD=2"
+AGP_LOOKAHEAD=2 timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "logpdf_posterior or config_c2 or golden or multicolumn" 2>&1 | tail -3 | tee gpurun_out/r02_tests_lookahead2.log
+timeout 200 python bench.py --steps 10 --warmup 5 --no-scaling-ref 2>/dev/null | tail -1 > gpurun_out/r02_bench_c2_la1.json
+AGP_LOOKAHEAD=2 timeout 200 python bench.py --steps 10 --warmup 5 --no-scaling-ref 2>/dev/null | tail -1 > gpurun_out/r02_bench_c2_la2.json
+python - <<'PY'
+import json
+for t in ("la1", "la2"):
+    try:
+        d = json.load(open("gpurun_out/r02_bench_c2_%s.json" % t)); print(t, d["value"], d["e2e"]["value"])
+    except Exception as e:
+        print(t, "n/a", e)
+PY
 echo "== 3. probe (validated modes first, variants last)"
 PROBE_CLUSTER=1 timeout 120 python tools/ozaki_probe.py > gpurun_out/r02_probe_stdout.json 2> gpurun_out/r02_probe.err
 cp gpurun_out/ozaki_probe.json gpurun_out/r02_ozaki_probe.json 2>/dev/null
