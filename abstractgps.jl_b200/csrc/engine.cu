@@ -287,7 +287,7 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
   }
   const bool la = ctx->cfg.lookahead != 0 && nblk > 2 * G;
   const bool la2 = la && ctx->cfg.lookahead >= 2;
-  bool rest_pending = false, restA_pending = false;
+  bool rest_pending = false, restA_pending = false, last_rest_full = false;
   size_t ev_idx = 0, last_rest = 0, last_restA = 0;
   for (int ko = 0; ko < nblk; ko += G) {
     const int g_end = (ko + G < nblk) ? ko + G : nblk;  // inner blocks [ko, g_end)
@@ -315,6 +315,9 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
       // chain steps to finish instead of one (it is serialised behind restB(k-1) and restA(k) on the side stream).
       cudaEvent_t e_panel = dep_event(ctx, ev_idx++), e_restA = dep_event(ctx, ev_idx++), e_restB = dep_event(ctx, ev_idx++);
       if (restA_pending) cudaStreamWaitEvent(s, dep_event(ctx, last_restA), 0);
+      // a previous step may have used the depth-1 branch (tcgen05 panel followed by a short DMMA tail): its rest update
+      // on the side stream touches the same block column as the update below
+      if (rest_pending && last_rest_full) cudaStreamWaitEvent(s, dep_event(ctx, last_rest), 0);
       cudaEventRecord(e_panel, s);
       const int64_t next_cols = (cols_trail < (int64_t)G * TILE) ? cols_trail : (int64_t)G * TILE;
       trailing_update<T>(ctx, L, lda, t0, t0, kc0, K, rows_total - t0, next_cols, s, nullptr, t0);
@@ -332,12 +335,14 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
         if (n_pad > r1) trailing_update<T>(ctx, L, lda, r1, r1, kc0, K, rows_total - r1, n_pad - r1, s2, nullptr, t0);
         cudaEventRecord(e_restB, s2);
         rest_pending = true;
+        last_rest_full = false;  // restB never touches the next panel's columns
         last_rest = ev_idx - 1;
       }
       continue;
     }
     cudaEvent_t e_panel = dep_event(ctx, ev_idx++), e_rest = dep_event(ctx, ev_idx++);
     if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, last_rest), 0);  // also frees the slice buffer
+    if (restA_pending) { cudaStreamWaitEvent(s, dep_event(ctx, last_restA), 0); restA_pending = false; }
     if constexpr (std::is_same<T, double>::value) { if (oz) ozaki_prepare(*oz, L + t0 + kc0 * lda, lda, rows_total - t0, s); }
     cudaEventRecord(e_panel, s);
     const int64_t next_cols = (cols_trail < (int64_t)G * TILE) ? cols_trail : (int64_t)G * TILE;
@@ -349,6 +354,7 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
       trailing_update<T>(ctx, L, lda, r0, r0, kc0, K, rows_total - r0, n_pad - r0, s2, oz, t0);
       cudaEventRecord(e_rest, s2);
       rest_pending = true;
+      last_rest_full = true;
       last_rest = ev_idx - 1;
     }
   }
@@ -1118,7 +1124,8 @@ int vfe_core(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
   CK(cudaSetDevice(ctx->device));
   Scratch sc(ctx);
   const bool keep = post_out != nullptr;
-  const int64_t m_pad = round_up(M, TILE), lda = m_pad + TILE, n_padN = round_up(N, TILE);
+  // + TILE: a rank's shard start is not tile-aligned, and the chunk Gram reads whole 128-point slabs from it
+  const int64_t m_pad = round_up(M, TILE), lda = m_pad + TILE, n_padN = round_up(N, TILE) + TILE;
   const int nblk = (int)(m_pad / TILE);
   CK(cudaEventRecord(ctx->ev[0], s));
   T *ard_d = nullptr, *mean_d = nullptr, *noise_d = nullptr, *jit_d = nullptr, *yd = nullptr, *Zt = nullptr, *Xt = nullptr;
@@ -1856,6 +1863,27 @@ int32_t agp_debug_ozaki_syrk(agp_ctx* ctx, void* C_dev, int64_t ldc, const void*
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { ctx->err = std::string("ozaki syrk: ") + cudaGetErrorString(e); return AGP_ERR_CUDA; }
+  return AGP_OK;
+}
+
+// block-cyclic column map of the distributed trailing update on ONE device: P has m_panel rows; row r of C pairs with
+// panel row r + a_off, local column n with panel row (n / b_tile_width) * b_tile_stride + n % b_tile_width + b_off.
+// This drives the strip-table enumeration of the persistent kernel exactly as fit_dist_impl does.
+int32_t agp_debug_ozaki_syrk_map(agp_ctx* ctx, void* C_dev, int64_t ldc, const void* P_dev, int64_t lda, int64_t m_panel,
+                                 int64_t M, int64_t N, int32_t K, int32_t S, int64_t b_tile_stride, int64_t b_tile_width,
+                                 int64_t b_off, int64_t a_off) {
+  if (!ctx || !C_dev || !P_dev) return AGP_ERR_INVALID;
+  if (N % 128 != 0 || N < 128 || M <= 0 || m_panel <= 0) { ctx->err = "N must be a positive multiple of 128"; return AGP_ERR_INVALID; }
+  cudaSetDevice(ctx->device);
+  OzakiWs ws;
+  int rc = ozaki_ws_create(&ws, m_panel, K, S, ctx->stream);
+  if (rc) { ctx->err = "ozaki_ws_create failed (code " + std::to_string(rc) + ")"; return rc == 1 ? AGP_ERR_INVALID : AGP_ERR_CUDA; }
+  ozaki_prepare(ws, (const double*)P_dev, lda, m_panel, ctx->stream);
+  ozaki_syrk(ws, (double*)C_dev, ldc, M, N, 1, b_tile_stride, b_tile_width, b_off, a_off, ctx->stream);
+  ozaki_ws_destroy(&ws, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { ctx->err = std::string("ozaki syrk (map): ") + cudaGetErrorString(e); return AGP_ERR_CUDA; }
   return AGP_OK;
 }
 

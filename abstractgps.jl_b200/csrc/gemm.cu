@@ -296,10 +296,9 @@ template <bool AK, bool BKM, int WM, int WN>
 static void launch_dmma(const GemmArgs& g, cudaStream_t s) {
   constexpr int TBM = 64 * WM, TBN = 32 * WN;
   const size_t smem = (size_t)D_STAGES * (d_opsz(TBM) + d_opsz(TBN)) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;  // per-device bit: the attribute is per device (one ctx per GPU in one process)
+  if (agp_first_use_on_device(&configured)) {
     cudaFuncSetAttribute(gemm_dmma_kernel<AK, BKM, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
   }
   dim3 grid((unsigned)((g.M + TBM - 1) / TBM), (unsigned)((g.N + TBN - 1) / TBN));
   gemm_dmma_kernel<AK, BKM, WM, WN><<<grid, 32 * WM * WN, smem, s>>>(g);

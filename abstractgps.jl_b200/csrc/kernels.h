@@ -123,5 +123,15 @@ template <typename T> void launch_vfe_prep(const T* y, int64_t n, int mean_kind,
                                            T* delta, T* inv_sqrt_noise, double* scal /*[0]=logdet_sy [1]=sum d^2 [2]=tr*/,
                                            cudaStream_t s);
 
+// true exactly once per (call site, current device): guards cudaFuncSetAttribute, which is a per-device setting
+static inline bool agp_first_use_on_device(uint64_t* mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+
 int64_t agp_kernel_launches();
 void agp_count_launch();  // global counter (all kernels above bump it)

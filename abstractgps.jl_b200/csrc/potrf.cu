@@ -802,10 +802,9 @@ trsm_sub_f64(double* __restrict__ A21, int64_t lda, int64_t M, const double* __r
 template <typename T>
 void launch_potrf_diag(T* Ablk, int64_t lda, T* Dinv, double* logdet_part, int blk, int* info, cudaStream_t s) {
   const size_t smem = (size_t)(PB * PLD + PB * 8 + PB) * sizeof(T);
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;  // per-device bit: the attribute is per device (one ctx per GPU in one process)
+  if (agp_first_use_on_device(&configured)) {
     cudaFuncSetAttribute(potrf_diag_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
   }
   potrf_diag_kernel<T><<<1, 256, smem, s>>>(Ablk, lda, Dinv, logdet_part, blk, info);
   agp_count_launch();
@@ -815,15 +814,14 @@ template <>
 void launch_potrf_diag<double>(double* Ablk, int64_t lda, double* Dinv, double* logdet_part, int blk, int* info,
                                cudaStream_t s) {
   const size_t smem = (size_t)(PB * PLD + PB * XLD + 64 + 8 + PB) * sizeof(double);
-  static bool configured = false;
+  static uint64_t configured = 0;  // per-device bit: the attribute is per device (one ctx per GPU in one process)
   static int split = 1;
-  if (!configured) {
+  if (agp_first_use_on_device(&configured)) {
     cudaFuncSetAttribute(potrf_diag_kernel_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(potrf_factor_only_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(trtri_strips_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const char* v = getenv("AGP_POTRF_SPLIT");
     if (v) split = atoi(v);
-    configured = true;
   }
   if (split) {  // factor on one CTA (critical path), inverse on 8 CTAs
     potrf_factor_only_f64<<<1, 256, smem, s>>>(Ablk, lda, logdet_part, blk, info);
@@ -843,23 +841,23 @@ int potrf_split_enabled() {
 }
 void launch_potrf_factor_f64(double* Ablk, int64_t lda, double* logdet_part, int blk, int* info, cudaStream_t s) {
   const size_t smem = (size_t)(PB * PLD + PB * XLD + 64 + 8 + PB) * sizeof(double);
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(potrf_factor_only_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+  static uint64_t configured = 0;  // per-device bit: the attribute is per device (one ctx per GPU in one process)
+  if (agp_first_use_on_device(&configured)) { cudaFuncSetAttribute(potrf_factor_only_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
   potrf_factor_only_f64<<<1, 256, smem, s>>>(Ablk, lda, logdet_part, blk, info);
   agp_count_launch();
 }
 void launch_trtri_f64(const double* Ablk, int64_t lda, double* Dinv, cudaStream_t s) {
   const size_t smem = (size_t)(PB * PLD + PB * XLD + 64 + 8 + PB) * sizeof(double);
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(trtri_strips_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+  static uint64_t configured = 0;  // per-device bit: the attribute is per device (one ctx per GPU in one process)
+  if (agp_first_use_on_device(&configured)) { cudaFuncSetAttribute(trtri_strips_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
   trtri_strips_f64<<<8, 256, smem, s>>>(Ablk, lda, Dinv);
   agp_count_launch();
 }
 void launch_trsm_sub_f64(double* A21, int64_t lda, int64_t M, const double* Lkk, cudaStream_t s) {
   if (M <= 0) return;
   const size_t smem = (size_t)(PB * PLD + PB * TS_XP + TS_R * XLD + 16 * 64 + PB) * sizeof(double);
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(trsm_sub_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+  static uint64_t configured = 0;  // per-device bit: the attribute is per device (one ctx per GPU in one process)
+  if (agp_first_use_on_device(&configured)) { cudaFuncSetAttribute(trsm_sub_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
   trsm_sub_f64<<<(unsigned)((M + TS_R - 1) / TS_R), 256, smem, s>>>(A21, lda, M, Lkk);
   agp_count_launch();
 }

@@ -440,10 +440,9 @@ void launch_extract_v(const T* A, int64_t lda, int64_t n_pad, int S, T* r, doubl
 template <typename T>
 void launch_bwd_solve(const T* A, int64_t lda, const T* Dinv, int nblk, T* r, int* flags_and_ticket, cudaStream_t s) {
   const size_t smem = (size_t)TB * TB * sizeof(T);
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;  // per-device bit: the attribute is per device (one ctx per GPU in one process)
+  if (agp_first_use_on_device(&configured)) {
     cudaFuncSetAttribute(bwd_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
   }
   cudaMemsetAsync(flags_and_ticket, 0, (size_t)(nblk + 1) * sizeof(int), s);
   bwd_solve_kernel<T><<<nblk, 256, smem, s>>>(A, lda, Dinv, nblk, r, flags_and_ticket, flags_and_ticket + nblk);

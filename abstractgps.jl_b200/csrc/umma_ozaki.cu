@@ -479,6 +479,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v2_kernel(c
           const int st = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[st], ph ^ 1);
+          if (a.epi == 5) { mbar_arrive(&full_bar[st]); continue; }  // PROBE 5: MMA-only loop, no operand traffic
           mbar_expect_tx(&full_bar[st], STAGE_BYTES);
           if (a.SLb) {  // contiguous 4 KB / 2 KB chunks already in the UMMA smem layout: 1-D bulk copies
             const int64_t nrb = a.m_alloc >> 7, nkb = a.K >> 5;
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v2_kernel(c
           tc_fence_after();
           const uint32_t a0 = smem_u32(a_tile(st, 0)), b0 = smem_u32(b_tile(st, 0));
 #pragma unroll 1
-          for (int sl = 0; sl < S; ++sl) {
+          for (int sl = (a.epi == 6 ? S : 0); sl < S; ++sl) {  // PROBE 6: operand traffic only, no MMAs
             const int Ns = (S - sl) * OZ_BN;
             const uint64_t adesc = a.SLb ? umma_desc_nosw(a0 + sl * A_BYTES) : umma_desc_sw32(a0 + sl * A_BYTES);
             for (int c = 0; c < Ns; c += 256) {
@@ -563,7 +564,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v2_kernel(c
       //     trip (all S loads of a trip in flight before one wait), then hand the accumulators back to the MMA
       //     warp -- the C read-modify-write below overlaps the next tile's MMAs.
       double v[CB];
-      if (a.epi >= 3) {  // PROBE: no drain at all (3) -- results are garbage, timing only
+      if (a.epi >= 3 && a.epi != 7) {  // PROBE: no drain at all (3, 4, 5, 6) -- results are garbage, timing only
 #pragma unroll
         for (int i = 0; i < CB; ++i) v[i] = 0.0;
       } else {
@@ -574,7 +575,15 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v2_kernel(c
         for (int d = 0; d < S; ++d)
           tmem_ld8_nowait(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(d * OZ_BN + c0 + c8), r[d]);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (a.epi == 1) {
+        if (a.epi == 7) {  // PROBE 7: TMEM reads only, one int op per value, one conversion per element
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint32_t x = r[0][i];
+#pragma unroll
+            for (int d = 1; d < S; ++d) x ^= r[d][i];
+            v[c8 + i] = __hiloint2double(0x43300000, (int)x);
+          }
+        } else if (a.epi == 1) {
           // adjacent diagonals combined exactly in int32 first: |ACC_d| <= (d+1) * K * 64 * 64, so for K <= 512
           // t_j = 128 * ACC_2j + ACC_2j+1 stays below 2^31 up to S = 8.  4 int->fp64 conversions and 4 fp64 ops
           // per element instead of 7 and 6 (S = 7): the drain is bound by the fp64 pipe, not by tcgen05.ld.
@@ -610,7 +619,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v2_kernel(c
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar);
       // (2) C -= scale_i * scale_j * v, streamed (.cs) so the int8 slices stay resident in L2
-      if (row_ok && a.epi != 2 && a.epi != 3) {  // PROBE 2/3: no C read-modify-write
+      if (row_ok && a.epi != 2 && a.epi != 3 && a.epi != 5 && a.epi != 6) {  // PROBE 2/3/5/6: no C read-modify-write
 #pragma unroll
         for (int c = 0; c < CB; c += 16) {
           double cv[16];
@@ -689,14 +698,13 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
   constexpr int STAGE_BYTES = S * (OZ_BM * V2_KB + OZ_BN * V2_KB);
   constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
-  static bool configured = false;
+  static uint64_t configured = 0;  // per-device bit: the attribute is per device (one ctx per GPU in one process)
   static int nsm = 148;
-  if (!configured) {
+  if (agp_first_use_on_device(&configured)) {
     cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S, 1, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
   }
   // EXPERIMENTAL switches (the variants compile, none has run on a device yet; the default <S, 1, 4, 0> kernel is the
   // validated one): AGP_OZAKI_CLUSTER=2 -> A-multicast CTA pairs, AGP_OZAKI_EPIWARPS=8 -> two epilogue warps per quarter,
@@ -803,10 +811,9 @@ void launch_syrk_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t
     return;
   }
   const size_t smem = (size_t)OZ_STAGES * S * (OZ_BM * OZ_KB + OZ_BN * OZ_KB) + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;  // per-device bit: the attribute is per device (one ctx per GPU in one process)
+  if (agp_first_use_on_device(&configured)) {
     cudaFuncSetAttribute(umma_ozaki_syrk_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
   }
   OzTileArgs a{};
   a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.m_alloc = ws.m_alloc; a.K = ws.K; a.rscale = ws.rscale;

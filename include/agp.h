@@ -208,6 +208,13 @@ int32_t agp_vfe_post_free(agp_vfe_post* p);
 int32_t agp_debug_ozaki_syrk(agp_ctx* ctx, void* C_dev, int64_t ldc, const void* P_dev, int64_t lda, int64_t M,
                              int64_t N, int32_t K, int32_t S, int32_t lower_only);
 
+/* same kernel through the block-cyclic column map of the multi-GPU trailing update (the strip-table tile enumeration):
+ * P has m_panel rows; row r of C (M x N local columns, N % 128 == 0) pairs with panel row r + a_off, local column n with
+ * panel row (n / b_tile_width) * b_tile_stride + n % b_tile_width + b_off; lower tiles only (relative to panel rows). */
+int32_t agp_debug_ozaki_syrk_map(agp_ctx* ctx, void* C_dev, int64_t ldc, const void* P_dev, int64_t lda, int64_t m_panel,
+                                 int64_t M, int64_t N, int32_t K, int32_t S, int64_t b_tile_stride, int64_t b_tile_width,
+                                 int64_t b_off, int64_t a_off);
+
 /* ---- host-only helpers of the 2D block-cyclic tile map (no GPU needed; used by the CPU
  * world_size-2 tests): owner rank of tile (i,j) on a P x Q grid and local tile counts. */
 int32_t agp_bc_owner(int32_t ti, int32_t tj, int32_t grid_p, int32_t grid_q);

@@ -209,3 +209,34 @@ def test_logpdf_grad_matches_finite_differences(fam, transform):
     h = 1e-6
     want = (ref.logpdf(k, mean, ref.NoiseSpec(0, 0.1 + h), X, y) - ref.logpdf(k, mean, ref.NoiseSpec(0, 0.1 - h), X, y)) / (2 * h)
     chk(gs["noise"], want)
+
+
+# ---- the two distance formulations: "direct" (differences; the CUDA kernel and the parity oracle) vs "gemm"
+# (||a||^2 + ||b||^2 - 2 a.b clamped at 0: the Distances.jl pairwise form KernelFunctions.kernelmatrix executes in the
+# reference, call sites src/base_gp.jl:70,74).  The GPU Gram is compared with "direct"; this bounds what that choice can
+# hide: the two agree to cancellation error of the gemm form, and the downstream logpdf agrees far inside rtol 1e-8.
+@pytest.mark.parametrize("fam", [ref.SE, ref.MATERN12, ref.MATERN32, ref.MATERN52])
+@pytest.mark.parametrize("d", [1, 8, 64])
+def test_gemm_and_direct_distance_forms_agree(fam, d):
+    rng = np.random.default_rng(d * 10 + fam)
+    n = 400
+    X = rng.random((n, d))
+    k = ref.KernelSpec(fam, 1.3, ref.T_SCALE, scale=1.0 / (0.5 * np.sqrt(d)))
+    Kd = ref.kernelmatrix(k, X, method="direct")
+    Kg = ref.kernelmatrix(k, X, method="gemm")
+    # d^2 error of the gemm form ~ eps * (||a||^2 + ||b||^2) <= eps * 8; kappa is 1-Lipschitz in d^2 for SE and
+    # ~ sqrt-amplified near d = 0 for the Matern family (|d kappa| <= c |d(d)|, d(d) <= sqrt(d(d^2)))
+    eps = np.finfo(np.float64).eps
+    tol = 1.3 * (8 * 8 * eps if fam == ref.SE else 3.0 * np.sqrt(8 * 8 * eps))
+    assert np.max(np.abs(Kd - Kg)) <= tol
+    assert np.array_equal(np.diag(Kd), np.diag(Kg))  # exactly-zero self distance in both
+    y = np.sin(3 * X[:, 0]) + 0.1 * rng.standard_normal(n)
+    old = ref.DEFAULT_METHOD
+    try:
+        ref.DEFAULT_METHOD = "direct"
+        lp_d = ref.logpdf(k, ref.MeanSpec(), ref.NoiseSpec(0, 0.1), X, y)
+        ref.DEFAULT_METHOD = "gemm"
+        lp_g = ref.logpdf(k, ref.MeanSpec(), ref.NoiseSpec(0, 0.1), X, y)
+    finally:
+        ref.DEFAULT_METHOD = old
+    assert abs(lp_d - lp_g) <= (1e-10 if fam == ref.SE else 2e-8) * abs(lp_d), (lp_d, lp_g)

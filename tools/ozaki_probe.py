@@ -125,7 +125,7 @@ out["partA"]["modes"]["0"] = {"ms": t_full, "syrk_ms": t_full - fixed,
 flops = 2.0 * K * (M * (M + 1) / 2)
 out["partA"]["modes"]["0"]["fp64_equiv_tflops"] = flops / ((t_full - fixed) * 1e-3) / 1e12
 save()
-for mode in (1, 3, 2, 4):
+for mode in (1, 3, 2, 4, 7, 5, 6):  # 5: MMA-only main loop, 6: operand traffic only, 7: TMEM reads without conversions
     t = syrk(mode, M)
     d = {"ms": t, "syrk_ms": t - fixed}
     if mode == 1:
