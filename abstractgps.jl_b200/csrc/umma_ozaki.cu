@@ -73,7 +73,9 @@ __global__ void ozaki_slice_kernel(const double* __restrict__ P, int64_t lda, in
       // k-block) = 4096 contiguous bytes = [16 row-groups][2 k-halves][8 rows][16 B]  (SBO 256 B, LBO 128 B)
       const int64_t rb = row >> 7, g = (row & 127) >> 3, r8 = row & 7;
       const int kb = k0 >> 5, h = (k0 >> 4) & 1;
-      const int64_t chunk = ((int64_t)s * (m_alloc >> 7) + rb) * (K >> 5) + kb;
+      // bulk 1: [slice][row block][k block]; bulk 2 (v3 kernel): [row block][k block][slice] -- the S chunks one
+      // (128-row tile, k block) needs are ONE contiguous S*4096-byte run
+      const int64_t chunk = (bulk == 2) ? (rb * (K >> 5) + kb) * S + s : ((int64_t)s * (m_alloc >> 7) + rb) * (K >> 5) + kb;
       *reinterpret_cast<uint4*>(SL + chunk * 4096 + ((g * 2 + h) * 8 + r8) * 16) = pk.v;
     } else {
       *reinterpret_cast<uint4*>(SL + ((int64_t)s * m_alloc + row) * K + k0) = pk.v;
@@ -647,6 +649,234 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v2_kernel(c
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// v3: same algorithm and tile walk as v2, restructured after the round-2 probe (profiles/r02_call1_*): the v2 main loop
+// ran at the SAME speed with its operand traffic switched off -- it was bound by the single issuing thread (~38 SASS
+// instructions with 7 R2UR.BROADCAST + an ELECT loop per tcgen05.mma because the issue sat in a divergent `lane == 0`
+// region), and so was the producer (14 bulk copies per K chunk, each behind its own address arithmetic).  Here
+//  * producer and MMA warps run warp-uniform loops and elect one lane only around the instruction itself, so
+//    descriptors / addresses live in uniform registers; the S x (S+3)/... MMA sequence is fully unrolled with
+//    compile-time instruction descriptors and descriptors formed by ONE add on a per-stage base;
+//  * the slices are stored [row block][k block][slice]: the S A-chunks of a stage are one 28 KB bulk copy
+//    (CL = 2: two multicast halves), the B chunks S copies of 2 KB -- 8 copies per stage instead of 14;
+//  * the drain combines the S int32 accumulators exactly in int64 (two words: 4 + (S-4) terms), converts them with the
+//    2^52 magic-number add instead of I2F.F64 and rounds ONCE (fma) -- 5 fp64-pipe operations per element, was 10.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ double i64_to_f64_exact(long long x) {  // |x| < 2^51: exact, one integer add + one DADD
+  return __longlong_as_double(x + 0x4338000000000000LL) - 6755399441055744.0;
+}
+// exact value of sum_d acc_d 128^(3-d) as two int64 words (hi: d = 0..3, lo: d = 4..S-1, scaled by 128^(S-4)), then ONE
+// rounding.  PAIR32: adjacent accumulators are first combined in int32 (valid for K <= 512, see v2).
+template <int S, bool PAIR32>
+__device__ __forceinline__ double oz_combine(const uint32_t (&r)[S][8], int i) {
+  long long h, l;
+  if constexpr (PAIR32) {
+    const int t01 = (int)r[0][i] * 128 + (int)r[1][i], t23 = (int)r[2][i] * 128 + (int)r[3][i];
+    h = (long long)t01 * 16384 + t23;
+    if constexpr (S == 5) l = (int)r[4][i];
+    else if constexpr (S == 6) l = (int)r[4][i] * 128 + (int)r[5][i];
+    else if constexpr (S == 7) l = (long long)((int)r[4][i] * 128 + (int)r[5][i]) * 128 + (int)r[6][i];
+    else l = (long long)((int)r[4][i] * 128 + (int)r[5][i]) * 16384 + ((int)r[6][i] * 128 + (int)r[7][i]);
+  } else {
+    h = (((long long)(int)r[0][i] * 128 + (int)r[1][i]) * 128 + (int)r[2][i]) * 128 + (int)r[3][i];
+    l = (int)r[4][i];
+#pragma unroll
+    for (int d = 5; d < S; ++d) l = l * 128 + (int)r[d][i];
+  }
+  constexpr double LO_SCALE = (S == 5) ? 1.0 / 128.0 : (S == 6) ? 1.0 / 16384.0 : (S == 7) ? 1.0 / 2097152.0 : 1.0 / 268435456.0;
+  return fma(i64_to_f64_exact(l), LO_SCALE, i64_to_f64_exact(h));
+}
+
+template <int S, int CL, int NEPI, int GE>
+__global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v3_kernel(OzTileArgs a, int64_t ntiles, int nbi, int nbj) {
+  constexpr int A_BYTES = OZ_BM * V2_KB, B_BYTES = OZ_BN * V2_KB;
+  constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
+  constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
+    mbar_init(&tmem_full_bar, 1);
+    mbar_init(&tmem_empty_bar, NEPI);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if constexpr (CL > 1) cluster_sync_all();
+  const uint32_t tmem_base = tmem_base_s;
+  const int num_kb = a.K / V2_KB;
+  constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1);
+
+  if (warp == 0) {
+    // ---- producer: all 32 lanes walk the loop (uniform control flow), one elected lane issues the copies
+    uint32_t it = 0;
+    const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+    const int64_t rb_bytes = (int64_t)num_kb * S * 4096;  // bytes of one 128-row block (all k blocks, all slices)
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int bi, bj;
+      int64_t brow64;
+      if (!v2_decode<GE>(a, t, nbi, nbj, bi, bj, brow64)) continue;
+      const int64_t arow = (int64_t)bi * OZ_BM + a.a_off;
+      const int8_t* asrc = a.SLb + (arow >> 7) * rb_bytes;
+      const int8_t* bsrc = a.SLb + (brow64 >> 7) * rb_bytes + (brow64 & 64) * 32;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        if (a.epi == 5) {  // PROBE 5: MMA-only loop, no operand traffic
+          if (elect_one()) mbar_arrive(&full_bar[st]);
+        } else if (elect_one()) {
+          uint8_t* dst = base + st * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+          if constexpr (CL > 1) {  // each CTA fetches 1/CL of the contiguous A run and multicasts it to the cluster
+            constexpr int PART = S * A_BYTES / CL;
+            bulk_load_mc(dst + crank * PART, asrc + crank * PART, PART, &full_bar[st], CL_MASK);
+          } else {
+            bulk_load(dst, asrc, S * A_BYTES, &full_bar[st]);
+          }
+#pragma unroll
+          for (int sl = 0; sl < S; ++sl) bulk_load(dst + S * A_BYTES + sl * B_BYTES, bsrc + sl * 4096, B_BYTES, &full_bar[st]);
+        }
+        __syncwarp();
+        asrc += S * 4096;
+        bsrc += S * 4096;
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: uniform loop, descriptors = per-stage base + compile-time offsets
+    constexpr uint32_t IDESC_BASE = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+    constexpr uint64_t DESC_HI = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);  // LBO, SBO, version
+    const uint32_t stage0_lo = (smem_u32(base) & 0x3FFFF) >> 4;
+    uint32_t it = 0, lt = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      {
+        int bi_, bj_;
+        int64_t br_;
+        if (!v2_decode<GE>(a, t, nbi, nbj, bi_, bj_, br_)) continue;
+      }
+      mbar_wait(&tmem_empty_bar, (lt & 1) ^ 1);  // epilogue has drained the previous tile's accumulators
+      tc_fence_after();
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const uint32_t st = it % STAGES, ph = (it / STAGES) & 1;
+        mbar_wait(&full_bar[st], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_lo = stage0_lo + st * (uint32_t)(STAGE_BYTES >> 4);
+          const uint32_t b_lo = a_lo + (uint32_t)((S * A_BYTES) >> 4);
+          const uint32_t acc0 = (kb != 0) ? 1u : 0u;
+          if (a.epi != 6) {  // PROBE 6: operand traffic only
+#pragma unroll
+            for (int sl = 0; sl < S; ++sl) {
+#pragma unroll
+              for (int c = 0; c < (S - sl) * OZ_BN; c += 256) {
+                const int nchunk = ((S - sl) * OZ_BN - c < 256) ? ((S - sl) * OZ_BN - c) : 256;
+                umma_i8(tmem_base + (uint32_t)(sl * OZ_BN + c), DESC_HI | (uint64_t)(a_lo + (uint32_t)(sl * (A_BYTES >> 4))),
+                        DESC_HI | (uint64_t)(b_lo + (uint32_t)((c * V2_KB) >> 4)), IDESC_BASE | ((uint32_t)(nchunk >> 3) << 17),
+                        (sl == 0) ? acc0 : 1u);
+              }
+            }
+          }
+          if constexpr (CL > 1) umma_commit_mc(&empty_bar[st], CL_MASK);
+          else umma_commit(&empty_bar[st]);
+          if (kb == num_kb - 1) umma_commit(&tmem_full_bar);
+        }
+        __syncwarp();
+      }
+      ++lt;
+    }
+  } else {
+    const int quarter = warp & 3;
+    constexpr int CB = OZ_BN * 4 / NEPI;                          // columns drained by one epilogue warp
+    const int c0 = (NEPI == 4) ? 0 : ((warp - 2) >> 2) * CB;      // warps 2-5: columns [0, CB), warps 6-9: [CB, 2 CB)
+    const bool pair32 = (a.epi == 1);
+    uint32_t lt = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int bi, bj;
+      int64_t brow64;
+      if (!v2_decode<GE>(a, t, nbi, nbj, bi, bj, brow64)) continue;
+      const int64_t m0 = (int64_t)bi * OZ_BM, n0 = (int64_t)bj * OZ_BN + c0;
+      brow64 += c0;
+      const int64_t row = m0 + 32 * quarter + lane;
+      const bool row_ok = row < a.M;
+      const double rs = row_ok ? a.rscale[row + a.a_off] * (1.0 / 8589934592.0) : 0.0;  // 2^e_i * 2^-12 * 128^-3
+      double* crow = a.C + row;
+      mbar_wait(&tmem_full_bar, lt & 1);
+      tc_fence_after();
+      double v[CB];
+      if (a.epi >= 3 && a.epi != 7) {  // PROBE: no drain (3, 4, 5, 6) -- results are garbage, timing only
+#pragma unroll
+        for (int i = 0; i < CB; ++i) v[i] = 0.0;
+      } else {
+#pragma unroll
+        for (int c8 = 0; c8 < CB; c8 += 8) {
+          uint32_t r[S][8];
+#pragma unroll
+          for (int d = 0; d < S; ++d)
+            tmem_ld8_nowait(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(d * OZ_BN + c0 + c8), r[d]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (a.epi == 7) {  // PROBE 7: TMEM reads only
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint32_t x = r[0][i];
+#pragma unroll
+              for (int d = 1; d < S; ++d) x ^= r[d][i];
+              v[c8 + i] = __hiloint2double(0x43300000, (int)x);
+            }
+          } else if (pair32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[c8 + i] = oz_combine<S, true>(r, i);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[c8 + i] = oz_combine<S, false>(r, i);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar);
+      // C -= (2^e_i 2^e_j 2^-33) * v, streamed (.cs) so the int8 slices stay resident in L2
+      if (row_ok && a.epi != 2 && a.epi != 3 && a.epi != 5 && a.epi != 6) {
+#pragma unroll
+        for (int c = 0; c < CB; c += 16) {
+          double cv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int64_t col = n0 + c + i;
+            cv[i] = (col < a.N) ? ld_cs(crow + col * a.ldc) : 0.0;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int64_t col = n0 + c + i;
+            if (col < a.N) st_cs(crow + col * a.ldc, fma(-v[c + i], rs * a.rscale[brow64 + c + i], cv[i]));
+          }
+        }
+      }
+      ++lt;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -692,6 +922,39 @@ void launch_v2_variant(const OzakiWs& ws, const OzTileArgs& a, int64_t ntiles, i
   cudaLaunchKernelEx(&lc, umma_ozaki_syrk_v2_kernel<S, CL, NEPI, GE>, ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
 }
 
+
+template <int S, int CL, int NEPI, int GE>
+void launch_v3_variant(const OzTileArgs& a, int64_t ntiles, int nbi, int nbj, int cap, size_t smem, cudaStream_t s) {
+  static int max_clusters[64] = {0};  // per device; 0 = not queried yet
+  static uint64_t configured = 0;
+  constexpr unsigned THREADS = 64 + 32 * NEPI;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaLaunchConfig_t lc{};
+  lc.blockDim = dim3(THREADS); lc.dynamicSmemBytes = smem; lc.stream = s;
+  cudaLaunchAttribute la[1];
+  la[0].id = cudaLaunchAttributeClusterDimension;
+  la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+  lc.attrs = la; lc.numAttrs = 1;
+  if (agp_first_use_on_device(&configured)) {
+    cudaFuncSetAttribute(umma_ozaki_syrk_v3_kernel<S, CL, NEPI, GE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int mc = 0;
+    if (CL > 1) {
+      lc.gridDim = dim3((unsigned)(cap / CL * CL));
+      if (cudaOccupancyMaxActiveClusters(&mc, umma_ozaki_syrk_v3_kernel<S, CL, NEPI, GE>, &lc) != cudaSuccess) { mc = 0; cudaGetLastError(); }
+    } else {
+      mc = 1 << 20;
+    }
+    max_clusters[dev & 63] = mc;
+  }
+  int64_t grid = (int64_t)max_clusters[dev & 63] * CL;
+  if (grid > cap) grid = cap / CL * CL;
+  if (grid > ntiles) grid = ntiles / CL * CL;  // the slot count is even when CL = 2 is selected
+  if (grid <= 0) return;
+  lc.gridDim = dim3((unsigned)grid);
+  cudaLaunchKernelEx(&lc, umma_ozaki_syrk_v3_kernel<S, CL, NEPI, GE>, a, ntiles, nbi, nbj);
+}
+
 template <int S>
 void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int64_t b_tile_stride,
                       int64_t b_tile_width, int64_t b_off, int64_t a_off, cudaStream_t s) {
@@ -728,7 +991,7 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
     // AGP_OZAKI_EPI=0 restores the plain Horner drain, >= 2 are the timing-only variants of tools/ozaki_probe.py.
     const char* e = getenv("AGP_OZAKI_EPI");
     a.epi = e ? atoi(e) : 1;
-    if (a.epi == 1 && (ws.K > 512 || S != 7)) a.epi = 0;  // the int32 pair bound needs K <= 512
+    if (a.epi == 1 && (ws.K > 512 || (S != 7 && ws.bulk != 2))) a.epi = 0;  // the int32 pair bound needs K <= 512 (v2: validated for S = 7 only)
   }
   const int nbi = (int)((M + OZ_BM - 1) / OZ_BM), nbj = (int)(N / OZ_BN);
   int64_t ntiles = 0;
@@ -784,6 +1047,21 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
   if (ntiles <= 0) return;
   const int cap = (ws.max_ctas > 0 && ws.max_ctas < nsm) ? ws.max_ctas : nsm;
   const bool ge = want_ge && a.strip_start;
+  if (ws.bulk == 2) {  // v3 kernel (default): 8 epilogue warps unless AGP_OZAKI_EPIWARPS=4; CTA pairs with AGP_OZAKI_CLUSTER=2
+    const char* f = getenv("AGP_OZAKI_EPIWARPS");
+    const int ew = (f && atoi(f) == 4) ? 4 : 8;
+    const bool cl2 = want_cl == 2 && (!a.strip_start || ge) && ntiles >= 2;
+    if (ge && cl2 && ew == 8) launch_v3_variant<S, 2, 8, 1>(a, ntiles, nbi, nbj, cap, smem, s);
+    else if (ge && cl2) launch_v3_variant<S, 2, 4, 1>(a, ntiles, nbi, nbj, cap, smem, s);
+    else if (ge && ew == 8) launch_v3_variant<S, 1, 8, 1>(a, ntiles, nbi, nbj, cap, smem, s);
+    else if (ge) launch_v3_variant<S, 1, 4, 1>(a, ntiles, nbi, nbj, cap, smem, s);
+    else if (cl2 && ew == 8) launch_v3_variant<S, 2, 8, 0>(a, ntiles, nbi, nbj, cap, smem, s);
+    else if (cl2) launch_v3_variant<S, 2, 4, 0>(a, ntiles, nbi, nbj, cap, smem, s);
+    else if (ew == 8) launch_v3_variant<S, 1, 8, 0>(a, ntiles, nbi, nbj, cap, smem, s);
+    else launch_v3_variant<S, 1, 4, 0>(a, ntiles, nbi, nbj, cap, smem, s);
+    agp_count_launch();
+    return;
+  }
   if (want_cl == 2 || want_ew == 8 || ge) {
     // CTA pairs need slots 2u, 2u + 1 on the same row tile: the closed-form order and the grouped table order give that
     const bool cl2 = want_cl == 2 && a.SLb && (!a.strip_start || ge) && ntiles >= 2;
@@ -856,6 +1134,8 @@ int ozaki_ws_create(OzakiWs* ws, int64_t max_rows, int K, int S, cudaStream_t s)
   ws->use_v2 = v ? atoi(v) : 1;
   const char* b = getenv("AGP_OZAKI_BULK");
   ws->bulk = (ws->use_v2 && (b ? atoi(b) : 1)) ? 1 : 0;
+  const char* kv = getenv("AGP_OZAKI_KERNEL");  // 3 (default): v3 kernel + [row block][k block][slice] layout; 2: the round-1 kernel
+  if (ws->bulk == 1 && !(kv && atoi(kv) == 2)) ws->bulk = 2;
   return 0;
 }
 

@@ -1,14 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the exact-GP hot path (BASELINE.json metric):
-ms to logpdf(fx,y) + posterior(fx,y) at N x D fp64, with the achieved fraction of the N^3/3 Cholesky
-roofline, next to the reference's CPU LAPACK path timed on the same box.
+ms to logpdf(fx,y) + posterior(fx,y) at N x D fp64, with the achieved fraction of the tensor roofline of the
+trailing update and of the N^3/3 Cholesky rate, next to the reference's CPU LAPACK path timed on the same box.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C4|...] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4|C2|C4h|C3|C5] [--impl ours|reference] [--n N]
 
-One "step" = one fused fit (ONE Gram + ONE Cholesky -> logpdf, alpha, posterior handle) of the named
-workload through the C ABI of libagp.so.  `value` is measured with the inputs resident in HBM
-(device-pointer mode of the ABI); `e2e` is the same call with pinned HOST buffers, H2D/D2H inside the
-timed region.  Device times come from CUDA events recorded by the library on its launching stream.
+The SAME workload (C4: N = 65 536, D = 64, SqExponential, fp64 -- the configuration BASELINE.json's metric and target are
+quoted on; it fits one B200) runs at every --gpus value, so the per-N values form a strong-scaling curve.  At N = 1 the
+line also carries C2 (N = 4096, D = 8) as the secondary key "c2".
+
+One "step" = one pass of the hot path through the C ABI of libagp.so:
+  fit workloads (C2, C4, C4h): ONE fused fit (Gram + Cholesky -> logpdf, alpha, posterior factor);
+  C3: fit (fp32, Matern32 o ARD) + mean_and_var at 10 000 test points;   C5: VFE elbo (streamed over N).
+`value` is measured with the inputs resident in HBM (device-pointer mode of the ABI); `e2e` is the same call with pinned
+HOST buffers, H2D/D2H inside the timed region.  Device times come from CUDA events recorded by the library on its
+launching stream, max over ranks.  The oracle (oracle/agp_ref.py) is used here only as the CPU baseline and as the
+out-of-timed-region parity checker.
 """
 from __future__ import annotations
 
@@ -26,17 +33,31 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {  # BASELINE.json configs
-    "C2": dict(N=4096, D=8, dtype="f64", kernel="SqExponential", s2=0.1),
-    "C4": dict(N=65536, D=64, dtype="f64", kernel="SqExponential", s2=0.1),
-    "C4h": dict(N=32768, D=64, dtype="f64", kernel="SqExponential", s2=0.1),
+    "C2": dict(kind="fit", N=4096, D=8, dtype="f64", kernel="SqExponential", s2=0.1, cfg="C2"),
+    "C4": dict(kind="fit", N=65536, D=64, dtype="f64", kernel="SqExponential", s2=0.1, cfg="C4"),
+    "C4h": dict(kind="fit", N=32768, D=64, dtype="f64", kernel="SqExponential", s2=0.1, cfg="C4"),
+    "C3": dict(kind="fit_predict", N=16384, D=32, M=10000, dtype="f32", kernel="Matern32 o ARDTransform", s2=0.05, cfg="C3"),
+    "C5": dict(kind="vfe", N=1000000, D=16, M=8192, dtype="f32", kernel="SqExponential", s2=0.1, cfg="C5"),
 }
+METRIC = {"fit": "ms to logpdf(fx,y)+posterior(fx,y)", "fit_predict": "ms to logpdf+posterior+mean_and_var(10000 test points)",
+          "vfe": "ms to elbo(VFE(f(z)), fx, y)"}
+CPU_SUB = 8192  # bounded CPU sample for the cubic workloads (scaled by (N/8192)^3, labelled extrapolated)
 
 
-def make_inputs(wl):
+def make_inputs(wl, n=None):
     from oracle import agp_ref as ref  # synthetic-input generator only (shared with the parity tests)
-    cid = "C4" if wl.startswith("C4") else wl
-    cfg = ref.make_config(cid, n=WORKLOADS[wl]["N"])
-    return cfg
+    W = WORKLOADS[wl]
+    return ref.make_config(W["cfg"], n=n or W["N"])
+
+
+def wl_string(wl, N, extra=""):
+    W = WORKLOADS[wl]
+    s = "%s: N=%d D=%d %s %s, sigma2=%g" % (wl, N, W["D"], W["kernel"], "fp64" if W["dtype"] == "f64" else "fp32", W["s2"])
+    if W["kind"] == "fit_predict":
+        s += ", M=%d test points" % W["M"]
+    if W["kind"] == "vfe":
+        s += ", M=%d inducing points" % min(W["M"], max(8, N // 8))
+    return s + extra
 
 
 class ClockSampler:
@@ -73,6 +94,7 @@ class ClockSampler:
             self.p.kill()
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
         reasons = set()
         for r in self.rows:
             if len(r) < 9:
@@ -81,32 +103,63 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def trailing_flops(N):
-    """algorithmic flops of the trailing SYRK launches of one factorisation: step k applies a symmetric
-    rank-128 update to the m x m trailing matrix (lower part): 2*128*m(m+1)/2, m = n_pad - 128(k+1)."""
+def trailing_flops(N, nb=128):
+    """algorithmic flops of the outer trailing updates of one factorisation with nb-wide panels: step k applies a
+    symmetric rank-K update to the m x m trailing matrix (lower part): 2*K*m(m+1)/2."""
     n_pad = (N + 127) // 128 * 128
-    tot = 0.0
-    for k in range(n_pad // 128):
-        m = n_pad - 128 * (k + 1)
-        tot += 2.0 * 128 * m * (m + 1) / 2
+    tot, t0 = 0.0, 0
+    while t0 < n_pad:
+        K = min(nb, n_pad - t0)
+        t0 += K
+        m = n_pad - t0
+        tot += 2.0 * K * m * (m + 1) / 2
     return tot
 
 
-def cpu_reference_step(cfg, faithful=True):
-    """The reference's own CPU algorithm (oracle port): logpdf then posterior -- TWO Gram builds and TWO
-    LAPACK potrf's as /root/reference/src/finite_gp_projection.jl:307-308 + src/exact_gpr_posterior.jl:30-31 do."""
+# ------------------------------------------------------------------------------------------------------------
+# CPU side: the reference's own algorithm (oracle port) on the box's host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_step(wl, cfg):
+    """One step of the reference's CPU algorithm for the workload (oracle port).  fit: logpdf THEN posterior -- TWO Gram
+    builds and TWO LAPACK potrf's, as /root/reference/src/finite_gp_projection.jl:307-308 + src/exact_gpr_posterior.jl:30-31
+    do; the Distances.jl (gemm) pairwise formulation the reference executes."""
     from oracle import agp_ref as ref
+    kind = WORKLOADS[wl]["kind"]
     old = ref.DEFAULT_METHOD
-    ref.DEFAULT_METHOD = "gemm"  # Distances.jl pairwise formulation = what the reference executes on CPU
+    ref.DEFAULT_METHOD = "gemm"
     try:
+        if kind == "vfe":
+            return ref.elbo(cfg["k"], cfg["mean"], cfg["noise"], cfg["X"], cfg["y"], cfg["Z"], cfg["jitter"])
         lp = ref.logpdf(cfg["k"], cfg["mean"], cfg["noise"], cfg["X"], cfg["y"])
         post = ref.posterior(cfg["k"], cfg["mean"], cfg["noise"], cfg["X"], cfg["y"])
+        if kind == "fit_predict":
+            ref.post_mean_and_var(post, cfg["Xs"], noise_s=cfg["noise"])
+        return lp
     finally:
         ref.DEFAULT_METHOD = old
-    return lp, post["alpha"]
+
+
+def cpu_sample(wl, n_full):
+    """bounded sample of the workload for the CPU arm: (cfg, scale, description)"""
+    W = WORKLOADS[wl]
+    if W["kind"] == "vfe":  # cost 2 M^2 N: bounded N and M (make_config ties M = min(8192, N / 8)), scaled back
+        sub = min(n_full, 20000)
+        cfg = make_inputs(wl, n=sub)
+        m_sub, m_full = cfg["Z"].shape[0], min(W["M"], max(8, n_full // 8))
+        scale = (n_full / sub) * (m_full / m_sub) ** 2
+        if scale == 1.0:
+            return cfg, 1.0, "full workload"
+        return cfg, scale, "N=%d, M=%d sub-sample scaled by (N/%d) x (M/%d)^2 = %.0f (extrapolated, cost 2 M^2 N)" % (sub, m_sub, sub, m_sub, scale)
+    if n_full > CPU_SUB:
+        cfg = make_inputs(wl, n=CPU_SUB)
+        scale = (n_full / CPU_SUB) ** 3
+        if W["kind"] == "fit_predict":
+            cfg["Xs"] = cfg["Xs"][: max(1, W["M"] * CPU_SUB // n_full)]  # N^2 M term scaled like N^3
+        return cfg, scale, "N=%d sub-sample scaled by (N/%d)^3 = %.0f (extrapolated)" % (CPU_SUB, CPU_SUB, scale)
+    return make_inputs(wl, n=n_full), 1.0, "full workload (N=%d)" % n_full
 
 
 def blas_threads():
@@ -117,9 +170,9 @@ def blas_threads():
         return os.cpu_count()
 
 
-def best_cpu_threads(cfg):
-    """OpenBLAS with every hardware thread of a 128-thread host is often slower than with fewer on an
-    N=4096 potrf; give the CPU arm its best setting: try a few thread counts once, keep the fastest."""
+def best_cpu_threads(wl, cfg):
+    """OpenBLAS with every hardware thread of a many-core host is often slower than with fewer on these sizes; give
+    the CPU arm its best setting: each candidate thread count is run ONCE, the fastest is kept."""
     try:
         from threadpoolctl import threadpool_limits
     except Exception:
@@ -128,49 +181,62 @@ def best_cpu_threads(cfg):
     best, best_c = 1e18, cand[-1]
     for c in cand:
         with threadpool_limits(limits=c):
-            cpu_reference_step(cfg)  # warm
             t0 = time.perf_counter()
-            cpu_reference_step(cfg)
+            cpu_step(wl, cfg)
             dt = time.perf_counter() - t0
         if dt < best:
             best, best_c = dt, c
     return threadpool_limits(limits=best_c), best_c
 
 
-def run_reference(args, wl):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+def cpu_baseline(wl, n_full, reps=2):
+    cfg, scale, sample = cpu_sample(wl, n_full)
+    limiter, cores = best_cpu_threads(wl, cfg)
+    best = 1e18
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_step(wl, cfg)
+        best = min(best, time.perf_counter() - t0)
+    del limiter
+    return {"value": best * 1e3 * scale, "unit": "ms", "cores": cores, "kind": "port",
+            "sample": sample + "; reference-faithful step (logpdf then posterior = 2 Gram + 2 potrf) for fit workloads; "
+                               "BLAS threads = fastest of {8,16,32,64,all}, best of %d" % reps}
+
+
+def run_reference(args, wl, n_full):
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    cfg = make_inputs(wl)
-    N = WORKLOADS[wl]["N"]
-    sample = "full %s workload (N=%d), logpdf + posterior = 2 Gram + 2 potrf, per step" % (wl, N)
-    if N > 16384:  # bounded sample: time N=16384 and scale by (N/16384)^3 (labelled)
-        cfg = make_inputs("C4")
-        sub = 16384
-        for key in ("X", "y"):
-            cfg[key] = cfg[key][:sub]
-        scale = (N / sub) ** 3
-        sample = "N=%d sub-sample of %s scaled by (N/%d)^3 = %.1f (extrapolated)" % (sub, wl, sub, scale)
-    else:
-        scale = 1.0
-    limiter, cores = best_cpu_threads(cfg)
+    W = WORKLOADS[wl]
+    cfg, scale, sample = cpu_sample(wl, n_full)
+    limiter, cores = best_cpu_threads(wl, cfg)
     for _ in range(args.warmup):
-        cpu_reference_step(cfg)
+        cpu_step(wl, cfg)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(cfg)
+        cpu_step(wl, cfg)
     ms = (time.perf_counter() - t0) * 1e3 / args.steps * scale
-    line = {"impl": "reference", "metric": "ms to logpdf(fx,y)+posterior(fx,y)", "value": ms, "unit": "ms",
+    del limiter
+    line = {"impl": "reference", "metric": METRIC[W["kind"]], "value": ms, "unit": "ms",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: N=%d D=%d %s fp64" % (wl, N, WORKLOADS[wl]["D"], WORKLOADS[wl]["kernel"])},
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": W["dtype"], "data": "synthetic",
+            "config": {"workload": wl_string(wl, n_full)},
             "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------------------
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
 def measure_dgemm_peak(torch, dev):
-    """fp64 roofline denominator: cuBLAS DGEMM 8192^3 on this box, best of 5 (CUDA events)."""
+    """native fp64 reference rate: cuBLAS DGEMM 8192^3 on this box, best of 5 (CUDA events)."""
     n = 8192
     a = torch.randn(n, n, dtype=torch.float64, device=dev)
     b = torch.randn(n, n, dtype=torch.float64, device=dev)
@@ -188,336 +254,381 @@ def measure_dgemm_peak(torch, dev):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def run_ours(args, wl):
+def measure_int8_mma_peak(eng, torch, dev, S=7):
+    """MEASURED int8 tcgen05 rate of this kernel's own instruction mix: the persistent trailing-update kernel run with
+    its operand traffic and epilogue switched off (probe mode 5: every tile still issues all of its tcgen05.mma.kind::i8
+    instructions on operands already in shared memory).  TOP/s = executed int8 ops / time, slicing time subtracted."""
     import ctypes as C
-    import torch
-    import agp_b200 as ag
-    from agp_b200 import _cabi as cabi
+    M, K = 16384, 512
+    P = torch.randn(K, M, dtype=torch.float64, device=dev)
+    Cm = torch.zeros(M, M, dtype=torch.float64, device=dev)
+    old = os.environ.get("AGP_OZAKI_EPI")
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        return run_ours_dist(args, wl, rank, world, local)
-    if args.gpus > 1:
-        print(json.dumps({"metric": "ms to logpdf(fx,y)+posterior(fx,y)", "n_gpus": args.gpus,
-                          "unavailable": "launch with torchrun --nproc-per-node N (one rank per GPU)"}))
-        return
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    cfg = make_inputs(wl)
-    W = WORKLOADS[wl]
-    N, D = W["N"], W["D"]
-    eng = ag.engine()
-    L = eng.L
-    X = np.ascontiguousarray(cfg["X"], dtype=np.float64)  # [N, D] C-order == D x N column-major (ColVecs)
-    y = np.ascontiguousarray(cfg["y"], dtype=np.float64)
-    ks = cabi.agp_kernel()
-    ks.family, ks.transform, ks.variance, ks.scale = 0, 1, 1.0, float(cfg["k"].scale)
-    ms_ = cabi.agp_mean()
-    ns = cabi.agp_noise()
-    ns.kind, ns.s = 0, W["s2"]
-
-    # pinned host buffers (e2e) and device-resident copies (value)
-    Xh = torch.from_numpy(X).pin_memory()
-    yh = torch.from_numpy(y).pin_memory()
-    alpha_h = torch.empty(N, dtype=torch.float64).pin_memory()
-    Xd, yd = Xh.to(dev), yh.to(dev)
-    alpha_d = torch.empty(N, dtype=torch.float64, device=dev)
-    lp = np.zeros(1)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def step(device_resident):
-        post = C.c_void_p()
-        eng.set_memspace(cabi.AGP_MEM_DEVICE if device_resident else cabi.AGP_MEM_HOST)
-        xp = Xd.data_ptr() if device_resident else Xh.data_ptr()
-        yp = yd.data_ptr() if device_resident else yh.data_ptr()
-        ap = alpha_d.data_ptr() if device_resident else alpha_h.data_ptr()
-        rc = L.agp_fit(eng.h, cabi.AGP_F64, C.byref(ks), C.byref(ms_), C.byref(ns), cabi.AGP_POINT_MAJOR,
-                       C.c_void_p(xp), N, D, C.c_void_p(yp), 1, cabi.ptr(lp), C.c_void_p(ap), C.byref(post))
-        eng.check(rc)
-        t = eng.timings()
-        L.agp_post_free(post)
-        return t
-
-    def timed(device_resident, steps, warmup):
-        for _ in range(warmup):
-            step(device_resident)
-        tot = {}
-        torch.cuda.synchronize()
-        launches0 = eng.launch_count()
-        wall = 0.0
-        for _ in range(steps):
-            flush.zero_()  # L2 flush between timed iterations (outside the event-timed region)
+    def run(ncols):
+        best = 1e9
+        for _ in range(3):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            t = step(device_resident)
-            torch.cuda.synchronize()
-            wall += time.perf_counter() - t0
-            for k_, v in t.items():
-                tot[k_] = tot.get(k_, 0.0) + v
-        launches = eng.launch_count() - launches0
-        return {k_: v / steps for k_, v in tot.items()}, wall * 1e3 / steps, launches
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    t_dev, wall_dev, launches = timed(True, args.steps, args.warmup)
-    t_e2e, wall_e2e, _ = timed(False, args.steps, args.warmup)
-    clocks = sampler.stop()
-
-    # parity spot check against the oracle on the same inputs (outside any timed region)
-    parity = None
-    if N <= 8192:
-        from oracle import agp_ref as ref
-        lp_ref = ref.logpdf(cfg["k"], cfg["mean"], cfg["noise"], cfg["X"], cfg["y"])
-        parity = {"logpdf": float(lp[0]), "oracle_logpdf": float(lp_ref),
-                  "rel_err": float(abs(lp[0] - lp_ref) / abs(lp_ref)), "tol": 1e-8}
-
-    dgemm = measure_dgemm_peak(torch, dev)
-    peaks = {}
+            eng.check(eng.L.agp_debug_ozaki_syrk(eng.h, C.c_void_p(Cm.data_ptr()), M, C.c_void_p(P.data_ptr()), M, M, ncols, K, S, 1))
+            best = min(best, time.perf_counter() - t0)
+        return best
     try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    # ---- roofline of the dominant kernel (the trailing update).  Its launches are timed with CUDA events
-    # around every launch inside the library; the look-ahead schedule overlaps two of them on two streams,
-    # so the per-kernel time is taken in a pass with look-ahead OFF (serial launches), same inputs, same kernels.
-    cfg0 = eng.get_config()
-    eng.set_config(lookahead=0, profile_kernels=1)
-    t_serial, _, _ = timed(True, max(2, min(args.steps, 5)), 1)
-    eng.set_config(lookahead=cfg0.lookahead, profile_kernels=cfg0.profile_kernels)
-    n_pad = (N + 127) // 128 * 128
-    nb = cfg0.tile_nb if cfg0.tile_nb > 0 else (512 if n_pad >= 8192 else 128)
-    mode = cfg0.fp64_mode if cfg0.fp64_mode >= 0 else (1 if n_pad >= 8192 else 0)
-    S_sl = cfg0.ozaki_slices
-    outer = []  # (m, K) of every outer trailing update
-    t0 = 0
-    while t0 < n_pad:
-        K = min(nb, n_pad - t0)
-        t0 += K
-        if n_pad - t0 > 0:
-            outer.append((n_pad - t0, K))
-    tf = sum(2.0 * K * m * (m + 1) / 2 for m, K in outer)  # algorithmic fp64 flops of the outer trailing updates
-    trailing_ms = t_serial.get("trailing", 0.0)
-    fp64_eq = tf / (trailing_ms * 1e-3) / 1e12 if trailing_ms > 0 else None
-    chol_tf = (N ** 3 / 3.0) / (t_dev["cholesky"] * 1e-3) / 1e12
-    if mode == 1:
-        pairs = S_sl * (S_sl + 1) // 2
-        int8_peak = 2.0 * peaks.get("bf16_tflops", 1590.0)  # int8 dense = 2x the measured bf16 GEMM rate (nominal 4.5 POP/s)
-        achieved = fp64_eq * pairs if fp64_eq else None      # executed int8 TOP/s: every fp64 MAC = S(S+1)/2 int8 MACs
-        roofline = {"bound": "tensor", "kernel": "umma_ozaki_syrk_v2_kernel<%d> (tcgen05.mma.kind::i8, TMA, TMEM; persistent)" % S_sl,
-                    "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8 tensor, dense)",
-                    "frac": (achieved / int8_peak) if achieved else None,
-                    "peak_source": "2 x bf16_tflops of MEASURED_PEAKS.json (%s); int8 kind runs at twice the bf16 rate (nominal 4.5 POP/s)"
-                                   % ("of measured" if "bf16_tflops" in peaks else "of fallback 1590"),
-                    "fp64_equivalent_tflops": fp64_eq, "fp64_equivalent_vs_cublas_dgemm": (fp64_eq / dgemm) if fp64_eq else None,
-                    "slices": S_sl, "int8_macs_per_fp64_mac": pairs}
-    else:
-        roofline = {"bound": "tensor", "kernel": "gemm_dmma_kernel<false,false,2,2> (DMMA mma.sync.m8n8k4.f64, lower tiles)",
-                    "achieved": fp64_eq, "peak": dgemm, "unit": "TFLOP/s (fp64)", "frac": (fp64_eq / dgemm) if fp64_eq else None,
-                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 entry); "
-                                   "DMMA microbenchmark on this pool: 37.0 TFLOP/s",
-                    "frac_of_bf16_measured": (fp64_eq / peaks["bf16_tflops"]) if (fp64_eq and "bf16_tflops" in peaks) else None}
-    roofline.update({"launches_per_step": len(outer), "alg_flops_per_step": tf, "kernel_ms_per_step": trailing_ms,
-                     "traffic_ncu": ncu_traffic(mode),
-                     "kernel_timing": "CUDA events around each launch, look-ahead off (serial), %d steps" % max(2, min(args.steps, 5)),
-                     "panel_width": nb, "cublas_dgemm_tflops": dgemm,
-                     # dram bytes of ONE launch from the committed `ncu --set full` capture; it was taken on the C4h
-                     # workload, so it is only comparable (per launch) when that workload is benched
-                     "traffic": (ncu_traffic(mode) or {}).get("dram_bytes_per_launch") if wl == "C4h" else None,
-                     "cholesky_third_n3_tflops": chol_tf, "cholesky_frac_of_dgemm": chol_tf / dgemm})
-
-    # CPU baseline (oracle port of the reference's LAPACK path) on this box's host cores, bounded sample
-    cfg_cpu, scale, sample = cfg, 1.0, "full %s workload (N=%d), logpdf+posterior = 2 Gram + 2 dpotrf, best of 3" % (wl, N)
-    if N > 8192:
-        sub = 8192
-        cfg_cpu = dict(cfg)
-        cfg_cpu["X"], cfg_cpu["y"] = cfg["X"][:sub], cfg["y"][:sub]
-        scale = (N / sub) ** 3
-        sample = "N=%d sub-sample scaled by (N/%d)^3=%.0f (extrapolated)" % (sub, sub, scale)
-    limiter, cpu_cores = best_cpu_threads(cfg_cpu)
-    best = 1e18
-    for _ in range(3):
-        t0 = time.perf_counter()
-        cpu_reference_step(cfg_cpu)
-        best = min(best, time.perf_counter() - t0)
-    cpu = {"value": best * 1e3 * scale, "unit": "ms", "cores": cpu_cores, "kind": "port",
-           "sample": sample + "; BLAS threads = fastest of {8,16,32,64,all}"}
-
-    line = {"metric": "ms to logpdf(fx,y)+posterior(fx,y)", "value": t_dev["total"], "unit": "ms", "n_gpus": 1,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev["total"], "higher_is_better": False,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: N=%d D=%d %s fp64, sigma2=%g, fused fit (1 Gram + 1 Cholesky)" % (wl, N, D, W["kernel"], W["s2"]),
-                       "l2": "256 MiB flush buffer written between timed iterations", "timer": "CUDA events on the library stream",
-                       "tile": 128},
-            "phases_ms": t_dev, "wall_ms_per_step": wall_dev,
-            "e2e": {"value": t_e2e["total"], "unit": "ms", "h2d_bytes_per_step": int(X.nbytes + y.nbytes),
-                    "d2h_bytes_per_step": int(alpha_h.numel() * 8 + 8 + 4 + 8), "wall_ms_per_step": wall_e2e,
-                    "phases_ms": t_e2e},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "parity": parity}
-    if wl == "C2" and not args.no_scaling_ref:
-        # --gpus N > 1 runs the sharded config C4 (C2 is too small to shard); its single-GPU time is the
-        # base of the strong-scaling curve, measured here so the N=1 line carries it
-        line["scaling_reference"] = c4_single_gpu_reference(eng, L, cabi, C, torch, dev)
-    print(json.dumps(line))
+        os.environ["AGP_OZAKI_EPI"] = "5"
+        fixed = run(128)
+        full = run(M)
+    finally:
+        if old is None:
+            os.environ.pop("AGP_OZAKI_EPI", None)
+        else:
+            os.environ["AGP_OZAKI_EPI"] = old
+    nbi, nbj = M // 128, M // 64
+    tiles = sum(min(nbj, 2 * bi + 2) for bi in range(nbi)) - 2  # minus the strip of the `fixed` run (approx.)
+    ops = 2.0 * tiles * 128 * 64 * K * (S * (S + 1) // 2)
+    del P, Cm
+    return ops / max(full - fixed, 1e-9) / 1e12
 
 
-def ncu_traffic(mode):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/): per launch, for the launch that was captured (the largest trailing update of the C4h step)."""
-    name = "r01_prof_ozaki_v2_c4h.txt" if mode == 1 else "r01_prof_syrk_c4h.txt"
+def ncu_traffic(tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed ncu capture
+    under profiles/ (see profiles/README.md), with that launch's algorithmic bytes -- None when no capture is committed."""
     try:
-        rd = wr = None
-        for line in open(os.path.join(ROOT, "profiles", name)):
-            parts = line.split()
-            if line.startswith("dram__bytes_read.sum ") and rd is None:
-                rd = float(parts[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3}.get(parts[2], 1.0)
-            if line.startswith("dram__bytes_write.sum ") and wr is None:
-                wr = float(parts[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3}.get(parts[2], 1.0)
-        return {"source": "profiles/" + name, "dram_bytes_per_launch": rd + wr, "read": rd, "write": wr}
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[tag]
     except Exception:
         return None
 
 
-def c4_single_gpu_reference(eng, L, cabi, C, torch, dev):
-    cfg = make_inputs("C4")
-    W = WORKLOADS["C4"]
-    N, D = W["N"], W["D"]
-    Xd = torch.from_numpy(np.ascontiguousarray(cfg["X"], dtype=np.float64)).to(dev)
-    yd = torch.from_numpy(np.ascontiguousarray(cfg["y"], dtype=np.float64)).to(dev)
-    alpha_d = torch.empty(N, dtype=torch.float64, device=dev)
-    ks = cabi.agp_kernel()
-    ks.family, ks.transform, ks.variance, ks.scale = 0, 1, 1.0, float(cfg["k"].scale)
-    ms_, ns = cabi.agp_mean(), cabi.agp_noise()
-    ns.kind, ns.s = 0, W["s2"]
-    lp = np.zeros(1)
-    eng.set_memspace(cabi.AGP_MEM_DEVICE)
-    tot = []
-    for it in range(3):
-        rc = L.agp_fit(eng.h, cabi.AGP_F64, C.byref(ks), C.byref(ms_), C.byref(ns), cabi.AGP_POINT_MAJOR,
-                       C.c_void_p(Xd.data_ptr()), N, D, C.c_void_p(yd.data_ptr()), 1, cabi.ptr(lp), C.c_void_p(alpha_d.data_ptr()), None)
-        eng.check(rc)
-        if it > 0:
-            tot.append(eng.timings()["total"])
-    return {"workload": "C4: N=65536 D=64 SqExponential fp64 on 1 GPU (the config --gpus N>1 shards)", "ms": float(np.mean(tot)),
-            "steps": len(tot), "logpdf": float(lp[0]), "third_n3_tflops": (N ** 3 / 3.0) / (np.mean(tot) * 1e-3) / 1e12}
+class FitProblem:
+    """device + pinned-host copies of one workload and the ABI call that is a 'step'"""
 
+    def __init__(self, wl, n, eng, torch, dev, need_post=True):
+        import ctypes as C
+        from agp_b200 import _cabi as cabi
+        self.C, self.cabi, self.eng, self.torch = C, cabi, eng, torch
+        W = WORKLOADS[wl]
+        self.wl, self.W, self.kind = wl, W, W["kind"]
+        cfg = make_inputs(wl, n)
+        self.cfg = cfg
+        self.np_dt = np.float64 if W["dtype"] == "f64" else np.float32
+        self.code = cabi.AGP_F64 if W["dtype"] == "f64" else cabi.AGP_F32
+        X = np.ascontiguousarray(cfg["X"], dtype=self.np_dt)  # [N, D] C-order == D x N column-major (ColVecs)
+        y = np.ascontiguousarray(cfg["y"], dtype=self.np_dt)
+        self.N, self.D = X.shape
+        ks = cabi.agp_kernel()
+        k = cfg["k"]
+        ks.family, ks.variance, ks.linear_c, ks.scale = int(k.family), float(k.variance), 0.0, 1.0
+        self.keep = []
+        if k.transform == 1:
+            ks.transform, ks.scale = 1, float(k.scale)
+        elif k.transform == 2:
+            ard = np.ascontiguousarray(k.ard, dtype=self.np_dt)
+            self.keep.append(ard)
+            ks.transform, ks.ard = 2, ard.ctypes.data
+        self.ks, self.ms, self.ns = ks, cabi.agp_mean(), cabi.agp_noise()
+        self.ns.kind, self.ns.s = 0, float(cfg["noise"].s)
+        tdt = torch.float64 if W["dtype"] == "f64" else torch.float32
+        self.Xh, self.yh = torch.from_numpy(X).pin_memory(), torch.from_numpy(y).pin_memory()
+        self.alpha_h = torch.empty(self.N, dtype=tdt).pin_memory()
+        self.Xd, self.yd = self.Xh.to(dev), self.yh.to(dev)
+        self.alpha_d = torch.empty(self.N, dtype=tdt, device=dev)
+        self.lp = np.zeros(2, dtype=self.np_dt)
+        self.h2d = int(X.nbytes + y.nbytes)
+        self.d2h = int(self.N * X.itemsize + X.itemsize + 12)
+        self.need_post = need_post
+        if self.kind == "fit_predict":
+            Xs = np.ascontiguousarray(cfg["Xs"], dtype=self.np_dt)
+            self.M = Xs.shape[0]
+            self.Xsh = torch.from_numpy(Xs).pin_memory()
+            self.Xsd = self.Xsh.to(dev)
+            self.mu_h, self.var_h = torch.empty(self.M, dtype=tdt).pin_memory(), torch.empty(self.M, dtype=tdt).pin_memory()
+            self.mu_d, self.var_d = torch.empty(self.M, dtype=tdt, device=dev), torch.empty(self.M, dtype=tdt, device=dev)
+            self.h2d += int(Xs.nbytes)
+            self.d2h += int(2 * self.M * Xs.itemsize)
+        if self.kind == "vfe":
+            Z = np.ascontiguousarray(cfg["Z"], dtype=self.np_dt)
+            self.M = Z.shape[0]
+            self.Zh = torch.from_numpy(Z).pin_memory()
+            self.Zd = self.Zh.to(dev)
+            self.js = cabi.agp_noise()
+            self.js.kind, self.js.s = 0, float(cfg["jitter"].s)
+            self.h2d += int(Z.nbytes)
+            self.d2h = 2 * X.itemsize
 
-def run_ours_dist(args, wl, rank, world, local):
-    """N > 1: one rank per GPU (torchrun); block-column-cyclic Cholesky with NCCL panel broadcast inside
-    libagp.so.  Strong scaling: the SAME workload at every N.  Time = max over ranks of the library's
-    CUDA-event time, bracketed by a barrier + device sync on both sides."""
-    import ctypes as C
-    import torch
-    import torch.distributed as dist
-    from agp_b200 import _cabi as cabi
-    from agp_b200.dist import init_distributed_engine
-
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    eng = init_distributed_engine()
-    L = eng.L
-    cfg = make_inputs(wl)
-    W = WORKLOADS[wl]
-    N, D = W["N"], W["D"]
-    X = np.ascontiguousarray(cfg["X"], dtype=np.float64)
-    y = np.ascontiguousarray(cfg["y"], dtype=np.float64)
-    ks = cabi.agp_kernel()
-    ks.family, ks.transform, ks.variance, ks.scale = 0, 1, 1.0, float(cfg["k"].scale)
-    ms_ = cabi.agp_mean()
-    ns = cabi.agp_noise()
-    ns.kind, ns.s = 0, W["s2"]
-    Xh, yh = torch.from_numpy(X).pin_memory(), torch.from_numpy(y).pin_memory()
-    alpha_h = torch.empty(N, dtype=torch.float64).pin_memory()
-    Xd, yd = Xh.to(dev), yh.to(dev)
-    alpha_d = torch.empty(N, dtype=torch.float64, device=dev)
-    lp = np.zeros(1)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-
-    def step(device_resident):
+    def step(self, device_resident, dist=False):
+        C, cabi, eng, L = self.C, self.cabi, self.eng, self.eng.L
         eng.set_memspace(cabi.AGP_MEM_DEVICE if device_resident else cabi.AGP_MEM_HOST)
-        xp = Xd.data_ptr() if device_resident else Xh.data_ptr()
-        yp = yd.data_ptr() if device_resident else yh.data_ptr()
-        ap = alpha_d.data_ptr() if device_resident else alpha_h.data_ptr()
-        rc = L.agp_fit(eng.h, cabi.AGP_F64, C.byref(ks), C.byref(ms_), C.byref(ns), cabi.AGP_POINT_MAJOR,
-                       C.c_void_p(xp), N, D, C.c_void_p(yp), 1, cabi.ptr(lp), C.c_void_p(ap), None)
+        pick = (lambda d, h: d.data_ptr()) if device_resident else (lambda d, h: h.data_ptr())
+        xp, yp, ap = pick(self.Xd, self.Xh), pick(self.yd, self.yh), pick(self.alpha_d, self.alpha_h)
+        if self.kind == "vfe":
+            rc = L.agp_vfe_elbo(eng.h, self.code, C.byref(self.ks), C.byref(self.ms), C.byref(self.ns), cabi.AGP_POINT_MAJOR,
+                                C.c_void_p(xp), self.N, self.D, C.c_void_p(pick(self.Zd, self.Zh)), self.M, C.byref(self.js),
+                                C.c_void_p(yp), cabi.ptr(self.lp[0:1]), cabi.ptr(self.lp[1:2]))
+            eng.check(rc)
+            return eng.timings()
+        post = C.c_void_p()
+        want_post = self.need_post and not dist
+        rc = L.agp_fit(eng.h, self.code, C.byref(self.ks), C.byref(self.ms), C.byref(self.ns), cabi.AGP_POINT_MAJOR,
+                       C.c_void_p(xp), self.N, self.D, C.c_void_p(yp), 1, cabi.ptr(self.lp), C.c_void_p(ap),
+                       C.byref(post) if want_post else None)
         eng.check(rc)
-        return eng.timings()
+        t = eng.timings()
+        if self.kind == "fit_predict":
+            rc = L.agp_post_mean_var(post, cabi.AGP_POINT_MAJOR, C.c_void_p(pick(self.Xsd, self.Xsh)), self.M, None,
+                                     C.byref(self.ns), C.c_void_p(pick(self.mu_d, self.mu_h)), C.c_void_p(pick(self.var_d, self.var_h)))
+            eng.check(rc)
+            t2 = eng.timings()
+            t["predict"] = t2["predict"]
+            t["total"] = t["total"] + t2["predict"]
+        if want_post:
+            L.agp_post_free(post)
+        return t
 
-    def timed(device_resident, steps, warmup):
-        for _ in range(warmup):
-            step(device_resident)
-        tot = {}
-        launches0 = eng.launch_count()
-        wall = 0.0
-        for _ in range(steps):
-            flush.zero_()
-            torch.cuda.synchronize()
+
+def timed(prob, torch, flush, device_resident, steps, warmup, dist=None):
+    eng = prob.eng
+    for _ in range(warmup):
+        prob.step(device_resident, dist is not None)
+    tot = {}
+    torch.cuda.synchronize()
+    launches0 = eng.launch_count()
+    wall = 0.0
+    for _ in range(steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the event-timed region)
+        torch.cuda.synchronize()
+        if dist is not None:
             dist.barrier()
-            t0 = time.perf_counter()
-            t = step(device_resident)
-            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        t = prob.step(device_resident, dist is not None)
+        torch.cuda.synchronize()
+        if dist is not None:
             dist.barrier()
-            wall += time.perf_counter() - t0
-            for k_, v in t.items():
-                tot[k_] = tot.get(k_, 0.0) + v
-        mine = {k_: v / steps for k_, v in tot.items()}
+        wall += time.perf_counter() - t0
+        for k_, v in t.items():
+            tot[k_] = tot.get(k_, 0.0) + v
+    launches = eng.launch_count() - launches0
+    mine = {k_: v / steps for k_, v in tot.items()}
+    if dist is not None:
         keys = sorted(mine)
         tt = torch.tensor([mine[k_] for k_ in keys], dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)  # max over ranks, per phase
-        return dict(zip(keys, tt.tolist())), wall * 1e3 / steps, eng.launch_count() - launches0
+        mine = dict(zip(keys, tt.tolist()))
+    return mine, wall * 1e3 / steps, launches
+
+
+def parity_check(wl, prob_cls_args, eng, torch, dev, dist=None):
+    """out-of-timed-region parity of the BENCHED path against the oracle: the workload itself when N <= 8192, else its
+    first 8192 points through the same engine configuration (n_pad >= 8192 keeps the tcgen05 / distributed path)."""
+    from oracle import agp_ref as ref
+    W = WORKLOADS[wl]
+    n_full = prob_cls_args["n"]
+    n = min(n_full, CPU_SUB)
+    if W["kind"] == "vfe":
+        n = min(n_full, 20000)
+    p = FitProblem(wl, n, eng, torch, dev)
+    p.step(True, dist is not None)
+    got = float(p.lp[0])
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    cfg = p.cfg
+    tol = 1e-8 if W["dtype"] == "f64" else 1e-4
+    old = ref.DEFAULT_METHOD
+    ref.DEFAULT_METHOD = "gemm"  # the reference's executed formulation (Distances.jl pairwise)
+    try:
+        c64 = {k_: (v.astype(np.float64) if isinstance(v, np.ndarray) else v) for k_, v in cfg.items()}
+        k64 = cfg["k"]
+        if getattr(k64, "ard", None) is not None:
+            k64 = ref.KernelSpec(k64.family, k64.variance, k64.transform, k64.scale, np.asarray(k64.ard, dtype=np.float64), k64.linear_c)
+        if W["kind"] == "vfe":
+            want = ref.elbo(k64, cfg["mean"], cfg["noise"], c64["X"], c64["y"], c64["Z"], cfg["jitter"])
+        else:
+            want = ref.logpdf(k64, cfg["mean"], cfg["noise"], c64["X"], c64["y"])
+    finally:
+        ref.DEFAULT_METHOD = old
+    return {"quantity": "elbo" if W["kind"] == "vfe" else "logpdf", "n": n, "ours": got, "oracle": float(want),
+            "rel_err": float(abs(got - want) / abs(want)), "tol": tol, "ok": bool(abs(got - want) <= tol * abs(want)),
+            "oracle_form": "fp64, Distances.jl gemm form", "sample": "full workload" if n == n_full else "first %d points, same engine config" % n}
+
+
+def fit_roofline(wl, N, eng, torch, dev, prob, flush, args, world=1, dist=None, t_dev=None):
+    """roofline of the dominant kernel = the outer trailing update.  Its launches are timed with CUDA events around every
+    launch inside the library (profile_kernels = 1); on one GPU the look-ahead schedule overlaps two of them on two
+    streams, so that pass runs with look-ahead OFF (serial launches), same inputs, same kernels."""
+    peaks = load_peaks()
+    cfg0 = eng.get_config()
+    W = WORKLOADS[wl]
+    if dist is None:
+        eng.set_config(lookahead=0, profile_kernels=1)
+    else:
+        eng.set_config(profile_kernels=1)
+    t_serial, _, _ = timed(prob, torch, flush, True, max(2, min(args.steps, 3)), 1, dist)
+    eng.set_config(lookahead=cfg0.lookahead, profile_kernels=cfg0.profile_kernels)
+    n_pad = (N + 127) // 128 * 128
+    nb = cfg0.tile_nb if cfg0.tile_nb > 0 else (512 if n_pad >= 8192 else 128)
+    if world > 1:
+        n_pad = (N + nb - 1) // nb * nb
+    mode = cfg0.fp64_mode if cfg0.fp64_mode >= 0 else (1 if n_pad >= 8192 else 0)
+    S_sl = cfg0.ozaki_slices
+    tf = trailing_flops(N, nb)
+    launches = max(1, n_pad // nb - 1)
+    trailing_ms = t_serial.get("trailing", 0.0)  # max over ranks of the per-rank sum of launch durations
+    out = {"launches_per_step": launches * world, "alg_flops_per_step": tf, "kernel_ms_per_step": trailing_ms,
+           "kernel_ms_per_step_rank_max": trailing_ms, "panel_width": nb,
+           "kernel_timing": "CUDA events around each launch%s, %d steps" % (", look-ahead off (serial)" if dist is None else ", max over ranks of the per-rank sum", max(2, min(args.steps, 3)))}
+    if W["dtype"] == "f64" and mode == 1:
+        pairs = S_sl * (S_sl + 1) // 2
+        fp64_eq = tf / world / (trailing_ms * 1e-3) / 1e12 if trailing_ms > 0 else None  # per GPU
+        achieved = fp64_eq * pairs if fp64_eq else None  # executed int8 TOP/s per GPU: every fp64 MAC = S(S+1)/2 int8 MACs
+        mma_peak = measure_int8_mma_peak(eng, torch, dev, S_sl)
+        nominal = 4500.0
+        out.update({"bound": "tensor", "kernel": "umma_ozaki_syrk_v2_kernel<%d> (tcgen05.mma.kind::i8, TMA, TMEM; persistent)" % S_sl,
+                    "achieved": achieved, "peak": mma_peak, "unit": "TOP/s (int8 tensor, dense, per GPU)",
+                    "frac": (achieved / mma_peak) if achieved else None,
+                    "peak_source": "MEASURED in this run: the same kernel's tcgen05.mma.kind::i8 instruction stream with operand traffic and "
+                                   "epilogue off (operands resident in shared memory), 16384 x 16384 x 512 -- the tensor-pipe ceiling of this "
+                                   "instruction mix on this box",
+                    "frac_of_2x_bf16_measured": (achieved / (2.0 * peaks["bf16_tflops"])) if (achieved and "bf16_tflops" in peaks) else None,
+                    "frac_of_nominal_4500": (achieved / nominal) if achieved else None,
+                    "fp64_equivalent_tflops_per_gpu": fp64_eq, "slices": S_sl, "int8_macs_per_fp64_mac": pairs})
+    elif W["dtype"] == "f64":
+        dgemm = measure_dgemm_peak(torch, dev)
+        fp64 = tf / world / (trailing_ms * 1e-3) / 1e12 if trailing_ms > 0 else None
+        out.update({"bound": "tensor", "kernel": "gemm_dmma_kernel (DMMA mma.sync.m8n8k4.f64, lower tiles)",
+                    "achieved": fp64, "peak": dgemm, "unit": "TFLOP/s (fp64, per GPU)", "frac": (fp64 / dgemm) if fp64 else None,
+                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 entry)"})
+    else:
+        fp32 = tf / world / (trailing_ms * 1e-3) / 1e12 if trailing_ms > 0 else None
+        tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
+        out.update({"bound": "tensor", "kernel": "fp32 trailing update (see DESIGN.md s4)",
+                    "achieved": fp32, "peak": tf32_peak / 3.0, "unit": "TFLOP/s (fp32-equivalent, 3 tf32 products per fp32 product)",
+                    "frac": (fp32 / (tf32_peak / 3.0)) if fp32 else None,
+                    "peak_source": "bf16_tflops of MEASURED_PEAKS.json / 2 (tf32 runs at half the bf16 rate) / 3 (3xTF32 split)"})
+    tr = ncu_traffic(wl if wl in ("C4", "C4h", "C2", "C3", "C5") else "C4")
+    out["traffic"] = tr.get("dram_bytes_per_launch") if tr else None
+    out["traffic_detail"] = tr
+    if t_dev:
+        chol_tf = (N ** 3 / 3.0) / (t_dev["cholesky"] * 1e-3) / 1e12
+        out["cholesky_third_n3_tflops"] = chol_tf
+    return out
+
+
+def run_ours(args, wl, n_full):
+    import torch
+    import agp_b200 as ag
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    W = WORKLOADS[wl]
+    if world == 1 and args.gpus > 1:
+        print(json.dumps({"metric": METRIC[W["kind"]], "n_gpus": args.gpus,
+                          "unavailable": "launch with torchrun --nproc-per-node N (one rank per GPU)"}))
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        from agp_b200.dist import init_distributed_engine
+        eng = init_distributed_engine()
+        if W["kind"] == "fit_predict":
+            if rank == 0:
+                print(json.dumps({"metric": METRIC[W["kind"]], "n_gpus": world, "unavailable": "C3 does not shard (N = 16384): replicas only"}))
+            return
+    else:
+        eng = ag.engine()
+    prob = FitProblem(wl, n_full, eng, torch, dev)
+    N, D = prob.N, prob.D
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    t_dev, wall_dev, launches = timed(True, args.steps, args.warmup)
-    t_e2e, wall_e2e, _ = timed(False, args.steps, args.warmup)
+    t_dev, wall_dev, launches = timed(prob, torch, flush, True, args.steps, args.warmup, dist)
+    t_e2e, wall_e2e, _ = timed(prob, torch, flush, False, args.steps, args.warmup, dist)
     clocks = sampler.stop() if rank == 0 else None
-    lt = torch.tensor([float(launches)])
-    dist.all_reduce(lt)
+    lp_val = float(prob.lp[0])
+    if dist is not None:
+        lt = torch.tensor([float(launches)])
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+
+    parity = None
+    try:
+        parity = parity_check(wl, {"n": n_full}, eng, torch, dev, dist)
+    except Exception as e:  # the parity probe must never take the bench line down
+        parity = {"error": repr(e)[:200]}
+
+    roofline = None
+    if W["kind"] in ("fit", "fit_predict"):
+        roofline = fit_roofline(wl, N, eng, torch, dev, prob, flush, args, world, dist, t_dev)
+        if world > 1:
+            roofline["whole_job_third_n3_tflops"] = roofline.pop("cholesky_third_n3_tflops", None)
+    else:  # VFE: streamed TRSM + SYRK, 2 M^2 N algorithmic flops (reference formulation, SURVEY s8d)
+        M = prob.M
+        peaks = load_peaks()
+        alg = 2.0 * M * M * N + 2.0 * M ** 3 / 3.0
+        tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
+        ach = alg / (t_dev["total"] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "VFE stream (cross-Gram -> TRSM -> SYRK accumulate), see DESIGN.md s4",
+                    "achieved": ach, "peak": tf32_peak / 3.0 * world, "unit": "TFLOP/s (fp32-equivalent, whole job)",
+                    "frac": ach / (tf32_peak / 3.0 * world), "alg_flops_per_step": alg,
+                    "peak_source": "N_gpus x bf16_tflops of MEASURED_PEAKS.json / 2 / 3 (3xTF32)", "traffic": None}
     if rank != 0:
         return
-    dgemm = measure_dgemm_peak(torch, dev)
-    tf = trailing_flops(N)
-    chol_tf = (N ** 3 / 3.0) / (t_dev["cholesky"] * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "trailing update of the local block columns (umma_ozaki_syrk_v2_kernel, tcgen05 kind::i8, "
-                                          "for n_pad >= 8192; gemm_dmma_kernel below)",
-                "achieved": chol_tf, "peak": dgemm * world, "unit": "TFLOP/s (fp64-equivalent, whole job)", "frac": chol_tf / (dgemm * world),
-                "peak_source": "N x cuBLAS DGEMM 8192^3 measured on rank 0 in this run (native fp64 rate); achieved = (N^3/3) / "
-                               "max-over-ranks factorisation time; > 1 is possible because the int8-sliced path is not bound by the fp64 pipe",
-                "alg_flops_per_step": N ** 3 / 3.0, "trailing_flops_per_step": tf,
-                "kernel_ms_per_step_rank_max": t_dev.get("trailing", 0.0), "traffic": None}
-    line = {"metric": "ms to logpdf(fx,y)+posterior(fx,y)", "value": t_dev["total"], "unit": "ms", "n_gpus": world,
+    cpu = cpu_baseline(wl, n_full)
+    line = {"metric": METRIC[W["kind"]], "value": t_dev["total"], "unit": "ms", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev["total"], "higher_is_better": False,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: N=%d D=%d %s fp64, sigma2=%g, fused fit (logpdf + alpha), block-column-cyclic over %d GPUs, "
-                                   "NCCL panel broadcast" % (wl, N, D, W["kernel"], W["s2"], world),
+            "scaling": "strong", "vs_baseline": None, "dtype": W["dtype"], "data": "synthetic",
+            "config": {"workload": wl_string(wl, N, ", fused fit (1 Gram + 1 Cholesky)" if W["kind"] == "fit" else ""),
                        "l2": "256 MiB flush buffer written between timed iterations",
-                       "timer": "CUDA events on the library stream, max over ranks", "tile": 128, "grid": "1x%d" % world},
+                       "timer": "CUDA events on the library stream" + (", max over ranks" if world > 1 else ""), "tile": 128,
+                       "grid": "1x%d block-column-cyclic, NCCL panel broadcast" % world if world > 1 else "single GPU"},
             "phases_ms": t_dev, "wall_ms_per_step": wall_dev,
-            "e2e": {"value": t_e2e["total"], "unit": "ms", "h2d_bytes_per_step": int((X.nbytes + y.nbytes) * world),
-                    "d2h_bytes_per_step": int((alpha_h.numel() * 8 + 12) * world), "wall_ms_per_step": wall_e2e,
-                    "phases_ms": t_e2e},
-            "gpu_launches": int(lt.item()), "roofline": roofline, "clocks": clocks,
-            "logpdf": float(lp[0])}
+            "e2e": {"value": t_e2e["total"], "unit": "ms", "h2d_bytes_per_step": int(prob.h2d * world),
+                    "d2h_bytes_per_step": int(prob.d2h * world), "wall_ms_per_step": wall_e2e, "phases_ms": t_e2e},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "parity": parity,
+            "result": lp_val}
+    if W["kind"] == "fit":
+        line["third_n3_tflops"] = (N ** 3 / 3.0) / (t_dev["total"] * 1e-3) / 1e12
+    if wl == "C4" and world == 1 and not args.no_c2:
+        line["c2"] = secondary_c2(eng, torch, dev, flush, args)
     print(json.dumps(line))
+
+
+def secondary_c2(eng, torch, dev, flush, args):
+    """BASELINE config C2 (N = 4096, D = 8): latency-bound single-GPU case, carried next to the C4 headline"""
+    p = FitProblem("C2", None, eng, torch, dev)
+    steps = max(5, min(args.steps, 20))
+    t_dev, _, launches = timed(p, torch, flush, True, steps, 3)
+    t_e2e, _, _ = timed(p, torch, flush, False, steps, 3)
+    par = None
+    try:
+        par = parity_check("C2", {"n": 4096}, eng, torch, dev)
+    except Exception as e:
+        par = {"error": repr(e)[:200]}
+    return {"workload": wl_string("C2", 4096), "value": t_dev["total"], "unit": "ms", "e2e": t_e2e["total"], "steps": steps,
+            "phases_ms": t_dev, "gpu_launches_per_step": launches / steps, "parity": par,
+            "third_n3_tflops": (4096 ** 3 / 3.0) / (t_dev["total"] * 1e-3) / 1e12, "cpu_baseline": cpu_baseline("C2", 4096)}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None)
-    ap.add_argument("--no-scaling-ref", action="store_true", help="skip the C4-on-1-GPU reference measurement at N=1")
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=None, help="override N of the workload (development / shard-sized runs)")
+    ap.add_argument("--no-c2", action="store_true", help="skip the secondary C2 measurement on the N=1 C4 line")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    wl = args.workload or ("C2" if args.gpus == 1 else "C4")
+    if args.impl == "ours":
+        args.warmup = max(args.warmup, 3)
+    wl = args.workload
+    n_full = args.n or WORKLOADS[wl]["N"]
     if args.impl == "reference":
-        run_reference(args, wl)
+        run_reference(args, wl, n_full)
     else:
-        run_ours(args, wl)
+        run_ours(args, wl, n_full)
 
 
 if __name__ == "__main__":

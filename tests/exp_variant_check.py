@@ -1,4 +1,4 @@
-"""Helper for tests/test_gpu_experimental.py (run as a subprocess so that a device trap in an unvalidated kernel
+"""Helper for tests/test_gpu_variants_grad_vfecov.py (run as a subprocess so that a device trap in an unvalidated kernel
 cannot poison the pytest process): runs the persistent tcgen05 SYRK with the default kernel and with the given
 environment switches on the same inputs and prints the largest difference.
 Usage: python tests/exp_variant_check.py N K S AGP_OZAKI_CLUSTER=2 [AGP_OZAKI_EPIWARPS=8 ...]"""
@@ -37,7 +37,10 @@ def main():
         outs.append(Cc.cpu().numpy())
     d = np.abs(outs[0] - outs[1]).max()
     changed = float(np.abs(outs[1] - C0.cpu().numpy()).max())
-    print("MAXDIFF %.3e CHANGED %.3e" % (d, changed))
+    rmax = P.abs().max(1).values.cpu().numpy()
+    scale = np.abs(outs[0]) + K * np.outer(rmax[:N], rmax).astype(np.float64)  # storage is N x M (column-major M x N)
+    rel = float((np.abs(outs[0] - outs[1]) / scale).max())
+    print("MAXDIFF %.3e CHANGED %.3e REL %.3e" % (d, changed, rel))
 
 
 if __name__ == "__main__":

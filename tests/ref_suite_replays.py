@@ -1,6 +1,6 @@
 """Replays of the reference's own test sets for the hot path, as plain functions of the host-API module `ag` (no pytest
 marks here): tests/test_api_on_fake_lib.py runs them on the CPU against the oracle-backed fake library (that pins the
-API semantics and the replay logic), tests/test_gpu_experimental.py runs them on a device (opt-in until they have passed
+API semantics and the replay logic), tests/test_gpu_variants_grad_vfecov.py runs them on a device (opt-in until they have passed
 there once).  File:line citations are relative to /root/reference.  Dense Sigma_y, AD (`adjoint_test`) and
 `update_posterior` cases are outside the device path and are not replayed."""
 import numpy as np

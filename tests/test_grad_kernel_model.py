@@ -1,7 +1,7 @@
 """CPU model of the experimental gradient path (abstractgps.jl_b200/csrc/grad.cu + post_logpdf_grad_impl in engine.cu): the
 same sums over the LOWER triangle with off-diagonal elements counted twice, computed from the TRANSFORMED points exactly
 as the kernel does, and the same host-side finalisation constants -- against the finite-difference-pinned gradient oracle.
-This pins the formulas; the device kernel itself is still to be validated on a GPU (tests/test_gpu_experimental.py)."""
+This pins the formulas; the device kernel itself is still to be validated on a GPU (tests/test_gpu_variants_grad_vfecov.py)."""
 import numpy as np
 import pytest
 

@@ -137,25 +137,39 @@ for mode in (1, 3, 2, 4, 7, 5, 6):  # 5: MMA-only main loop, 6: operand traffic 
     save()
 
 def cluster_part():
-    """EXPERIMENTAL kernels (A-multicast CTA pairs, 8 epilogue warps): opt-in with PROBE_CLUSTER=1 and run LAST -- a protocol bug traps and
-    kills the CUDA context, everything above is already saved."""
+    """variants of the default (v3) kernel: CTA pairs with multicast A, 4 / 8 epilogue warps; timing-only modes 3 (no
+    epilogue), 5 (MMA only), 6 (operand traffic only).  Run LAST: a protocol bug traps and kills the CUDA context,
+    everything above is already saved."""
     os.environ["AGP_OZAKI_EPI"] = "1"
     os.environ["AGP_OZAKI_CLUSTER"] = "1"
+    os.environ.pop("AGP_OZAKI_EPIWARPS", None)
     syrk(1, M)
     _, base = sample()
     res = {}
-    for tag, cl, ew in (("epiwarps8", "1", "8"), ("cluster2", "2", "4"), ("cluster2_epiwarps8", "2", "8")):
-        for epi in (1, 3):
+    for tag, cl, ew in (("epiwarps4", "1", "4"), ("cluster2", "2", "8"), ("cluster2_epiwarps4", "2", "4")):
+        for epi in (1, 3, 5, 6):
             os.environ["AGP_OZAKI_CLUSTER"], os.environ["AGP_OZAKI_EPIWARPS"] = cl, ew
             t = syrk(epi, M)
             d = {"ms": t, "syrk_ms": t - fixed, "fp64_equiv_tflops": flops / ((t - fixed) * 1e-3) / 1e12}
             if epi == 1:
                 _, got = sample()
-                d["max_abs_diff_vs_validated"] = float(max(np.max(np.abs(r - w)) for r, w in zip(got, base)))
+                d["max_abs_diff_vs_default"] = float(max(np.max(np.abs(r - w)) for r, w in zip(got, base)))
             res["%s_epi%d" % (tag, epi)] = d
             out["partA"]["variants"] = res
             save()
-    os.environ["AGP_OZAKI_CLUSTER"], os.environ["AGP_OZAKI_EPIWARPS"] = "1", "4"
+    os.environ["AGP_OZAKI_CLUSTER"] = "1"
+    os.environ.pop("AGP_OZAKI_EPIWARPS", None)
+    # the round-1 kernel on the same problem, for the record
+    os.environ["AGP_OZAKI_KERNEL"] = "2"
+    for epi in (1, 3, 5, 6):
+        t = syrk(epi, M)
+        d = {"ms": t, "syrk_ms": t - fixed, "fp64_equiv_tflops": flops / ((t - fixed) * 1e-3) / 1e12}
+        if epi == 1:
+            _, got = sample()
+            d["max_rel_diff_vs_default"] = float(max(np.max(np.abs(r - w) / sc) for r, w, sc in zip(got, base, scale)))
+        res["kernel_v2_epi%d" % epi] = d
+        save()
+    os.environ.pop("AGP_OZAKI_KERNEL", None)
 
 
 run_cluster_last = os.environ.get("PROBE_CLUSTER") == "1"
