@@ -37,6 +37,7 @@ struct agp_ctx {
   std::string err;
   int64_t info = 0;
   int memspace = AGP_MEM_HOST;
+  bool out_dev_override = false;  // internal: outputs of the current call are device pointers whatever memspace says
   double timings[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t ev[8]{};
   std::vector<cudaEvent_t> prof_ev;  // pairs around every trailing-update launch
@@ -45,7 +46,9 @@ struct agp_ctx {
   int rank = 0, nranks = 1, grid_p = 1, grid_q = 1;
   ncclComm_t nccl = nullptr;
   OzakiWs oz{};            // slice workspace of the tcgen05 fp64 path (cached across fits of the same shape)
-  int64_t oz_rows = 0;
+  OzakiWs oz2{};           // second slice buffer of the pipelined distributed schedule (panel k+1 is sliced while rest(k) runs)
+  int64_t oz_rows = 0, oz2_rows = 0;
+  cudaStream_t stream_comm = nullptr;  // panel broadcasts of the pipelined distributed schedule
   int oz_S = 7;
 };
 
@@ -66,6 +69,13 @@ struct agp_post {
   int mean_kind = 0;
   double mean_c = 0.0;
   double logdet = 0.0;
+  // distributed posterior (multi-GPU fit): the factor stays in its block-column-cyclic form (Lloc: lda x nloc*W, block
+  // column jo = lj*R + me) until the first operation that needs it whole; post_replicate() then gathers it over NVLink
+  // (one ncclBroadcast per block column from its owner) into L / Dinv and every rank holds a regular handle.
+  int dist_R = 0, dist_me = 0, dist_G = 0, dist_nloc = 0;
+  int64_t dist_W = 0;
+  void* Lloc = nullptr;
+  void* Dinv_loc = nullptr;
 };
 
 struct agp_vfe_post {
@@ -88,6 +98,10 @@ struct agp_vfe_post {
 namespace {
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int64_t env_int64(const char* name, int64_t dflt) {
+  const char* v = getenv(name);
+  return v ? atoll(v) : dflt;
+}
 
 #define CK(call)                                                                          \
   do {                                                                                    \
@@ -99,6 +113,21 @@ static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * 
       return AGP_ERR_CUDA;                                                                \
     }                                                                                     \
   } while (0)
+
+#define CKN(call)                                                                         \
+  do {                                                                                    \
+    ncclResult_t _r = (call);                                                             \
+    if (_r != ncclSuccess) {                                                              \
+      char _b[512];                                                                       \
+      snprintf(_b, sizeof(_b), "%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(_r)); \
+      ctx->err = _b;                                                                      \
+      return AGP_ERR_NCCL;                                                                \
+    }                                                                                     \
+  } while (0)
+
+template <typename T> struct NcclType;
+template <> struct NcclType<float> { static constexpr ncclDataType_t v = ncclFloat; };
+template <> struct NcclType<double> { static constexpr ncclDataType_t v = ncclDouble; };
 
 struct Scratch {  // stream-ordered allocations freed together
   agp_ctx* ctx;
@@ -130,7 +159,7 @@ int upload(agp_ctx* ctx, Scratch& sc, const void* src, size_t count, bool always
 template <typename T>
 int download(agp_ctx* ctx, void* dst, const T* src, size_t count, bool always_host) {
   if (!dst || count == 0) return AGP_OK;
-  cudaMemcpyKind kind = (!always_host && ctx->memspace == AGP_MEM_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  cudaMemcpyKind kind = (!always_host && (ctx->memspace == AGP_MEM_DEVICE || ctx->out_dev_override)) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   CK(cudaMemcpyAsync(dst, src, count * sizeof(T), kind, ctx->stream));
   return AGP_OK;
 }
@@ -229,22 +258,33 @@ static int resolve_fp64_mode(const agp_ctx* ctx, int64_t n_pad) {
 // factor one outer panel in place: Lp points at its diagonal element; Gp inner 128-blocks; rows = rows from the
 // panel's first row to the end of the (local) column storage (border rows included)
 template <typename T>
-void factor_panel(agp_ctx* ctx, T* Lp, int64_t lda, int Gp, int64_t rows, T* Dinv_p, double* logdet_part, int blk_base,
-                  int* info, cudaStream_t s) {
-  for (int g = 0; g < Gp; ++g) {
+void factor_panel_step(agp_ctx* ctx, T* Lp, int64_t lda, int Gp, int g, int64_t rows, T* Dinv_p, double* logdet_part,
+                       int blk_base, int* info, cudaStream_t s) {
+  {
     T* Akk = Lp + (int64_t)g * TILE + (int64_t)g * TILE * lda;
     const int64_t rows_below = rows - (int64_t)(g + 1) * TILE;
     bool split_done = false;
     if constexpr (std::is_same<T, double>::value) {
       if (potrf_split_enabled()) {
-        // factor on the main stream; the 128x128 inverse (only the solves need it) on stream3;
-        // the panel TRSM by blocked substitution straight from L11
         launch_potrf_factor_f64(Akk, lda, logdet_part, blk_base + g, info, s);
-        cudaEventRecord(ctx->ev_fac, s);
-        cudaStreamWaitEvent(ctx->stream3, ctx->ev_fac, 0);
-        launch_trtri_f64(Akk, lda, Dinv_p + (int64_t)g * TILE * TILE, ctx->stream3);
-        ctx->s3_dirty = true;
-        if (rows_below > 0) launch_trsm_sub_f64(Akk + TILE, lda, rows_below, Akk, s);
+        static const int64_t trsm_gemm_min = env_int64("AGP_TRSM_GEMM_MIN", 8192);
+        if (rows_below >= trsm_gemm_min) {
+          // tall panels: the substitution kernel (32 rows per CTA, 16 dependent steps) runs at ~4 TFLOP/s; the 128x128
+          // inverse (8 CTAs, 14 us) followed by ONE in-place DMMA GEMM A21 <- A21 inv(L11)' is ~3x faster from ~8k rows
+          launch_trtri_f64(Akk, lda, Dinv_p + (int64_t)g * TILE * TILE, s);
+          GemmArgs t{};
+          t.A = Akk + TILE; t.lda = lda; t.B = Dinv_p + (int64_t)g * TILE * TILE; t.ldb = TILE;
+          t.C = Akk + TILE; t.ldc = lda; t.M = rows_below; t.N = TILE; t.K = TILE;
+          launch_gemm<T>(t, s);
+        } else {
+          // short panels (latency-bound): factor on the main stream; the inverse (only the solves need it) on stream3;
+          // the panel TRSM by blocked substitution straight from L11
+          cudaEventRecord(ctx->ev_fac, s);
+          cudaStreamWaitEvent(ctx->stream3, ctx->ev_fac, 0);
+          launch_trtri_f64(Akk, lda, Dinv_p + (int64_t)g * TILE * TILE, ctx->stream3);
+          ctx->s3_dirty = true;
+          if (rows_below > 0) launch_trsm_sub_f64(Akk + TILE, lda, rows_below, Akk, s);
+        }
         split_done = true;
       }
     }
@@ -257,7 +297,7 @@ void factor_panel(agp_ctx* ctx, T* Lp, int64_t lda, int Gp, int64_t rows, T* Din
         launch_gemm<T>(t, s);
       }
     }
-    if (rows_below <= 0) continue;
+    if (rows_below <= 0) return;
     const int64_t ncols_in = (int64_t)(Gp - (g + 1)) * TILE;  // rank-128 update of the remaining inner columns
     if (ncols_in > 0) {
       GemmArgs u{};
@@ -267,6 +307,13 @@ void factor_panel(agp_ctx* ctx, T* Lp, int64_t lda, int Gp, int64_t rows, T* Din
       launch_gemm<T>(u, s);
     }
   }
+}
+
+// factor one outer panel in place (all inner blocks)
+template <typename T>
+void factor_panel(agp_ctx* ctx, T* Lp, int64_t lda, int Gp, int64_t rows, T* Dinv_p, double* logdet_part, int blk_base,
+                  int* info, cudaStream_t s) {
+  for (int g = 0; g < Gp; ++g) factor_panel_step<T>(ctx, Lp, lda, Gp, g, rows, Dinv_p, logdet_part, blk_base, info, s);
 }
 
 template <typename T>
@@ -619,10 +666,87 @@ int post_mean_var_impl(agp_post* p, int layout, const void* Xs, int64_t M, const
   return AGP_OK;
 }
 
+
+// ---- distributed posterior: gather the block-column-cyclic factor so that every rank holds it whole (SURVEY s8e:
+// "partition the M test points across GPUs if the factor is replicated").  Collective: every rank of the communicator
+// calls it at the same point (all handle operations are SPMD, like agp_fit on a distributed context).
+template <typename T>
+int post_replicate(agp_post* p) {
+  if (!p->Lloc) return AGP_OK;
+  agp_ctx* ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  CK(cudaSetDevice(ctx->device));
+  const int R = p->dist_R, me = p->dist_me, G = p->dist_G;
+  const int64_t W = p->dist_W, lda = p->lda, n_pad = p->n_pad;
+  const int nto = (int)(n_pad / W), nt = (int)(n_pad / TILE);
+  void *Lf = nullptr, *Df = nullptr;
+  CK(cudaMallocAsync(&Lf, (size_t)lda * n_pad * sizeof(T), s));
+  CK(cudaMallocAsync(&Df, (size_t)nt * TILE * TILE * sizeof(T), s));
+  for (int jo = 0; jo < nto; ++jo) {
+    const int owner = jo % R, lj = jo / R;
+    T* dstL = (T*)Lf + (int64_t)jo * W * lda;
+    T* dstD = (T*)Df + (int64_t)jo * G * TILE * TILE;
+    const T* srcL = owner == me ? (const T*)p->Lloc + (int64_t)lj * W * lda : dstL;
+    const T* srcD = owner == me ? (const T*)p->Dinv_loc + (int64_t)lj * G * TILE * TILE : dstD;
+    CKN(ncclBroadcast(srcL, dstL, (size_t)lda * W, NcclType<T>::v, owner, ctx->nccl, s));
+    CKN(ncclBroadcast(srcD, dstD, (size_t)G * TILE * TILE, NcclType<T>::v, owner, ctx->nccl, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  cudaFreeAsync(p->Lloc, s);
+  cudaFreeAsync(p->Dinv_loc, s);
+  p->Lloc = nullptr; p->Dinv_loc = nullptr;
+  p->L = Lf; p->Dinv = Df;
+  return AGP_OK;
+}
+
+// mean_and_var over a distributed posterior: the factor is replicated (once), the test points are partitioned over the
+// ranks (point-major inputs), every rank predicts its slice with the single-GPU path and the M-vectors are exchanged
+// with one broadcast per rank.  Every rank returns the complete outputs.
+template <typename T>
+int post_mean_var_dist(agp_post* p, int layout, const void* Xs, int64_t M, const agp_mean* mean_s,
+                       const agp_noise* noise_s, void* mean_out, void* var_out) {
+  agp_ctx* ctx = p->ctx;
+  int rc = post_replicate<T>(p);
+  if (rc) return rc;
+  const int R = p->dist_R, me = p->dist_me;
+  if (layout != AGP_POINT_MAJOR || M < 2 * R)  // small or feature-major: every rank computes everything (same result)
+    return post_mean_var_impl<T>(p, layout, Xs, M, mean_s, noise_s, mean_out, var_out);
+  cudaStream_t s = ctx->stream;
+  Scratch sc(ctx);
+  const int64_t per = (M + R - 1) / R, lo = (int64_t)me * per < M ? (int64_t)me * per : M;
+  const int64_t hi = lo + per < M ? lo + per : M;
+  void* tmp = nullptr;
+  CK(sc.alloc(&tmp, (size_t)2 * M * sizeof(T)));
+  T* mu_all = (T*)tmp; T* var_all = mu_all + M;
+  agp_mean ms; agp_noise ns;
+  const agp_mean* msp = nullptr; const agp_noise* nsp = nullptr;
+  if (mean_s) { ms = *mean_s; if (ms.kind == 2 && ms.v) ms.v = (const T*)ms.v + lo; msp = &ms; }
+  if (noise_s) { ns = *noise_s; if (ns.kind == 1 && ns.v) ns.v = (const T*)ns.v + lo; nsp = &ns; }
+  if (hi > lo) {
+    ctx->out_dev_override = true;
+    rc = post_mean_var_impl<T>(p, layout, (const char*)Xs + (size_t)lo * p->D * sizeof(T), hi - lo, msp, nsp,
+                               mean_out ? mu_all + lo : nullptr, var_out ? var_all + lo : nullptr);
+    ctx->out_dev_override = false;
+    if (rc) return rc;
+  }
+  for (int r = 0; r < R; ++r) {
+    const int64_t rlo = (int64_t)r * per < M ? (int64_t)r * per : M, rhi = rlo + per < M ? rlo + per : M;
+    if (rhi <= rlo) continue;
+    if (mean_out) CKN(ncclBroadcast(mu_all + rlo, mu_all + rlo, (size_t)(rhi - rlo), NcclType<T>::v, r, ctx->nccl, s));
+    if (var_out) CKN(ncclBroadcast(var_all + rlo, var_all + rlo, (size_t)(rhi - rlo), NcclType<T>::v, r, ctx->nccl, s));
+  }
+  if (mean_out) { rc = download<T>(ctx, mean_out, mu_all, (size_t)M, false); if (rc) return rc; }
+  if (var_out) { rc = download<T>(ctx, var_out, var_all, (size_t)M, false); if (rc) return rc; }
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  return AGP_OK;
+}
+
 template <typename T>
 int post_mean_cov_impl(agp_post* p, int layout, const void* Xs, int64_t M, const agp_mean* mean_s, void* mean_out,
                        void* cov_out) {
   agp_ctx* ctx = p->ctx;
+  { int rrc = post_replicate<T>(p); if (rrc) return rrc; }
   cudaStream_t s = ctx->stream;
   CK(cudaSetDevice(ctx->device));
   if (M <= 0) return AGP_OK;
@@ -671,6 +795,7 @@ int post_cond_impl(agp_post* p, int layout, const void* Xs, int64_t M, const agp
                    const agp_noise* noise_s, const void* Y, int S, void* logpdf_out, const void* Z, int Sz,
                    void* rand_out) {
   agp_ctx* ctx = p->ctx;
+  { int rrc = post_replicate<T>(p); if (rrc) return rrc; }
   cudaStream_t s = ctx->stream;
   CK(cudaSetDevice(ctx->device));
   if (M <= 0) { ctx->err = "M must be positive"; return AGP_ERR_DIM_MISMATCH; }
@@ -773,6 +898,7 @@ int post_cond_impl(agp_post* p, int layout, const void* Xs, int64_t M, const agp
 template <typename T>
 int post_logpdf_grad_impl(agp_post* p, double* grad_out, void* noise_diag_out) {
   agp_ctx* ctx = p->ctx;
+  { int rrc = post_replicate<T>(p); if (rrc) return rrc; }
   cudaStream_t s = ctx->stream;
   CK(cudaSetDevice(ctx->device));
   if (p->valid || p->segs.size() > 1) { ctx->err = "gradient of an extended (sequentially conditioned) posterior is unsupported"; return AGP_ERR_UNSUPPORTED; }
@@ -824,6 +950,7 @@ int post_logpdf_grad_impl(agp_post* p, double* grad_out, void* noise_diag_out) {
 template <typename T>
 int post_solve_lower_impl(agp_post* p, const void* Bh, int64_t nrhs, void* V_out) {
   agp_ctx* ctx = p->ctx;
+  { int rrc = post_replicate<T>(p); if (rrc) return rrc; }
   cudaStream_t s = ctx->stream;
   CK(cudaSetDevice(ctx->device));
   if (nrhs <= 0) return AGP_OK;
@@ -856,6 +983,7 @@ int post_solve_lower_impl(agp_post* p, const void* Bh, int64_t nrhs, void* V_out
 template <typename T>
 int post_export_impl(agp_post* p, void* U_out) {
   agp_ctx* ctx = p->ctx;
+  { int rrc = post_replicate<T>(p); if (rrc) return rrc; }
   cudaStream_t s = ctx->stream;
   CK(cudaSetDevice(ctx->device));
   Scratch sc(ctx);
@@ -892,6 +1020,7 @@ template <typename T>
 int post_extend_impl(agp_post* p, int layout, const void* X2, int64_t N2, const void* y2, const agp_mean* mean2,
                      const agp_noise* noise2, void* alpha_out, agp_post** post_out) {
   agp_ctx* ctx = p->ctx;
+  { int rrc = post_replicate<T>(p); if (rrc) return rrc; }
   cudaStream_t s = ctx->stream;
   CK(cudaSetDevice(ctx->device));
   if (N2 <= 0) { ctx->err = "N2 must be positive"; return AGP_ERR_DIM_MISMATCH; }
@@ -1086,20 +1215,7 @@ int gram_impl(agp_ctx* ctx, const agp_kernel* k, int layout, const void* X, int6
   return AGP_OK;
 }
 
-#define CKN(call)                                                                         \
-  do {                                                                                    \
-    ncclResult_t _r = (call);                                                             \
-    if (_r != ncclSuccess) {                                                              \
-      char _b[512];                                                                       \
-      snprintf(_b, sizeof(_b), "%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(_r)); \
-      ctx->err = _b;                                                                      \
-      return AGP_ERR_NCCL;                                                                \
-    }                                                                                     \
-  } while (0)
 
-template <typename T> struct NcclType;
-template <> struct NcclType<float> { static constexpr ncclDataType_t v = ncclFloat; };
-template <> struct NcclType<double> { static constexpr ncclDataType_t v = ncclDouble; };
 
 
 // ---- VFE (Titsias) : elbo / dtc / approximate posterior --------------------------------------------
@@ -1436,11 +1552,13 @@ int vfe_cond_impl(agp_vfe_post* p, int layout, const void* Xs, int64_t M, const 
 
 template <typename T>
 int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_noise* noise, int layout,
-                  const void* X, int64_t N, int D, const void* Y, int S, void* logpdf_out, void* alpha_out) {
+                  const void* X, int64_t N, int D, const void* Y, int S, void* logpdf_out, void* alpha_out,
+                  agp_post** post_out) {
   int rc = check_kernel(ctx, k, D);
   if (rc) return rc;
   if (N <= 0) { ctx->err = "N must be positive"; return AGP_ERR_DIM_MISMATCH; }
   if (S < 1 || S > TILE || !Y) { ctx->err = "distributed fit needs 1..128 right-hand sides"; return AGP_ERR_UNSUPPORTED; }
+  const bool keep = post_out != nullptr;
   static const agp_mean zero_mean{0, 0.0, nullptr};
   static const agp_noise default_noise{0, 1e-18, nullptr};
   if (!mean) mean = &zero_mean;
@@ -1464,15 +1582,33 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
   if (mean->kind == 2) { rc = upload<T>(ctx, sc, mean->v, N, true, &mean_d); if (rc) return rc; }
   if (noise->kind == 1) { rc = upload<T>(ctx, sc, noise->v, N, true, &noise_d); if (rc) return rc; }
   rc = upload<T>(ctx, sc, Y, (size_t)N * S, false, &Yd); if (rc) return rc;
-  rc = prep_points<T>(ctx, sc, k, ard_d, layout, X, N, n_pad, D, &Xt, false); if (rc) return rc;
+  rc = prep_points<T>(ctx, sc, k, ard_d, layout, X, N, n_pad, D, &Xt, keep); if (rc) return rc;
   CK(cudaEventRecord(ctx->ev[1], s));
   void* tmp = nullptr;
-  CK(sc.alloc(&tmp, (size_t)lda * (nloc > 0 ? nloc : 1) * W * sizeof(T)));
-  T* L = (T*)tmp;
-  CK(sc.alloc(&tmp, (size_t)(nloc > 0 ? nloc : 1) * G * TILE * TILE * sizeof(T)));
-  T* Dinv = (T*)tmp;  // inverse diagonal blocks of the LOCAL 128-blocks
-  CK(sc.alloc(&tmp, (size_t)2 * lda * W * sizeof(T)));
-  T* P[2] = {(T*)tmp, (T*)tmp + lda * W};  // double-buffered packed panels (rows_below x W, ld = rows_below)
+  // the factor and its inverse diagonal blocks outlive the call when a posterior handle is requested
+  agp_post* post = nullptr;
+  void *Lv = nullptr, *Dv = nullptr;
+  CK(cudaMallocAsync(&Lv, (size_t)lda * (nloc > 0 ? nloc : 1) * W * sizeof(T), s));
+  CK(cudaMallocAsync(&Dv, (size_t)(nloc > 0 ? nloc : 1) * G * TILE * TILE * sizeof(T), s));
+  if (keep) {
+    post = new agp_post();
+    post->ctx = ctx; post->dtype = sizeof(T) == 8 ? AGP_F64 : AGP_F32;
+    post->n = N; post->n_pad = n_pad; post->lda = lda; post->D = D;
+    post->Lloc = Lv; post->Dinv_loc = Dv; post->Xt = Xt;
+    post->dist_R = R; post->dist_me = me; post->dist_G = G; post->dist_nloc = nloc; post->dist_W = W;
+    post->k = *k; post->k.ard = nullptr;
+    post->mean_kind = mean->kind == 2 ? 0 : mean->kind; post->mean_c = mean->c;
+    post->segs.push_back({0, N});
+    if (ard_d) { sc.release(ard_d); post->ard = ard_d; }
+  } else {
+    sc.ptrs.push_back(Lv); sc.ptrs.push_back(Dv);
+  }
+  struct PostGuard { agp_post* p; ~PostGuard() { if (p) agp_post_free(p); } } guard{post};  // freed on every error return
+  T* L = (T*)Lv;
+  T* Dinv = (T*)Dv;  // inverse diagonal blocks of the LOCAL 128-blocks
+  CK(sc.alloc(&tmp, (size_t)3 * lda * W * sizeof(T)));
+  T* P[3] = {(T*)tmp, (T*)tmp + lda * W, (T*)tmp + 2 * lda * W};  // packed panels (rows_below x W, ld = rows_below): two in
+                                                                   // flight in the default schedule, three in the pipelined one
   CK(sc.alloc(&tmp, (size_t)(nt + TILE + 4) * sizeof(double)));
   double* dscal = (double*)tmp;  // [0..nt) logdet parts, [nt..nt+TILE) sqmahal, [nt+TILE] logdet
   CK(cudaMemsetAsync(dscal, 0, (size_t)(nt + TILE + 4) * sizeof(double), s));
@@ -1495,6 +1631,22 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
       if (ctx->oz.SL) oz = &ctx->oz;
     }
   }
+  // schedule: 2 = pipelined (default for R > 1; see the loop below), 1 = round-1 owner-first experiment, 0 = plain look-ahead
+  int dist_sched = (R > 1) ? 2 : 0;
+  { const char* e1 = getenv("AGP_DIST_SCHED"); if (e1) dist_sched = atoi(e1); }
+  const OzakiWs* oz_b = nullptr;  // second slice buffer (pipelined schedule only)
+  if constexpr (std::is_same<T, double>::value) {
+    if (dist_sched == 2 && oz) {
+      if (!ctx->oz2.SL || ctx->oz2.K != W || ctx->oz2_rows < lda || ctx->oz2.S != ctx->oz_S) {
+        if (ctx->oz2.SL) ozaki_ws_destroy(&ctx->oz2, s);
+        if (ozaki_ws_create(&ctx->oz2, lda, (int)W, ctx->oz_S, s) == 0) ctx->oz2_rows = lda;
+        else { memset(&ctx->oz2, 0, sizeof(ctx->oz2)); ctx->oz2_rows = 0; }
+      }
+      oz_b = ctx->oz2.SL ? &ctx->oz2 : nullptr;
+      if (!oz_b) dist_sched = 0;
+    }
+  }
+  if (dist_sched == 2 && !ctx->stream_comm) CK(cudaStreamCreateWithFlags(&ctx->stream_comm, cudaStreamNonBlocking));
 
   // ---- Gram: only the local outer blocks, lower part, + border rows
   for (int lj = 0; lj < nloc; ++lj) {
@@ -1515,6 +1667,7 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
     while ((int64_t)lj * R + me <= kk) ++lj;
     return lj;
   };
+  const OzakiWs* oz_cur = oz;  // slice buffer the `trailing` launches read (the pipelined schedule alternates two)
   auto trailing = [&](int kk, T* Pk, int lj_lo, int lj_hi, bool use_oz, cudaStream_t st) {  // local outer blocks [lj_lo, lj_hi)
     if (lj_lo >= lj_hi) return;
     const int64_t rows_below = lda - (int64_t)(kk + 1) * W;
@@ -1524,7 +1677,7 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
     if (ctx->profile) cudaEventRecord(prof_event(ctx), st);
     bool done = false;
     if constexpr (std::is_same<T, double>::value) {
-      if (use_oz) { ozaki_syrk(*oz, C, lda, rows_below, Ncols, 1, (int64_t)R * W, W, b_off, 0, st); done = true; }
+      if (use_oz) { ozaki_syrk(*oz_cur, C, lda, rows_below, Ncols, 1, (int64_t)R * W, W, b_off, 0, st); done = true; }
     }
     if (!done) {
       GemmArgs u{};
@@ -1546,8 +1699,7 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
   bool sched2 = false;
   int reserve_sms = 16;
   if (R > 1) {
-    const char* e1 = getenv("AGP_DIST_SCHED");
-    sched2 = e1 && atoi(e1) == 1;
+    sched2 = dist_sched == 1;
     const char* e2 = getenv("AGP_DIST_RESERVE_SMS");
     if (e2) reserve_sms = atoi(e2);
     if (reserve_sms < 0 || reserve_sms > 64) reserve_sms = 16;
@@ -1562,6 +1714,104 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
     if (oz) oz->max_ctas = 0;
     cudaEventRecord(e_rest, s2);
   };
+  if (dist_sched == 2) {
+    // ---- PIPELINED schedule.  The critical path of a 1 x R factorisation is the owner chain
+    //   [panel k-1 received] -> update of block column k -> factor panel k -> broadcast panel k,
+    // so (1) the owner factors its panel BEFORE its own rest update of the previous step (deferred to stream2 behind the
+    // factorisation); (2) the panel is broadcast in G column pieces on a communication stream, each as soon as its inner
+    // block is final, so only the last piece is exposed; (3) rest updates leave `reserve_sms` SMs to the NCCL kernels;
+    // (4) panels rotate through three buffers and slices through two, so receiving / slicing panel k+1 never waits for
+    // the rest update of step k.  Every rank issues the same collectives in the same order on stream_comm; the
+    // collectives that follow the factorisation are issued after the streams are joined.
+    cudaStream_t scm = ctx->stream_comm;
+    std::vector<cudaEvent_t> e_rest((size_t)nto, nullptr);
+    auto ev = [&]() { return dep_event(ctx, ev_idx++); };
+    cudaEvent_t e_start = ev();
+    cudaEventRecord(e_start, s);
+    cudaStreamWaitEvent(scm, e_start, 0);  // the Gram (and the previous call) precede the first broadcast
+    cudaStreamWaitEvent(s2, e_start, 0);
+    struct Deferred { bool on; int kk; T* Pk; int lo, hi; bool use_oz; const OzakiWs* ws; cudaEvent_t e_prep; } dfr{false, 0, nullptr, 0, 0, false, nullptr, nullptr};
+    auto issue_rest = [&](int kk, T* Pk, int lo, int hi, bool use_oz, const OzakiWs* ws) {
+      e_rest[(size_t)kk] = ev();
+      if (ws) ws->max_ctas = nsm_dev - reserve_sms;
+      oz_cur = ws;
+      trailing(kk, Pk, lo, hi, use_oz, s2);
+      if (ws) ws->max_ctas = 0;
+      cudaEventRecord(e_rest[(size_t)kk], s2);
+    };
+    for (int kk = 0; kk < nto; ++kk) {
+      const int owner = kk % R;
+      const int64_t rows_below = lda - (int64_t)(kk + 1) * W;
+      T* Pk = P[kk % 3];
+      const OzakiWs* ws_k = (kk & 1) ? oz_b : oz;
+      if (kk >= 3 && e_rest[(size_t)kk - 3]) cudaStreamWaitEvent(scm, e_rest[(size_t)kk - 3], 0);  // P[kk % 3] is free again
+      if (owner == me) {
+        const int lk = kk / R;
+        T* Lp = L + (int64_t)kk * W + (int64_t)lk * W * lda;
+        if (kk >= 3 && e_rest[(size_t)kk - 3]) cudaStreamWaitEvent(s, e_rest[(size_t)kk - 3], 0);  // the pack below writes P[kk % 3]
+        for (int g = 0; g < G; ++g) {
+          // inner block g of the panel: rows from the panel's diagonal block down to the border
+          factor_panel_step<T>(ctx, Lp, lda, G, g, lda - (int64_t)kk * W, Dinv + (int64_t)lk * G * TILE * TILE, dscal, kk * G, dinfo, s);
+          launch_copy2d<T>(Lp + W + (int64_t)g * TILE * lda, lda, Pk + (int64_t)g * TILE * rows_below, rows_below, rows_below, TILE, s);
+          cudaEvent_t e_col = ev();
+          cudaEventRecord(e_col, s);
+          cudaStreamWaitEvent(scm, e_col, 0);
+          if (rows_below > 0)
+            CKN(ncclBroadcast(Pk + (int64_t)g * TILE * rows_below, Pk + (int64_t)g * TILE * rows_below, (size_t)rows_below * TILE,
+                              NcclType<T>::v, owner, ctx->nccl, scm));
+        }
+        if (dfr.on) {  // this rank's rest update of step kk-1, behind the factorisation it must not delay
+          cudaEvent_t e_fact = ev();
+          cudaEventRecord(e_fact, s);
+          cudaStreamWaitEvent(s2, e_fact, 0);
+          issue_rest(dfr.kk, dfr.Pk, dfr.lo, dfr.hi, dfr.use_oz, dfr.ws);
+          dfr.on = false;
+        }
+      } else if (rows_below > 0) {
+        for (int g = 0; g < G; ++g)
+          CKN(ncclBroadcast(Pk + (int64_t)g * TILE * rows_below, Pk + (int64_t)g * TILE * rows_below, (size_t)rows_below * TILE,
+                            NcclType<T>::v, owner, ctx->nccl, scm));
+      }
+      if (kk == nto - 1) break;
+      cudaEvent_t e_recv = ev();
+      cudaEventRecord(e_recv, scm);
+      cudaStreamWaitEvent(s, e_recv, 0);
+      if (kk >= 2 && e_rest[(size_t)kk - 2]) cudaStreamWaitEvent(s, e_rest[(size_t)kk - 2], 0);  // slice buffer kk & 1 is free again
+      bool use_oz = false;
+      if constexpr (std::is_same<T, double>::value) {
+        if (ws_k && (int64_t)(nto - 1 - kk) * W >= 2 * TILE) {
+          ozaki_prepare(*ws_k, (const double*)Pk, rows_below, rows_below, s);
+          use_oz = true;
+        }
+      }
+      cudaEvent_t e_prep = ev();
+      cudaEventRecord(e_prep, s);
+      const int lj_first = local_first_after(kk);
+      int lj_bulk = lj_first;
+      const bool next_is_mine = (kk + 1) % R == me;
+      if (next_is_mine) {  // the next panel's block column first, on the main stream; its factorisation follows
+        oz_cur = ws_k;
+        trailing(kk, Pk, lj_first, lj_first + 1, use_oz, s);
+        lj_bulk = lj_first + 1;
+      }
+      if (next_is_mine) {
+        dfr = Deferred{true, kk, Pk, lj_bulk, nloc, use_oz, use_oz ? ws_k : nullptr, e_prep};
+      } else {
+        cudaStreamWaitEvent(s2, e_prep, 0);
+        issue_rest(kk, Pk, lj_bulk, nloc, use_oz, use_oz ? ws_k : nullptr);
+      }
+    }
+    if (dfr.on) {  // cannot happen (the last step has no trailing work), kept for safety
+      cudaStreamWaitEvent(s2, dfr.e_prep, 0);
+      issue_rest(dfr.kk, dfr.Pk, dfr.lo, dfr.hi, dfr.use_oz, dfr.ws);
+    }
+    cudaEvent_t e_s2 = ev(), e_cm = ev();
+    cudaEventRecord(e_s2, s2);
+    cudaEventRecord(e_cm, scm);
+    cudaStreamWaitEvent(s, e_s2, 0);
+    cudaStreamWaitEvent(s, e_cm, 0);
+    oz_cur = oz;
+  } else
   for (int kk = 0; kk < nto; ++kk) {
     const int owner = kk % R;
     const int64_t rows_below = lda - (int64_t)(kk + 1) * W;
@@ -1618,14 +1868,21 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
   }
   for (int sI = 0; sI < S; ++sI) launch_sumsq<T>(rwork + (size_t)sI * n_pad, n_pad, dscal + nt + sI, s);
   if (R > 1) CKN(ncclAllReduce(dscal, dscal, (size_t)(nt + TILE), ncclDouble, ncclSum, ctx->nccl, s));
-  // ---- distributed backward substitution for column 0: alpha = L^-T v  (128-block granularity)
-  for (int i = nt - 1; i >= 0; --i) {
-    const int io = i / G, owner = io % R;
-    T* a_i = alpha + (int64_t)i * TILE;
-    if (owner == me)
-      launch_bwd_diag<T>(Dinv + ((int64_t)(io / R) * G + (i % G)) * TILE * TILE, rwork + (int64_t)i * TILE, a_i, s);
-    if (R > 1) CKN(ncclBroadcast(a_i, a_i, TILE, NcclType<T>::v, owner, ctx->nccl, s));
-    if (i > 0) launch_bwd_update_local<T>(L, lda, i, a_i, rwork, nloc * G, me, R, G, s);
+  // ---- distributed backward substitution for column 0: alpha = L^-T v.  The owner of an outer block holds its G diagonal
+  // blocks and every tile between them, so it resolves the whole block locally (G dependent steps) and ONE broadcast per
+  // outer block ships G*128 values (128 collectives at C4, was 512); the other ranks then apply the block in one launch.
+  for (int io = nto - 1; io >= 0; --io) {
+    const int owner = io % R, i_lo = io * G;
+    if (owner == me) {
+      for (int i = i_lo + G - 1; i >= i_lo; --i) {
+        T* a_i = alpha + (int64_t)i * TILE;
+        launch_bwd_diag<T>(Dinv + ((int64_t)(io / R) * G + (i % G)) * TILE * TILE, rwork + (int64_t)i * TILE, a_i, s);
+        if (i > 0) launch_bwd_update_local<T>(L, lda, i, a_i, rwork, nloc * G, me, R, G, s);
+      }
+    }
+    if (R > 1) CKN(ncclBroadcast(alpha + (int64_t)i_lo * TILE, alpha + (int64_t)i_lo * TILE, (size_t)G * TILE, NcclType<T>::v, owner, ctx->nccl, s));
+    if (owner != me && i_lo > 0)
+      launch_bwd_update_local_multi<T>(L, lda, i_lo, G, alpha + (int64_t)i_lo * TILE, rwork, nloc * G, me, R, G, s);
   }
   launch_finalize_logpdf<T>(dscal, nt, dscal + nt, S, N, lp_d, dscal + nt + TILE, s);
   CK(cudaEventRecord(ctx->ev[4], s));
@@ -1647,6 +1904,19 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
     ctx->info = h_info;
     ctx->err = "matrix is not positive definite (distributed Cholesky)";
     return AGP_ERR_NOT_POSDEF;
+  }
+  if (keep) {  // alpha, delta = y - m (first column) and log det move into the handle
+    CK(cudaMallocAsync(&post->alpha, (size_t)n_pad * sizeof(T), s));
+    CK(cudaMallocAsync(&post->delta, (size_t)n_pad * sizeof(T), s));
+    CK(cudaMemcpyAsync(post->alpha, alpha, (size_t)n_pad * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemsetAsync(post->delta, 0, (size_t)n_pad * sizeof(T), s));
+    launch_sub_mean<T>(Yd, N, mean->kind, mean->c, mean_d, (T*)post->delta, s);
+    double h_logdet = 0.0;
+    CK(cudaMemcpyAsync(&h_logdet, dscal + nt + TILE, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    post->logdet = h_logdet;
+    guard.p = nullptr;
+    *post_out = post;
   }
   return AGP_OK;
 }
@@ -1710,6 +1980,8 @@ int32_t agp_destroy(agp_ctx* ctx) {
   for (auto e : ctx->prof_ev) cudaEventDestroy(e);
   for (auto e : ctx->dep_ev) cudaEventDestroy(e);
   if (ctx->oz.SL) ozaki_ws_destroy(&ctx->oz, ctx->stream);
+  if (ctx->oz2.SL) ozaki_ws_destroy(&ctx->oz2, ctx->stream);
+  if (ctx->stream_comm) { cudaStreamSynchronize(ctx->stream_comm); cudaStreamDestroy(ctx->stream_comm); }
   if (ctx->nccl) ncclCommDestroy(ctx->nccl);
   cudaEventDestroy(ctx->ev_s3);
   cudaEventDestroy(ctx->ev_fac);
@@ -1765,9 +2037,8 @@ int32_t agp_fit(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, const agp_mean
   if (!ctx) return AGP_ERR_INVALID;
   if (post_out) *post_out = nullptr;
   if (ctx->nccl) {  // distributed context: every rank calls with the same (replicated) inputs
-    if (post_out) { ctx->err = "posterior handles are single-GPU in this build; distributed fit returns logpdf and alpha"; }
-    return DISPATCH(dtype, fit_dist_impl<float>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out),
-                    fit_dist_impl<double>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out));
+    return DISPATCH(dtype, fit_dist_impl<float>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out, post_out),
+                    fit_dist_impl<double>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out, post_out));
   }
   return DISPATCH(dtype,
                   fit_impl<float>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out, post_out, nullptr, nullptr, nullptr),
@@ -1777,6 +2048,9 @@ int32_t agp_fit(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, const agp_mean
 int32_t agp_post_mean_var(agp_post* p, int32_t layout, const void* Xs, int64_t M, const agp_mean* mean_s,
                           const agp_noise* noise_s, void* mean_out, void* var_out) {
   if (!p) return AGP_ERR_INVALID;
+  if (p->dist_R > 1)
+    return DISPATCH(p->dtype, post_mean_var_dist<float>(p, layout, Xs, M, mean_s, noise_s, mean_out, var_out),
+                    post_mean_var_dist<double>(p, layout, Xs, M, mean_s, noise_s, mean_out, var_out));
   return DISPATCH(p->dtype, post_mean_var_impl<float>(p, layout, Xs, M, mean_s, noise_s, mean_out, var_out),
                   post_mean_var_impl<double>(p, layout, Xs, M, mean_s, noise_s, mean_out, var_out));
 }
@@ -1838,6 +2112,8 @@ int32_t agp_post_free(agp_post* p) {
   if (p->ard) cudaFreeAsync(p->ard, s);
   if (p->delta) cudaFreeAsync(p->delta, s);
   if (p->valid) cudaFreeAsync(p->valid, s);
+  if (p->Lloc) cudaFreeAsync(p->Lloc, s);
+  if (p->Dinv_loc) cudaFreeAsync(p->Dinv_loc, s);
   delete p;
   return AGP_OK;
 }
@@ -1970,7 +2246,11 @@ int32_t agp_init_dist(agp_ctx** out, int32_t device, int32_t rank, int32_t nrank
   ctx->rank = rank; ctx->nranks = nranks; ctx->grid_p = grid_p; ctx->grid_q = grid_q;
   ncclUniqueId id;
   memcpy(&id, id128, 128);
-  if (ncclCommInitRank(&ctx->nccl, nranks, id, rank) != ncclSuccess) {
+  // the panel broadcasts run beside the persistent trailing-update kernel, which leaves a few SMs free: keep NCCL's
+  // kernels within that reserve
+  ncclConfig_t ncfg = NCCL_CONFIG_INITIALIZER;
+  ncfg.maxCTAs = env_int("AGP_NCCL_MAX_CTAS", 16);
+  if (ncclCommInitRankConfig(&ctx->nccl, nranks, id, rank, &ncfg) != ncclSuccess) {
     agp_destroy(ctx);
     *out = nullptr;
     return AGP_ERR_NCCL;

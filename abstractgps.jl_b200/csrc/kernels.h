@@ -79,6 +79,8 @@ template <typename T> void launch_bwd_solve(const T* A, int64_t lda, const T* Di
 template <typename T> void launch_bwd_diag(const T* Dinv_i, const T* r_i, T* alpha_i, cudaStream_t s);
 template <typename T> void launch_bwd_update_local(const T* Lloc, int64_t lda, int i_blk, const T* alpha_i, T* r, int nloc,
                                                    int rank, int nranks, int G, cudaStream_t s);
+template <typename T> void launch_bwd_update_local_multi(const T* Lloc, int64_t lda, int i_lo, int Gn, const T* alpha_lo, T* r,
+                                                         int nloc, int rank, int nranks, int G, cudaStream_t s);
 template <typename T> void launch_finalize_logpdf(const double* logdet_part, int nblk, const double* sq, int S,
                                                   int64_t n, T* out, double* logdet_out, cudaStream_t s);
 // mu[j] = mean_j + sum_i B[i + j*ldb] * alpha[i]

@@ -217,6 +217,28 @@ __global__ void __launch_bounds__(256) bwd_update_local_kernel(const T* __restri
   if (h == 0) r[j * TB + o] -= (T)acc;
 }
 
+// the same for a whole distribution block of G inner 128-blocks received in ONE broadcast: r_j -= sum_g L(i_lo+g, j)' alpha_{i_lo+g}
+// for the local column blocks j < i_lo (a rank that does not own the block has no column inside it)
+template <typename T>
+__global__ void __launch_bounds__(256) bwd_update_local_multi_kernel(const T* __restrict__ Lloc, int64_t lda, int i_lo, int Gn,
+                                                                      const T* __restrict__ alpha_lo, T* __restrict__ r,
+                                                                      int rank, int nranks, int G) {
+  __shared__ T ak[8 * TB];
+  const int lj = blockIdx.x;
+  const int64_t j = ((int64_t)(lj / G) * nranks + rank) * G + (lj % G);
+  if (j >= i_lo) return;
+  const int tid = threadIdx.x, o = tid >> 1, h = tid & 1;
+  for (int q = tid; q < Gn * TB; q += 256) ak[q] = alpha_lo[q];
+  __syncthreads();
+  double acc = 0.0;
+  for (int g = 0; g < Gn; ++g) {
+    const T* tile = Lloc + (int64_t)(i_lo + g) * TB + ((int64_t)lj * TB + o) * lda;
+    acc += col_dot_half<T>(tile, ak + g * TB, h);
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (h == 0) r[j * TB + o] -= (T)acc;
+}
+
 template <typename T>
 __global__ void finalize_logpdf_kernel(const double* __restrict__ logdet_part, int nblk, const double* __restrict__ sq,
                                        int S, int64_t n, T* __restrict__ out, double* __restrict__ logdet_out) {
@@ -589,6 +611,15 @@ void launch_bwd_update_local(const T* Lloc, int64_t lda, int i_blk, const T* alp
   bwd_update_local_kernel<T><<<nloc, 256, 0, s>>>(Lloc, lda, i_blk, alpha_i, r, rank, nranks, G);
   agp_count_launch();
 }
+template <typename T>
+void launch_bwd_update_local_multi(const T* Lloc, int64_t lda, int i_lo, int Gn, const T* alpha_lo, T* r, int nloc, int rank,
+                                   int nranks, int G, cudaStream_t s) {
+  if (nloc <= 0 || Gn <= 0) return;
+  bwd_update_local_multi_kernel<T><<<nloc, 256, 0, s>>>(Lloc, lda, i_lo, Gn, alpha_lo, r, rank, nranks, G);
+  agp_count_launch();
+}
+template void launch_bwd_update_local_multi<float>(const float*, int64_t, int, int, const float*, float*, int, int, int, int, cudaStream_t);
+template void launch_bwd_update_local_multi<double>(const double*, int64_t, int, int, const double*, double*, int, int, int, int, cudaStream_t);
 
 // explicit instantiations
 template void launch_border_init_cols<float>(float*, int64_t, int64_t, int64_t, int64_t, int64_t, const float*, int64_t, int, int, double, const float*, cudaStream_t);

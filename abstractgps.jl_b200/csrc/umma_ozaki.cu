@@ -35,16 +35,29 @@ constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KB = 64, OZ_STAGES = 2;
 // ---------------------------------------------------------------------------------------------
 // pre-pass 1: row exponents
 // ---------------------------------------------------------------------------------------------
-__global__ void ozaki_rowscale_kernel(const double* __restrict__ P, int64_t lda, int64_t m, int K, double* __restrict__ rscale,
-                                      double* __restrict__ rinv) {
-  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (row >= m) return;
+__global__ void __launch_bounds__(256) ozaki_rowscale_kernel(const double* __restrict__ P, int64_t lda, int64_t m, int K,
+                                                             double* __restrict__ rscale, double* __restrict__ rinv) {
+  // 32 rows x 8 column groups per block: every load instruction of a warp covers 32 consecutive rows (256 B) of one
+  // column, 8 warps scan interleaved columns, the row maxima meet in shared memory
+  __shared__ double part[8][33];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int64_t row = blockIdx.x * 32ll + x;
   double mx = 0.0;
-  for (int k = 0; k < K; ++k) mx = fmax(mx, fabs(P[row + (int64_t)k * lda]));
-  int e = 0;
-  if (mx > 0.0 && isfinite(mx)) frexp(mx, &e);  // mx = f * 2^e, f in [0.5, 1)
-  rscale[row] = ldexp(1.0, e);
-  rinv[row] = ldexp(1.0, -e);
+  if (row < m) {
+    const double* p = P + row + (int64_t)y * lda;
+#pragma unroll 4
+    for (int k = y; k < K; k += 8, p += 8 * lda) mx = fmax(mx, fabs(*p));
+  }
+  part[y][x] = mx;
+  __syncthreads();
+  if (y == 0 && row < m) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) mx = fmax(mx, part[j][x]);
+    int e = 0;
+    if (mx > 0.0 && isfinite(mx)) frexp(mx, &e);  // mx = f * 2^e, f in [0.5, 1)
+    rscale[row] = ldexp(1.0, e);
+    rinv[row] = ldexp(1.0, -e);
+  }
 }
 
 // pre-pass 2: error-free slicing, 16 consecutive k per thread -> one 16-byte store per slice
@@ -1149,7 +1162,7 @@ void ozaki_ws_destroy(OzakiWs* ws, cudaStream_t s) {
 
 void ozaki_prepare(const OzakiWs& ws, const double* P, int64_t lda, int64_t m, cudaStream_t s) {
   if (m <= 0) return;
-  ozaki_rowscale_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(P, lda, m, ws.K, ws.rscale, ws.rinv);
+  ozaki_rowscale_kernel<<<(unsigned)((m + 31) / 32), 256, 0, s>>>(P, lda, m, ws.K, ws.rscale, ws.rinv);
   agp_count_launch();
   const int64_t m_used = (m + 127) / 128 * 128;  // zero-fill up to the tile edge
   dim3 grid((unsigned)((m_used + 127) / 128), (unsigned)(ws.K / 16));

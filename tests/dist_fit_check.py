@@ -32,8 +32,9 @@ def main():
         ns.kind, ns.s = 0, 0.1
         lp = np.zeros(2, dtype=dtype)
         alpha = np.zeros(n, dtype=dtype)
+        post = C.c_void_p()
         rc = eng.L.agp_fit(eng.h, cabi.dtype_code(dtype), C.byref(ks), C.byref(ms), C.byref(ns), cabi.AGP_POINT_MAJOR,
-                           cabi.ptr(X), n, d, cabi.ptr(Y), 2, cabi.ptr(lp), cabi.ptr(alpha), None)
+                           cabi.ptr(X), n, d, cabi.ptr(Y), 2, cabi.ptr(lp), cabi.ptr(alpha), C.byref(post))
         eng.check(rc)
         lp_ref = ref.logpdf(ksr, ref.MeanSpec(1, 0.25), ref.NoiseSpec(0, 0.1), X, Y)
         pr = ref.posterior(ksr, ref.MeanSpec(1, 0.25), ref.NoiseSpec(0, 0.1), X, Y[:, 0])
@@ -42,8 +43,56 @@ def main():
         sc = np.abs(pr["alpha"]).max()
         good &= np.allclose(alpha, pr["alpha"], rtol=1e-6 if dtype == np.float64 else 1e-2,
                             atol=(1e-7 if dtype == np.float64 else 5e-3) * sc)
+        # the distributed posterior handle: mean_and_var at M test points (partitioned over the ranks after the factor
+        # is gathered), /root/reference/src/exact_gpr_posterior.jl:85-90, and the exported factor U
+        M = 257
+        Xs = np.random.default_rng(n + 1).random((M, d)).astype(dtype)
+        mu, var = np.zeros(M, dtype=dtype), np.zeros(M, dtype=dtype)
+        eng.check(eng.L.agp_post_mean_var(post, cabi.AGP_POINT_MAJOR, cabi.ptr(Xs), M, None, C.byref(ns), cabi.ptr(mu), cabi.ptr(var)))
+        mu_r, var_r = ref.post_mean_and_var(pr, Xs, noise_s=ref.NoiseSpec(0, 0.1))
+        tol = dict(rtol=1e-6, atol=1e-7) if dtype == np.float64 else dict(rtol=5e-3, atol=5e-3)
+        good_p = np.allclose(mu, mu_r, **tol) and np.allclose(var, var_r, **tol)
+        ld = C.c_double()
+        eng.check(eng.L.agp_post_logdet(post, C.byref(ld)))
+        good_p &= bool(np.isclose(ld.value, ref.logdet_chol(pr["U"]), rtol=1e-9 if dtype == np.float64 else 1e-4))
+        if n <= 1537:
+            U = np.zeros((n, n), dtype=dtype, order="F")
+            eng.check(eng.L.agp_post_factor_export(post, cabi.ptr(U)))
+            good_p &= bool(np.allclose(U, pr["U"], rtol=1e-7 if dtype == np.float64 else 1e-2, atol=1e-9 if dtype == np.float64 else 2e-3))
+        eng.L.agp_post_free(post)
         if rank == 0:
-            print("n=%d %s fam=%d: logpdf %s ref %s  ok=%s" % (n, np.dtype(dtype).name, fam, lp, lp_ref, good), flush=True)
+            print("n=%d %s fam=%d: logpdf %s ref %s  ok=%s  posterior(mean_and_var, logdet, U) ok=%s"
+                  % (n, np.dtype(dtype).name, fam, lp, lp_ref, good, good_p), flush=True)
+        ok &= bool(good) and bool(good_p)
+    # a case large enough for the tcgen05 trailing update with the block-cyclic strip table (n_pad >= 8192, W = 512)
+    if os.environ.get("DIST_CHECK_LARGE", "1") == "1":
+        n, d = 8704, 8
+        cfg = ref.make_config("C4", n=n)
+        X = np.ascontiguousarray(cfg["X"][:, :d])
+        yv = np.asfortranarray(cfg["y"].reshape(-1, 1))
+        ksr = ref.KernelSpec(ref.SE, 1.0, ref.T_SCALE, scale=1.0 / (0.5 * np.sqrt(d)))
+        ks = cabi.agp_kernel()
+        ks.family, ks.transform, ks.variance, ks.scale = 0, 1, 1.0, ksr.scale
+        ns = cabi.agp_noise()
+        ns.kind, ns.s = 0, 0.1
+        lp = np.zeros(1)
+        alpha = np.zeros(n)
+        post = C.c_void_p()
+        eng.check(eng.L.agp_fit(eng.h, cabi.AGP_F64, C.byref(ks), None, C.byref(ns), cabi.AGP_POINT_MAJOR, cabi.ptr(X), n, d,
+                                cabi.ptr(yv), 1, cabi.ptr(lp), cabi.ptr(alpha), C.byref(post)))
+        lp_ref = ref.logpdf(ksr, ref.MeanSpec(), ref.NoiseSpec(0, 0.1), X, yv[:, 0])
+        pr = ref.posterior(ksr, ref.MeanSpec(), ref.NoiseSpec(0, 0.1), X, yv[:, 0])
+        good = abs(lp[0] - lp_ref) <= 1e-8 * abs(lp_ref)
+        good &= np.allclose(alpha, pr["alpha"], rtol=1e-6, atol=1e-7 * np.abs(pr["alpha"]).max())
+        M = 1000
+        Xs = np.random.default_rng(3).random((M, d))
+        mu, var = np.zeros(M), np.zeros(M)
+        eng.check(eng.L.agp_post_mean_var(post, cabi.AGP_POINT_MAJOR, cabi.ptr(Xs), M, None, None, cabi.ptr(mu), cabi.ptr(var)))
+        mu_r, var_r = ref.post_mean_and_var(pr, Xs)
+        good &= np.allclose(mu, mu_r, rtol=1e-6, atol=1e-7) and np.allclose(var, var_r, rtol=1e-6, atol=1e-8)
+        eng.L.agp_post_free(post)
+        if rank == 0:
+            print("large n=%d (tcgen05 + strip table): logpdf %r ref %r ok=%s" % (n, lp[0], lp_ref, bool(good)), flush=True)
         ok &= bool(good)
     # VFE elbo with the data dimension sharded over the ranks (one all-reduce): must match the oracle
     for dtype in (np.float64, np.float32):
