@@ -80,6 +80,8 @@ SIGNATURES = {
     "agp_vfe_post_free": (C.c_int32, [_P]),
     "agp_debug_ozaki_syrk": (C.c_int32, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
                                          C.c_int32]),
+    "agp_debug_ozaki_gemm": (C.c_int32, [_P, _P, C.c_int32, C.c_int64, _P, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int32,
+                                         C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_double]),
     "agp_debug_ozaki_syrk_map": (C.c_int32, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                              C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64]),
     "agp_bc_owner": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

@@ -50,6 +50,7 @@ struct agp_ctx {
   int64_t oz_rows = 0, oz2_rows = 0;
   cudaStream_t stream_comm = nullptr;  // panel broadcasts of the pipelined distributed schedule
   int oz_S = 7;
+  int oz_S32 = 4;          // slices of the fp32 operands (4 x 7 bits >= the 24-bit significand)
 };
 
 struct agp_post {
@@ -216,10 +217,12 @@ void trailing_update(agp_ctx* ctx, T* L, int64_t lda, int64_t row0, int64_t col0
   if (M <= 0 || N <= 0) return;
   if (ctx->profile) cudaEventRecord(prof_event(ctx), st);
   bool done = false;
-  if constexpr (std::is_same<T, double>::value) {
-    if (oz) {  // tcgen05 int8-sliced path: the slices of panel rows [oz_row0, ...) are already in *oz
+  if (oz) {  // tcgen05 int8-sliced path: the slices of panel rows [oz_row0, ...) are already in *oz
+    if constexpr (std::is_same<T, double>::value) {
       ozaki_syrk(*oz, L + row0 + col0 * lda, lda, M, N, 1, 0, 0, col0 - oz_row0, row0 - oz_row0, st);
       done = true;
+    } else {
+      done = ozaki_update_ex(*oz, L + row0 + col0 * lda, 1, lda, M, N, 0, -1.0, 0, 0, col0 - oz_row0, row0 - oz_row0, st) == 0;
     }
   }
   if (!done) {
@@ -248,11 +251,30 @@ static int resolve_G(const agp_ctx* ctx, int64_t n_pad) {
   int nb = ctx->cfg.tile_nb;
   if (nb <= 0) nb = (n_pad >= 8192) ? 512 : TILE;
   int G = nb / TILE;
+  if (G > 8) G = 8;  // kernels that stage a whole outer block (distributed backward solve) hold at most 8 inner blocks
   return G < 1 ? 1 : G;
 }
 static int resolve_fp64_mode(const agp_ctx* ctx, int64_t n_pad) {
   if (ctx->cfg.fp64_mode >= 0) return ctx->cfg.fp64_mode;
   return n_pad >= 8192 ? 1 : 0;
+}
+// fp32: 0 = FFMA tile kernels, 1 = int8-sliced tcgen05 path (4 slices); auto = tcgen05 from n_pad >= 4096
+static int resolve_fp32_mode(const agp_ctx* ctx, int64_t n_pad) {
+  if (ctx->cfg.fp32_mode >= 0) return ctx->cfg.fp32_mode;
+  return n_pad >= 4096 ? 1 : 0;
+}
+template <typename T> static int resolve_tensor_mode(const agp_ctx* ctx, int64_t n_pad) {
+  return std::is_same<T, double>::value ? resolve_fp64_mode(ctx, n_pad) : resolve_fp32_mode(ctx, n_pad);
+}
+template <typename T> static int slices_of(const agp_ctx* ctx) { return std::is_same<T, double>::value ? ctx->oz_S : ctx->oz_S32; }
+// (re)size the cached slice workspace: rows x K bytes per slice, S slices
+static bool ensure_oz(agp_ctx* ctx, int64_t rows, int K, int S, cudaStream_t s) {
+  if (!ctx->oz.SL || ctx->oz.K != K || ctx->oz_rows < rows || ctx->oz.S != S) {
+    if (ctx->oz.SL) ozaki_ws_destroy(&ctx->oz, s);
+    if (ozaki_ws_create(&ctx->oz, rows, K, S, s) == 0) ctx->oz_rows = rows;
+    else { memset(&ctx->oz, 0, sizeof(ctx->oz)); ctx->oz_rows = 0; }
+  }
+  return ctx->oz.SL != nullptr;
 }
 
 // factor one outer panel in place: Lp points at its diagonal element; Gp inner 128-blocks; rows = rows from the
@@ -321,17 +343,11 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
                       double* logdet_part, int* info) {
   cudaStream_t s = ctx->stream, s2 = ctx->stream2;
   const int nblk = (int)(n_pad / TILE);
-  const int G = resolve_G(ctx, n_pad);
-  const int fp64_mode = resolve_fp64_mode(ctx, n_pad);
-  if constexpr (std::is_same<T, double>::value) {
-    if (fp64_mode == 1 && nblk > 2 * G) {  // (re)size the slice workspace of the tcgen05 path
-      if (!ctx->oz.SL || ctx->oz.K != G * TILE || ctx->oz_rows < rows_total || ctx->oz.S != ctx->oz_S) {
-        if (ctx->oz.SL) ozaki_ws_destroy(&ctx->oz, s);
-        if (ozaki_ws_create(&ctx->oz, rows_total, G * TILE, ctx->oz_S, s) == 0) ctx->oz_rows = rows_total;
-        else { memset(&ctx->oz, 0, sizeof(ctx->oz)); ctx->oz_rows = 0; }
-      }
-    }
-  }
+  const int fp64_mode = resolve_tensor_mode<T>(ctx, n_pad);  // 1: int8-sliced tcgen05 trailing update (fp64: 7 slices, fp32: 4)
+  int G = resolve_G(ctx, n_pad);
+  if (!std::is_same<T, double>::value && fp64_mode == 1 && ctx->cfg.tile_nb <= 0 && n_pad >= 4096) G = 4;  // 512-wide panels
+  const bool oz_ok = fp64_mode == 1 && nblk > 2 * G && ensure_oz(ctx, rows_total, G * TILE, slices_of<T>(ctx), s) &&
+                     (std::is_same<T, double>::value || ctx->oz.bulk == 2);
   const bool la = ctx->cfg.lookahead != 0 && nblk > 2 * G;
   const bool la2 = la && ctx->cfg.lookahead >= 2;
   bool rest_pending = false, restA_pending = false, last_rest_full = false;
@@ -345,12 +361,11 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
     if (cols_trail <= 0) continue;
     const int64_t K = (int64_t)(g_end - ko) * TILE, kc0 = (int64_t)ko * TILE;
     const OzakiWs* oz = nullptr;
-    if constexpr (std::is_same<T, double>::value) {
-      // tcgen05 path: needs the full outer-panel width it was sized for and enough trailing work to pay for slicing
-      if (fp64_mode == 1 && ctx->oz.SL && K == ctx->oz.K && cols_trail >= 2 * TILE) oz = &ctx->oz;
-    }
+    // tcgen05 path: needs the full outer-panel width it was sized for and enough trailing work to pay for slicing
+    if (oz_ok && K == ctx->oz.K && cols_trail >= 2 * TILE) oz = &ctx->oz;
+    constexpr int is_f32 = std::is_same<T, double>::value ? 0 : 1;
     if (!la) {
-      if constexpr (std::is_same<T, double>::value) { if (oz) ozaki_prepare(*oz, L + t0 + kc0 * lda, lda, rows_total - t0, s); }
+      if (oz) ozaki_prepare_ex(*oz, L + t0 + kc0 * lda, is_f32, 0, lda, rows_total - t0, 0, s);
       trailing_update<T>(ctx, L, lda, t0, t0, kc0, K, rows_total - t0, cols_trail, s, oz, t0);
       continue;
     }
@@ -390,7 +405,7 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
     cudaEvent_t e_panel = dep_event(ctx, ev_idx++), e_rest = dep_event(ctx, ev_idx++);
     if (rest_pending) cudaStreamWaitEvent(s, dep_event(ctx, last_rest), 0);  // also frees the slice buffer
     if (restA_pending) { cudaStreamWaitEvent(s, dep_event(ctx, last_restA), 0); restA_pending = false; }
-    if constexpr (std::is_same<T, double>::value) { if (oz) ozaki_prepare(*oz, L + t0 + kc0 * lda, lda, rows_total - t0, s); }
+    if (oz) ozaki_prepare_ex(*oz, L + t0 + kc0 * lda, is_f32, 0, lda, rows_total - t0, 0, s);
     cudaEventRecord(e_panel, s);
     const int64_t next_cols = (cols_trail < (int64_t)G * TILE) ? cols_trail : (int64_t)G * TILE;
     trailing_update<T>(ctx, L, lda, t0, t0, kc0, K, rows_total - t0, next_cols, s, oz, t0);  // next outer panel first
@@ -409,12 +424,70 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
   join_inverses(ctx);  // Dinv (stream3) is complete before any solve on the main stream
 }
 
+// V <- L^-1 V on the tensor cores: two-level blocked substitution.  Inside an outer block of W = 512 rows the 128-step
+// loop runs on the tile GEMMs (W^2 ncols work); everything below the block receives ONE rank-W update
+//   B[below] -= L[below, block] * B[block]
+// on the int8-sliced tcgen05 kernel: the L panel (rows_below x W, row-contiguous) and B[block]' (ncols x W, k-major) are
+// sliced into one workspace (A rows first, B rows behind them) and the product is a rectangular update of B[below].
+// This is `C.U' \ X` of /root/reference/src/util/common_covmat_ops.jl:54,90 (prediction, N^2 M flops at config C3) and the
+// A = U' \ K_zx solve of /root/reference/src/sparse_approximations.jl:296.
+template <typename T>
+bool forward_subst_multi_tc(agp_ctx* ctx, const T* L, int64_t lda, const T* Dinv, int64_t n_pad, T* B, int64_t ldb,
+                            int64_t ncols) {
+  cudaStream_t s = ctx->stream;
+  constexpr int GW = 4;
+  const int64_t W = (int64_t)GW * TILE;
+  const int nblk = (int)(n_pad / TILE);
+  constexpr int is_f32 = std::is_same<T, double>::value ? 0 : 1;
+  const int64_t a_rows = round_up(n_pad, TILE);
+  if (!ensure_oz(ctx, a_rows + ncols, (int)W, slices_of<T>(ctx), s) || ctx->oz.bulk != 2) return false;
+  const OzakiWs& ws = ctx->oz;
+  for (int ko = 0; ko < nblk; ko += GW) {
+    const int k_end = (ko + GW < nblk) ? ko + GW : nblk;
+    const int64_t blk_end = (int64_t)k_end * TILE;
+    for (int k = ko; k < k_end; ++k) {  // in-block substitution (128-steps, rows of this outer block only)
+      T* Bk = B + (int64_t)k * TILE;
+      GemmArgs a{};
+      a.A = Dinv + (int64_t)k * TILE * TILE; a.lda = TILE; a.a_kmajor = 0;
+      a.B = Bk; a.ldb = ldb; a.b_kmajor = 1;
+      a.C = Bk; a.ldc = ldb; a.M = TILE; a.N = ncols; a.K = TILE;
+      launch_gemm<T>(a, s);
+      const int64_t rows_in = blk_end - (int64_t)(k + 1) * TILE;
+      if (rows_in <= 0) continue;
+      GemmArgs u{};
+      u.A = L + (int64_t)(k + 1) * TILE + (int64_t)k * TILE * lda; u.lda = lda; u.a_kmajor = 0;
+      u.B = Bk; u.ldb = ldb; u.b_kmajor = 1;
+      u.C = Bk + TILE; u.ldc = ldb; u.M = rows_in; u.N = ncols; u.K = TILE; u.alpha_neg = 1; u.beta_one = 1;
+      launch_gemm<T>(u, s);
+    }
+    const int64_t rows_below = n_pad - blk_end, Kw = blk_end - (int64_t)ko * TILE;
+    if (rows_below <= 0) continue;
+    if (Kw != W) {  // ragged last outer block (n_pad not a multiple of 512): finish on the tile GEMM
+      GemmArgs u{};
+      u.A = L + blk_end + (int64_t)ko * TILE * lda; u.lda = lda; u.a_kmajor = 0;
+      u.B = B + (int64_t)ko * TILE; u.ldb = ldb; u.b_kmajor = 1;
+      u.C = B + blk_end; u.ldc = ldb; u.M = rows_below; u.N = ncols; u.K = Kw; u.alpha_neg = 1; u.beta_one = 1;
+      launch_gemm<T>(u, s);
+      continue;
+    }
+    ozaki_prepare_ex(ws, L + blk_end + (int64_t)ko * TILE * lda, is_f32, 0, lda, rows_below, 0, s);
+    ozaki_prepare_ex(ws, B + (int64_t)ko * TILE, is_f32, 1, ldb, ncols, a_rows, s);
+    if (ozaki_update_ex(ws, B + blk_end, is_f32, ldb, rows_below, ncols, 1, -1.0, 0, 0, a_rows, 0, s) != 0) return false;
+  }
+  return true;
+}
+
 // V <- L^-1 V for a n_pad x ncols block of right-hand sides (ncols multiple of 4), in place
 template <typename T>
 void forward_subst_multi(agp_ctx* ctx, const T* L, int64_t lda, const T* Dinv, int64_t n_pad, T* B, int64_t ldb,
                          int64_t ncols) {
   cudaStream_t s = ctx->stream;
   const int nblk = (int)(n_pad / TILE);
+  static const int64_t tc_min_cols = env_int64("AGP_SOLVE_TC_MIN_COLS", 512);
+  if (resolve_tensor_mode<T>(ctx, n_pad >= 2048 ? (int64_t)1 << 20 : 0) == 1 && n_pad >= 2048 && ncols % TILE == 0 &&
+      ncols >= tc_min_cols) {
+    if (forward_subst_multi_tc<T>(ctx, L, lda, Dinv, n_pad, B, ldb, ncols)) return;
+  }
   for (int k = 0; k < nblk; ++k) {
     T* Bk = B + (int64_t)k * TILE;
     GemmArgs a{};
@@ -1950,12 +2023,14 @@ int32_t agp_init(agp_ctx** out, int32_t device, const agp_config* cfg) {
   ctx->cfg.tile_nb = env_int("AGP_NB", (cfg && cfg->tile_nb > 0) ? cfg->tile_nb : 0);  // 0 = auto
   if (ctx->cfg.tile_nb % TILE) ctx->cfg.tile_nb = 0;
   ctx->cfg.fp64_mode = env_int("AGP_FP64_MODE", cfg ? ctx->cfg.fp64_mode : -1);            // -1 = auto
-  ctx->cfg.fp32_mode = env_int("AGP_FP32_MODE", ctx->cfg.fp32_mode);
+  ctx->cfg.fp32_mode = env_int("AGP_FP32_MODE", cfg ? ctx->cfg.fp32_mode : -1);            // -1 = auto
   ctx->cfg.lookahead = env_int("AGP_LOOKAHEAD", cfg ? ctx->cfg.lookahead : 1);
   ctx->cfg.use_graph = env_int("AGP_GRAPH", ctx->cfg.use_graph);
   ctx->profile = env_int("AGP_PROFILE", cfg ? cfg->profile_kernels : 0);
   ctx->oz_S = env_int("AGP_OZAKI_S", (cfg && cfg->ozaki_slices) ? cfg->ozaki_slices : 7);
   if (ctx->oz_S < 5 || ctx->oz_S > 8) ctx->oz_S = 7;
+  ctx->oz_S32 = env_int("AGP_OZAKI_S32", 4);
+  if (ctx->oz_S32 < 3 || ctx->oz_S32 > 5) ctx->oz_S32 = 4;
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
@@ -2004,6 +2079,7 @@ int32_t agp_set_config(agp_ctx* ctx, const agp_config* cfg) {
   if (cfg->tile_nb < 0 || cfg->tile_nb % TILE) return AGP_ERR_INVALID;
   ctx->cfg.tile_nb = cfg->tile_nb;
   ctx->cfg.fp64_mode = cfg->fp64_mode;
+  ctx->cfg.fp32_mode = cfg->fp32_mode;
   ctx->cfg.lookahead = cfg->lookahead;
   ctx->profile = cfg->profile_kernels;
   if (cfg->ozaki_slices >= 5 && cfg->ozaki_slices <= 8) { ctx->cfg.ozaki_slices = cfg->ozaki_slices; ctx->oz_S = cfg->ozaki_slices; }
@@ -2139,6 +2215,29 @@ int32_t agp_debug_ozaki_syrk(agp_ctx* ctx, void* C_dev, int64_t ldc, const void*
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { ctx->err = std::string("ozaki syrk: ") + cudaGetErrorString(e); return AGP_ERR_CUDA; }
+  return AGP_OK;
+}
+
+// general product on the tcgen05 path: C (M x N, fp32 or fp64) += sign * A B', A = M x K, B = N x K (B_dev == NULL: B = A,
+// lower tiles only).  Each operand is fp32 or fp64, row-contiguous (element (r, k) at [r + k*ld]) or k-major ([k + r*ld]).
+// Both operands are sliced into one workspace (A rows first, B rows from the next multiple of 128).
+int32_t agp_debug_ozaki_gemm(agp_ctx* ctx, void* C_dev, int32_t c_is_float, int64_t ldc, const void* A_dev, int32_t a_is_float,
+                             int32_t a_kmajor, int64_t lda, int64_t M, const void* B_dev, int32_t b_is_float, int32_t b_kmajor,
+                             int64_t ldb, int64_t N, int32_t K, int32_t S, double sign) {
+  if (!ctx || !C_dev || !A_dev) return AGP_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const int64_t m_pad = (M + 127) / 128 * 128, n_rows = B_dev ? (N + 127) / 128 * 128 : 0;
+  OzakiWs ws;
+  int rc = ozaki_ws_create(&ws, m_pad + n_rows, K, S, ctx->stream);
+  if (rc) { ctx->err = "ozaki_ws_create failed (code " + std::to_string(rc) + ")"; return rc == 1 ? AGP_ERR_INVALID : AGP_ERR_CUDA; }
+  ozaki_prepare_ex(ws, A_dev, a_is_float, a_kmajor, lda, M, 0, ctx->stream);
+  if (B_dev) ozaki_prepare_ex(ws, B_dev, b_is_float, b_kmajor, ldb, N, m_pad, ctx->stream);
+  const int urc = ozaki_update_ex(ws, C_dev, c_is_float, ldc, M, N, B_dev ? 1 : 0, sign, 0, 0, B_dev ? m_pad : 0, 0, ctx->stream);
+  ozaki_ws_destroy(&ws, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (urc) { ctx->err = "ozaki_update_ex: unsupported shape / slice count (N % 128, S)"; return AGP_ERR_UNSUPPORTED; }
+  if (e != cudaSuccess) { ctx->err = std::string("ozaki gemm: ") + cudaGetErrorString(e); return AGP_ERR_CUDA; }
   return AGP_OK;
 }
 

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "kernels.h"
@@ -35,24 +36,44 @@ constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KB = 64, OZ_STAGES = 2;
 // ---------------------------------------------------------------------------------------------
 // pre-pass 1: row exponents
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ozaki_rowscale_kernel(const double* __restrict__ P, int64_t lda, int64_t m, int K,
+template <typename Tin>
+__global__ void __launch_bounds__(256) ozaki_rowscale_kernel(const Tin* __restrict__ P, int64_t lda, int64_t m, int K, int kmajor,
                                                              double* __restrict__ rscale, double* __restrict__ rinv) {
-  // 32 rows x 8 column groups per block: every load instruction of a warp covers 32 consecutive rows (256 B) of one
-  // column, 8 warps scan interleaved columns, the row maxima meet in shared memory
+  // 32 rows x 8 column groups per block: every load instruction of a warp covers 32 consecutive rows of one column
+  // (row-contiguous operand) or 32 consecutive k of one row (k-major operand); the row maxima meet in shared memory
   __shared__ double part[8][33];
-  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
-  const int64_t row = blockIdx.x * 32ll + x;
   double mx = 0.0;
-  if (row < m) {
-    const double* p = P + row + (int64_t)y * lda;
+  int64_t row;
+  if (!kmajor) {
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    row = blockIdx.x * 32ll + x;
+    if (row < m) {
+      const Tin* p = P + row + (int64_t)y * lda;
 #pragma unroll 4
-    for (int k = y; k < K; k += 8, p += 8 * lda) mx = fmax(mx, fabs(*p));
-  }
-  part[y][x] = mx;
-  __syncthreads();
-  if (y == 0 && row < m) {
+      for (int k = y; k < K; k += 8, p += 8 * lda) mx = fmax(mx, fabs((double)*p));
+    }
+    part[y][x] = mx;
+    __syncthreads();
+    if (y != 0) return;
 #pragma unroll
     for (int j = 1; j < 8; ++j) mx = fmax(mx, part[j][x]);
+  } else {  // element (row, k) at P[k + row * lda]: one warp per row, lanes along k
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int rr = w; rr < 32; rr += 8) {
+      const int64_t r2 = blockIdx.x * 32ll + rr;
+      double v = 0.0;
+      if (r2 < m)
+        for (int k = lane; k < K; k += 32) v = fmax(v, fabs((double)P[k + r2 * lda]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+      if (lane == 0) part[0][rr] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    row = blockIdx.x * 32ll + threadIdx.x;
+    mx = part[0][threadIdx.x];
+  }
+  if (row < m) {
     int e = 0;
     if (mx > 0.0 && isfinite(mx)) frexp(mx, &e);  // mx = f * 2^e, f in [0.5, 1)
     rscale[row] = ldexp(1.0, e);
@@ -60,18 +81,26 @@ __global__ void __launch_bounds__(256) ozaki_rowscale_kernel(const double* __res
   }
 }
 
-// pre-pass 2: error-free slicing, 16 consecutive k per thread -> one 16-byte store per slice
-template <int S>
-__global__ void ozaki_slice_kernel(const double* __restrict__ P, int64_t lda, int64_t m, int64_t m_fill, int64_t m_alloc,
-                                   int K, const double* __restrict__ rinv, int8_t* __restrict__ SL, int bulk) {
+// pre-pass 2: error-free slicing, 16 consecutive k per thread -> one 16-byte store per slice.  Rows land at
+// [dst_row0, dst_row0 + m_fill) of the slice buffer (dst_row0 a multiple of 128; rscale / rinv are already offset).
+template <int S, typename Tin>
+__global__ void ozaki_slice_kernel(const Tin* __restrict__ P, int64_t lda, int64_t m, int64_t m_fill, int64_t m_alloc,
+                                   int K, int kmajor, int64_t dst_row0, const double* __restrict__ rinv, int8_t* __restrict__ SL,
+                                   int bulk) {
   const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int k0 = blockIdx.y * 16;
   if (row >= m_fill) return;
   double r[16];
   const double inv = (row < m) ? rinv[row] : 0.0;
+  if (!kmajor) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) r[i] = (row < m) ? P[row + (int64_t)(k0 + i) * lda] * inv : 0.0;
+    for (int i = 0; i < 16; ++i) r[i] = (row < m) ? (double)P[row + (int64_t)(k0 + i) * lda] * inv : 0.0;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = (row < m) ? (double)P[(k0 + i) + row * lda] * inv : 0.0;
+  }
   double up = 64.0, dn = 1.0 / 64.0;  // 2^(7s-1), 2^-(7s-1)
+  const int64_t drow = row + dst_row0;
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     union { int8_t b[16]; uint4 v; } pk;
@@ -84,14 +113,14 @@ __global__ void ozaki_slice_kernel(const double* __restrict__ P, int64_t lda, in
     if (bulk) {
       // UMMA "interleaved" (no-swizzle) K-major layout, written directly: chunk (slice, 128-row block, 32-byte
       // k-block) = 4096 contiguous bytes = [16 row-groups][2 k-halves][8 rows][16 B]  (SBO 256 B, LBO 128 B)
-      const int64_t rb = row >> 7, g = (row & 127) >> 3, r8 = row & 7;
+      const int64_t rb = drow >> 7, g = (drow & 127) >> 3, r8 = drow & 7;
       const int kb = k0 >> 5, h = (k0 >> 4) & 1;
       // bulk 1: [slice][row block][k block]; bulk 2 (v3 kernel): [row block][k block][slice] -- the S chunks one
       // (128-row tile, k block) needs are ONE contiguous S*4096-byte run
       const int64_t chunk = (bulk == 2) ? (rb * (K >> 5) + kb) * S + s : ((int64_t)s * (m_alloc >> 7) + rb) * (K >> 5) + kb;
       *reinterpret_cast<uint4*>(SL + chunk * 4096 + ((g * 2 + h) * 8 + r8) * 16) = pk.v;
     } else {
-      *reinterpret_cast<uint4*>(SL + ((int64_t)s * m_alloc + row) * K + k0) = pk.v;
+      *reinterpret_cast<uint4*>(SL + ((int64_t)s * m_alloc + drow) * K + k0) = pk.v;
     }
     up *= 128.0;
     dn *= (1.0 / 128.0);
@@ -161,7 +190,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 
 struct OzTileArgs {
-  double* C; int64_t ldc;
+  void* C; int64_t ldc;   // fp64 (v1, v2, v3) or fp32 (v3<..., float>)
+  double sign;            // v3: C += sign * (P P'); -1 for the trailing updates, +1 for accumulations
   int64_t M, N;           // extent of C (rows of P used, columns updated)
   int64_t m_alloc;        // row stride between slices in the slice buffer
   int K;                  // bytes (= elements) per slice row
@@ -283,12 +313,12 @@ __global__ void __launch_bounds__(192, 1) umma_ozaki_syrk_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int64_t col = n0 + c + i;
-          cv[i] = (col < a.N) ? a.C[row + col * a.ldc] : 0.0;
+          cv[i] = (col < a.N) ? ((double*)a.C)[row + col * a.ldc] : 0.0;
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int64_t col = n0 + c + i;
-          if (col < a.N) a.C[row + col * a.ldc] = fma(-v[i] * rs, a.rscale[n_src0 + c + i], cv[i]);
+          if (col < a.N) ((double*)a.C)[row + col * a.ldc] = fma(-v[i] * rs, a.rscale[n_src0 + c + i], cv[i]);
         }
       }
     }
@@ -373,6 +403,12 @@ __device__ __forceinline__ double ld_cs(const double* p) {
   return v;
 }
 __device__ __forceinline__ void st_cs(double* p, double v) { asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ double ld_cs(const float* p) {
+  float v;
+  asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return (double)v;
+}
+__device__ __forceinline__ void st_cs(float* p, double v) { asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"((float)v) : "memory"); }
 
 // slot index -> (bi, bj) for the diagonal-anchored lower triangle, L2-BLOCKED: the tile grid is cut into
 // super-blocks of SB row tiles x 2*SB column tiles (2048 x 2048 elements for SB = 16); slots walk one
@@ -434,7 +470,7 @@ __device__ __forceinline__ bool v2_decode(const OzTileArgs& a, int64_t t, int nb
       v2_tile_tab(t, nbj, a.strip_start, a.strip_bimin, bi, bj);
     }
     const int64_t n0 = (int64_t)bj * OZ_BN, bw = a.b_tile_width ? a.b_tile_width : 128;
-    brow = (n0 / bw) * a.b_tile_stride + (n0 % bw) + a.b_off;
+    brow = (a.b_tile_stride ? (n0 / bw) * a.b_tile_stride + (n0 % bw) : n0) + a.b_off;  // stride 0 = identity column map
     return true;
   }
   const bool ok = v2_tile(t, nbi, nbj, bi, bj);
@@ -572,7 +608,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v2_kernel(c
       const int64_t row = m0 + 32 * quarter + lane;
       const bool row_ok = row < a.M;
       const double rs = row_ok ? a.rscale[row + a.a_off] * (1.0 / 4096.0) : 0.0;
-      double* crow = a.C + row;
+      double* crow = (double*)a.C + row;
       mbar_wait(&tmem_full_bar, lt & 1);
       tc_fence_after();
       // (1) drain TMEM: Horner-combine the S int32 accumulators of all 64 columns into registers, 8 columns per
@@ -688,8 +724,15 @@ __device__ __forceinline__ double i64_to_f64_exact(long long x) {  // |x| < 2^51
 // rounding.  PAIR32: adjacent accumulators are first combined in int32 (valid for K <= 512, see v2).
 template <int S, bool PAIR32>
 __device__ __forceinline__ double oz_combine(const uint32_t (&r)[S][8], int i) {
-  long long h, l;
-  if constexpr (PAIR32) {
+  long long h = 0, l = 0;
+  if constexpr (S <= 4) {  // fp32 operands (3 or 4 slices): everything fits one word, the conversion is the only rounding
+    h = (int)r[0][i];
+#pragma unroll
+    for (int d = 1; d < S; ++d) h = h * 128 + (int)r[d][i];
+#pragma unroll
+    for (int d = S; d < 4; ++d) h *= 128;  // same 128^3 scaling as the longer splits
+    return i64_to_f64_exact(h);
+  } else if constexpr (PAIR32) {
     const int t01 = (int)r[0][i] * 128 + (int)r[1][i], t23 = (int)r[2][i] * 128 + (int)r[3][i];
     h = (long long)t01 * 16384 + t23;
     if constexpr (S == 5) l = (int)r[4][i];
@@ -702,11 +745,11 @@ __device__ __forceinline__ double oz_combine(const uint32_t (&r)[S][8], int i) {
 #pragma unroll
     for (int d = 5; d < S; ++d) l = l * 128 + (int)r[d][i];
   }
-  constexpr double LO_SCALE = (S == 5) ? 1.0 / 128.0 : (S == 6) ? 1.0 / 16384.0 : (S == 7) ? 1.0 / 2097152.0 : 1.0 / 268435456.0;
+  constexpr double LO_SCALE = (S <= 5) ? 1.0 / 128.0 : (S == 6) ? 1.0 / 16384.0 : (S == 7) ? 1.0 / 2097152.0 : 1.0 / 268435456.0;
   return fma(i64_to_f64_exact(l), LO_SCALE, i64_to_f64_exact(h));
 }
 
-template <int S, int CL, int NEPI, int GE>
+template <int S, int CL, int NEPI, int GE, typename CT>
 __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v3_kernel(OzTileArgs a, int64_t ntiles, int nbi, int nbj) {
   constexpr int A_BYTES = OZ_BM * V2_KB, B_BYTES = OZ_BN * V2_KB;
   constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
@@ -825,8 +868,8 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v3_kernel(O
       brow64 += c0;
       const int64_t row = m0 + 32 * quarter + lane;
       const bool row_ok = row < a.M;
-      const double rs = row_ok ? a.rscale[row + a.a_off] * (1.0 / 8589934592.0) : 0.0;  // 2^e_i * 2^-12 * 128^-3
-      double* crow = a.C + row;
+      const double rs = row_ok ? a.sign * a.rscale[row + a.a_off] * (1.0 / 8589934592.0) : 0.0;  // +-2^e_i * 2^-12 * 128^-3
+      CT* crow = (CT*)a.C + row;
       mbar_wait(&tmem_full_bar, lt & 1);
       tc_fence_after();
       double v[CB];
@@ -861,7 +904,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v3_kernel(O
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar);
-      // C -= (2^e_i 2^e_j 2^-33) * v, streamed (.cs) so the int8 slices stay resident in L2
+      // C += sign * (2^e_i 2^e_j 2^-33) * v, streamed (.cs) so the int8 slices stay resident in L2
       if (row_ok && a.epi != 2 && a.epi != 3 && a.epi != 5 && a.epi != 6) {
 #pragma unroll
         for (int c = 0; c < CB; c += 16) {
@@ -874,7 +917,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v3_kernel(O
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int64_t col = n0 + c + i;
-            if (col < a.N) st_cs(crow + col * a.ldc, fma(-v[c + i], rs * a.rscale[brow64 + c + i], cv[i]));
+            if (col < a.N) st_cs(crow + col * a.ldc, fma(v[c + i], rs * a.rscale[brow64 + c + i], cv[i]));
           }
         }
       }
@@ -936,7 +979,7 @@ void launch_v2_variant(const OzakiWs& ws, const OzTileArgs& a, int64_t ntiles, i
 }
 
 
-template <int S, int CL, int NEPI, int GE>
+template <int S, int CL, int NEPI, int GE, typename CT = double>
 void launch_v3_variant(const OzTileArgs& a, int64_t ntiles, int nbi, int nbj, int cap, size_t smem, cudaStream_t s) {
   static int max_clusters[64] = {0};  // per device; 0 = not queried yet
   static uint64_t configured = 0;
@@ -950,11 +993,11 @@ void launch_v3_variant(const OzTileArgs& a, int64_t ntiles, int nbi, int nbj, in
   la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
   lc.attrs = la; lc.numAttrs = 1;
   if (agp_first_use_on_device(&configured)) {
-    cudaFuncSetAttribute(umma_ozaki_syrk_v3_kernel<S, CL, NEPI, GE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(umma_ozaki_syrk_v3_kernel<S, CL, NEPI, GE, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int mc = 0;
     if (CL > 1) {
       lc.gridDim = dim3((unsigned)(cap / CL * CL));
-      if (cudaOccupancyMaxActiveClusters(&mc, umma_ozaki_syrk_v3_kernel<S, CL, NEPI, GE>, &lc) != cudaSuccess) { mc = 0; cudaGetLastError(); }
+      if (cudaOccupancyMaxActiveClusters(&mc, umma_ozaki_syrk_v3_kernel<S, CL, NEPI, GE, CT>, &lc) != cudaSuccess) { mc = 0; cudaGetLastError(); }
     } else {
       mc = 1 << 20;
     }
@@ -965,19 +1008,20 @@ void launch_v3_variant(const OzTileArgs& a, int64_t ntiles, int nbi, int nbj, in
   if (grid > ntiles) grid = ntiles / CL * CL;  // the slot count is even when CL = 2 is selected
   if (grid <= 0) return;
   lc.gridDim = dim3((unsigned)grid);
-  cudaLaunchKernelEx(&lc, umma_ozaki_syrk_v3_kernel<S, CL, NEPI, GE>, a, ntiles, nbi, nbj);
+  cudaLaunchKernelEx(&lc, umma_ozaki_syrk_v3_kernel<S, CL, NEPI, GE, CT>, a, ntiles, nbi, nbj);
 }
 
-template <int S>
-void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int64_t b_tile_stride,
-                      int64_t b_tile_width, int64_t b_off, int64_t a_off, cudaStream_t s) {
+template <int S, typename CT = double>
+void launch_syrk_v2_S(const OzakiWs& ws, void* C, int64_t ldc, int64_t M, int64_t N, int64_t b_tile_stride,
+                      int64_t b_tile_width, int64_t b_off, int64_t a_off, cudaStream_t s, int full = 0, double sign = -1.0) {
   constexpr int STAGE_BYTES = S * (OZ_BM * V2_KB + OZ_BN * V2_KB);
   constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
   static uint64_t configured = 0;  // per-device bit: the attribute is per device (one ctx per GPU in one process)
   static int nsm = 148;
   if (agp_first_use_on_device(&configured)) {
-    cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S, 1, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if constexpr (S >= 5 && std::is_same<CT, double>::value)
+      cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S, 1, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -998,6 +1042,8 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
   a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.m_alloc = ws.m_alloc; a.K = ws.K; a.rscale = ws.rscale;
   a.b_tile_stride = b_tile_stride; a.b_tile_width = b_tile_width; a.b_off = b_off; a.a_off = a_off; a.lower_only = 1;
   a.SLb = ws.bulk ? ws.SL : nullptr;
+  a.sign = sign;
+  if (full) want_ge = 0;
   {
     // default: the int32 pair pre-combination where it was measured and validated on the device (S = 7, K <= 512:
     // +4.4% kernel throughput, sampled output bit-identical to variant 0 -- profiles/r01_ozaki_probe.json);
@@ -1008,7 +1054,7 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
   }
   const int nbi = (int)((M + OZ_BM - 1) / OZ_BM), nbj = (int)(N / OZ_BN);
   int64_t ntiles = 0;
-  if (b_tile_stride == 0 && a_off == b_off) {  // diagonal-anchored: closed-form, L2-blocked slot enumeration
+  if (!full && b_tile_stride == 0 && a_off == b_off) {  // diagonal-anchored: closed-form, L2-blocked slot enumeration
     const int64_t nJ = (nbj + 2 * V2_SB - 1) / (2 * V2_SB), nI = (nbi + V2_SB - 1) / V2_SB;
     const int64_t nsb = (nI <= nJ) ? nI * (nI + 1) / 2 : nJ * (nJ + 1) / 2 + (nI - nJ) * nJ;
     ntiles = nsb * (int64_t)V2_SB * 2 * V2_SB;  // slots, including the skipped ones of diagonal / edge super-blocks
@@ -1043,6 +1089,7 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
       const int64_t n0 = (int64_t)j * OZ_BN;
       const int64_t nsrc = (b_tile_stride ? (n0 / bw) * b_tile_stride + (n0 % bw) : n0) + b_off;
       int64_t bm = (nsrc - a_off) >= 0 ? (nsrc - a_off) / OZ_BM : 0;  // first row tile with nsrc < a_off + bi*128 + 128
+      if (full) bm = 0;  // rectangular product: every row tile of every strip
       if (bm > nbi) bm = nbi;
       bimin[j] = (int32_t)bm;
       start[j] = ntiles;
@@ -1064,17 +1111,24 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
     const char* f = getenv("AGP_OZAKI_EPIWARPS");
     const int ew = (f && atoi(f) == 4) ? 4 : 8;
     const bool cl2 = want_cl == 2 && (!a.strip_start || ge) && ntiles >= 2;
-    if (ge && cl2 && ew == 8) launch_v3_variant<S, 2, 8, 1>(a, ntiles, nbi, nbj, cap, smem, s);
-    else if (ge && cl2) launch_v3_variant<S, 2, 4, 1>(a, ntiles, nbi, nbj, cap, smem, s);
-    else if (ge && ew == 8) launch_v3_variant<S, 1, 8, 1>(a, ntiles, nbi, nbj, cap, smem, s);
-    else if (ge) launch_v3_variant<S, 1, 4, 1>(a, ntiles, nbi, nbj, cap, smem, s);
-    else if (cl2 && ew == 8) launch_v3_variant<S, 2, 8, 0>(a, ntiles, nbi, nbj, cap, smem, s);
-    else if (cl2) launch_v3_variant<S, 2, 4, 0>(a, ntiles, nbi, nbj, cap, smem, s);
-    else if (ew == 8) launch_v3_variant<S, 1, 8, 0>(a, ntiles, nbi, nbj, cap, smem, s);
-    else launch_v3_variant<S, 1, 4, 0>(a, ntiles, nbi, nbj, cap, smem, s);
+    if constexpr (std::is_same<CT, double>::value && S >= 5) {
+      if (ge && cl2 && ew == 8) launch_v3_variant<S, 2, 8, 1>(a, ntiles, nbi, nbj, cap, smem, s);
+      else if (ge && cl2) launch_v3_variant<S, 2, 4, 1>(a, ntiles, nbi, nbj, cap, smem, s);
+      else if (ge && ew == 8) launch_v3_variant<S, 1, 8, 1>(a, ntiles, nbi, nbj, cap, smem, s);
+      else if (ge) launch_v3_variant<S, 1, 4, 1>(a, ntiles, nbi, nbj, cap, smem, s);
+      else if (cl2 && ew == 8) launch_v3_variant<S, 2, 8, 0>(a, ntiles, nbi, nbj, cap, smem, s);
+      else if (cl2) launch_v3_variant<S, 2, 4, 0>(a, ntiles, nbi, nbj, cap, smem, s);
+      else if (ew == 8) launch_v3_variant<S, 1, 8, 0>(a, ntiles, nbi, nbj, cap, smem, s);
+      else launch_v3_variant<S, 1, 4, 0>(a, ntiles, nbi, nbj, cap, smem, s);
+    } else {  // fp32 output and / or short (3-, 4-slice) splits: the two main variants only
+      if (cl2) launch_v3_variant<S, 2, 8, 0, CT>(a, ntiles, nbi, nbj, cap, smem, s);
+      else launch_v3_variant<S, 1, 8, 0, CT>(a, ntiles, nbi, nbj, cap, smem, s);
+    }
     agp_count_launch();
     return;
   }
+  if constexpr (!(S >= 5 && std::is_same<CT, double>::value)) return;  // the round-1 kernels exist for fp64, S >= 5 only
+  else {
   if (want_cl == 2 || want_ew == 8 || ge) {
     // CTA pairs need slots 2u, 2u + 1 on the same row tile: the closed-form order and the grouped table order give that
     const bool cl2 = want_cl == 2 && a.SLb && (!a.strip_start || ge) && ntiles >= 2;
@@ -1092,6 +1146,7 @@ void launch_syrk_v2_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int6
   const int grid = (int)(ntiles < cap ? ntiles : cap);
   umma_ozaki_syrk_v2_kernel<S, 1, 4, 0><<<grid, 192, smem, s>>>(ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
   agp_count_launch();
+  }
 }
 
 template <int S>
@@ -1118,7 +1173,7 @@ void launch_syrk_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t
 
 int ozaki_ws_create(OzakiWs* ws, int64_t max_rows, int K, int S, cudaStream_t s) {
   memset(ws, 0, sizeof(*ws));
-  if (S < 5 || S > 8 || K % OZ_KB != 0) return 1;
+  if (S < 3 || S > 8 || K % OZ_KB != 0) return 1;
   EncodeTiledFn enc = get_encode();
   if (!enc) return 2;
   ws->m_alloc = (max_rows + 127) / 128 * 128;
@@ -1160,19 +1215,63 @@ void ozaki_ws_destroy(OzakiWs* ws, cudaStream_t s) {
   memset(ws, 0, sizeof(*ws));
 }
 
-void ozaki_prepare(const OzakiWs& ws, const double* P, int64_t lda, int64_t m, cudaStream_t s) {
-  if (m <= 0) return;
-  ozaki_rowscale_kernel<<<(unsigned)((m + 31) / 32), 256, 0, s>>>(P, lda, m, ws.K, ws.rscale, ws.rinv);
+template <typename Tin>
+static void prepare_t(const OzakiWs& ws, const Tin* P, int kmajor, int64_t lda, int64_t m, int64_t dst_row0, cudaStream_t s) {
+  double* rs = ws.rscale + dst_row0;
+  double* ri = ws.rinv + dst_row0;
+  ozaki_rowscale_kernel<Tin><<<(unsigned)((m + 31) / 32), 256, 0, s>>>(P, lda, m, ws.K, kmajor, rs, ri);
   agp_count_launch();
   const int64_t m_used = (m + 127) / 128 * 128;  // zero-fill up to the tile edge
   dim3 grid((unsigned)((m_used + 127) / 128), (unsigned)(ws.K / 16));
+#define AGP_SLICE(SS) ozaki_slice_kernel<SS, Tin><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, kmajor, dst_row0, ri, ws.SL, ws.bulk)
   switch (ws.S) {
-    case 5: ozaki_slice_kernel<5><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL, ws.bulk); break;
-    case 6: ozaki_slice_kernel<6><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL, ws.bulk); break;
-    case 7: ozaki_slice_kernel<7><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL, ws.bulk); break;
-    default: ozaki_slice_kernel<8><<<grid, 128, 0, s>>>(P, lda, m, m_used, ws.m_alloc, ws.K, ws.rinv, ws.SL, ws.bulk); break;
+    case 3: AGP_SLICE(3); break;
+    case 4: AGP_SLICE(4); break;
+    case 5: AGP_SLICE(5); break;
+    case 6: AGP_SLICE(6); break;
+    case 7: AGP_SLICE(7); break;
+    default: AGP_SLICE(8); break;
   }
+#undef AGP_SLICE
   agp_count_launch();
+}
+
+void ozaki_prepare(const OzakiWs& ws, const double* P, int64_t lda, int64_t m, cudaStream_t s) {
+  if (m <= 0) return;
+  prepare_t<double>(ws, P, 0, lda, m, 0, s);
+}
+
+void ozaki_prepare_ex(const OzakiWs& ws, const void* P, int p_is_float, int kmajor, int64_t lda, int64_t m, int64_t dst_row0,
+                      cudaStream_t s) {
+  if (m <= 0) return;
+  if (p_is_float) prepare_t<float>(ws, (const float*)P, kmajor, lda, m, dst_row0, s);
+  else prepare_t<double>(ws, (const double*)P, kmajor, lda, m, dst_row0, s);
+}
+
+int ozaki_update_ex(const OzakiWs& ws, void* C, int c_is_float, int64_t ldc, int64_t M, int64_t N, int full, double sign,
+                    int64_t b_tile_stride, int64_t b_tile_width, int64_t b_off, int64_t a_off, cudaStream_t s) {
+  if (M <= 0 || N <= 0) return 0;
+  if (ws.bulk != 2 || N % 128 != 0 || N / OZ_BN > ws.tab_cap) return 1;  // v3 kernel + interleaved slice layout only
+#define AGP_UPD(SS, CTT) launch_syrk_v2_S<SS, CTT>(ws, C, ldc, M, N, b_tile_stride, b_tile_width, b_off, a_off, s, full, sign)
+  if (c_is_float) {
+    switch (ws.S) {
+      case 3: AGP_UPD(3, float); break;
+      case 4: AGP_UPD(4, float); break;
+      case 5: AGP_UPD(5, float); break;
+      default: return 1;
+    }
+  } else {
+    switch (ws.S) {
+      case 4: AGP_UPD(4, double); break;
+      case 5: AGP_UPD(5, double); break;
+      case 6: AGP_UPD(6, double); break;
+      case 7: AGP_UPD(7, double); break;
+      case 8: AGP_UPD(8, double); break;
+      default: return 1;
+    }
+  }
+#undef AGP_UPD
+  return 0;
 }
 
 void ozaki_syrk(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int lower_only, int64_t b_tile_stride,

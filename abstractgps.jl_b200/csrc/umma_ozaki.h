@@ -32,3 +32,14 @@ void ozaki_prepare(const OzakiWs& ws, const double* P, int64_t lda, int64_t m, c
 // lower_only skips tiles above the diagonal
 void ozaki_syrk(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int lower_only, int64_t b_tile_stride,
                 int64_t b_tile_width, int64_t b_off, int64_t a_off, cudaStream_t s);
+
+// generalised entry points (v3 kernel, interleaved slice layout only):
+//  * operands may be fp32 or fp64, row-contiguous (element (row, k) at P[row + k*lda]) or k-major (P[k + row*lda]); the
+//    rows land at [dst_row0, dst_row0 + m) of the slice buffer (dst_row0 a multiple of 128), so the two operands of a general
+//    product C += sign * A B' are sliced into ONE workspace and addressed with a_off / b_off;
+//  * C may be fp32 or fp64; full = 1: every row tile of every 64-column strip (rectangular product), 0: lower tiles only.
+// returns 0 on success, 1 if the workspace / shape is not supported by the v3 path.
+void ozaki_prepare_ex(const OzakiWs& ws, const void* P, int p_is_float, int kmajor, int64_t lda, int64_t m, int64_t dst_row0,
+                      cudaStream_t s);
+int ozaki_update_ex(const OzakiWs& ws, void* C, int c_is_float, int64_t ldc, int64_t M, int64_t N, int full, double sign,
+                    int64_t b_tile_stride, int64_t b_tile_width, int64_t b_off, int64_t a_off, cudaStream_t s);

@@ -76,13 +76,14 @@ typedef struct {
   int32_t tile_nb;       /* OUTER panel width (multiple of 128); 0 -> auto (512 from n_pad >= 8192, else 128) */
   int32_t fp64_mode;     /* -1 auto (tcgen05 from n_pad >= 8192), 0 = DMMA mma.sync trailing update,
                             1 = int8-sliced (Ozaki) trailing update on tcgen05.mma.kind::i8 */
-  int32_t fp32_mode;     /* reserved (0 = FFMA) */
+  int32_t fp32_mode;     /* -1 auto (tcgen05 from n_pad >= 4096), 0 = FFMA tile kernels, 1 = int8-sliced trailing update /
+                            triangular solves on tcgen05.mma.kind::i8 (4 seven-bit slices cover the fp32 significand) */
   int32_t lookahead;     /* 0/1: overlap the next panel with the bulk of the trailing update */
   int32_t use_graph;     /* reserved */
   int32_t ozaki_slices;  /* 5..8 seven-bit slices of the tcgen05 fp64 path; 0 -> 7 (~2^-49 of the row scale) */
   int32_t profile_kernels; /* 1: CUDA events around every trailing-update launch (agp_last_timings[7]); default 0 */
   int32_t reserved[9];
-} agp_config; /* NULL -> defaults; env AGP_NB, AGP_FP64_MODE, AGP_LOOKAHEAD, AGP_OZAKI_S override at agp_init */
+} agp_config; /* NULL -> defaults; env AGP_NB, AGP_FP64_MODE, AGP_FP32_MODE, AGP_LOOKAHEAD, AGP_OZAKI_S, AGP_OZAKI_S32 override at agp_init */
 
 /* ---- context ------------------------------------------------------------------------- */
 int32_t agp_init(agp_ctx** ctx, int32_t device, const agp_config* cfg);
@@ -208,6 +209,12 @@ int32_t agp_vfe_post_free(agp_vfe_post* p);
 int32_t agp_debug_ozaki_syrk(agp_ctx* ctx, void* C_dev, int64_t ldc, const void* P_dev, int64_t lda, int64_t M,
                              int64_t N, int32_t K, int32_t S, int32_t lower_only);
 
+/* general product on the same tcgen05 path: C (M x N, N % 128 == 0) += sign * A B' with fp32 or fp64 operands and output,
+ * row-contiguous (element (r,k) at [r + k*ld]) or k-major ([k + r*ld]) operands; B_dev == NULL: B = A, lower tiles only.
+ * S = number of 7-bit slices (3..5 for fp32 output, 4..8 for fp64). */
+int32_t agp_debug_ozaki_gemm(agp_ctx* ctx, void* C_dev, int32_t c_is_float, int64_t ldc, const void* A_dev, int32_t a_is_float,
+                             int32_t a_kmajor, int64_t lda, int64_t M, const void* B_dev, int32_t b_is_float, int32_t b_kmajor,
+                             int64_t ldb, int64_t N, int32_t K, int32_t S, double sign);
 /* same kernel through the block-cyclic column map of the multi-GPU trailing update (the strip-table tile enumeration):
  * P has m_panel rows; row r of C (M x N local columns, N % 128 == 0) pairs with panel row r + a_off, local column n with
  * panel row (n / b_tile_width) * b_tile_stride + n % b_tile_width + b_off; lower tiles only (relative to panel rows). */

@@ -113,3 +113,49 @@ def test_strip_table_enumeration_matches_fp64(ag, R, me, kk, nto, W):
     assert bool((got[~owned] == C0.t()[:rows_below][~owned]).all())   # tiles above the diagonal are untouched
     assert bool((Cst.t()[rows_below:] == C0.t()[rows_below:]).all())  # rows beyond M (ldc padding) untouched
     assert float((got - C0.t()[:rows_below]).abs()[owned].max()) > 0      # the update really happened
+
+
+# ---- fp32 on the tensor cores: the same int8-sliced kernel with 4 slices (28 bits cover the fp32 significand), fp32 C
+@pytest.mark.parametrize("n,d,fam", [(4224, 8, ref.SE), (6000, 32, ref.MATERN32)])
+def test_fp32_fit_on_tcgen05_matches_fp64_oracle(ag, n, d, fam):
+    """auto policy for fp32: n_pad >= 4096 -> 512-wide panels, tcgen05 trailing update; logpdf rtol 1e-4 (BASELINE.json)"""
+    cfg = ref.make_config("C3", n=n)
+    X = np.ascontiguousarray(cfg["X"][:, :d])
+    y = cfg["y"]
+    ard = np.ascontiguousarray(cfg["k"].ard[:d]) * np.float32(np.sqrt(32.0 / d))
+    k64 = ref.KernelSpec(fam, 1.0, ref.T_ARD, ard=ard.astype(np.float64))
+    kern = (ag.SqExponentialKernel() if fam == ref.SE else ag.Matern32Kernel()).compose(ag.ARDTransform(ard))
+    eng = ag.engine()
+    assert eng.get_config().fp32_mode < 0
+    lp, post = ag.fit(ag.GP(kern)(ag.RowVecs(X), 0.05), y)
+    assert lp.dtype == np.float32
+    X64, y64 = X.astype(np.float64), y.astype(np.float64)
+    lp_ref = ref.logpdf(k64, cfg["mean"], cfg["noise"], X64, y64)
+    assert abs(lp - lp_ref) <= 1e-4 * abs(lp_ref), (lp, lp_ref)
+    pr = ref.posterior(k64, cfg["mean"], cfg["noise"], X64, y64)
+    Xs = cfg["Xs"][:1024, :d]
+    mu, v = ag.mean_and_var(post(ag.RowVecs(Xs), 0.05))     # 1024 columns: the tensor-core forward substitution
+    mu_r, v_r = ref.post_mean_and_var(pr, Xs.astype(np.float64), noise_s=cfg["noise"])
+    assert np.allclose(mu, mu_r, rtol=2e-3, atol=2e-3) and np.allclose(v, v_r, rtol=2e-3, atol=2e-3)
+    # the tensor path really ran: the FFMA path gives different last bits
+    eng.set_config(fp32_mode=0)
+    lp0, post0 = ag.fit(ag.GP(kern)(ag.RowVecs(X), 0.05), y)
+    eng.set_config(fp32_mode=-1)
+    assert abs(lp0 - lp_ref) <= 1e-4 * abs(lp_ref)
+    assert not np.array_equal(post.data.alpha, post0.data.alpha)
+
+
+def test_fp64_predict_uses_tensor_forward_substitution(ag):
+    """mean_and_var at 1536 test points on an fp64 posterior with n_pad >= 2048: B[below] -= L[below, block] B[block] runs on
+    the tcgen05 kernel (7 slices, rectangular product); parity with the oracle at fp64 tolerances"""
+    n, d = 3000, 6
+    cfg = ref.make_config("C2", n=n)
+    X = np.ascontiguousarray(cfg["X"][:, :d])
+    ks = ref.KernelSpec(ref.SE, 1.0, ref.T_SCALE, scale=1.0 / (0.5 * np.sqrt(d)))
+    f = ag.GP(ag.SqExponentialKernel().compose(ag.ScaleTransform(ks.scale)))
+    post = ag.posterior(f(ag.RowVecs(X), 0.1), cfg["y"])
+    pr = ref.posterior(ks, cfg["mean"], cfg["noise"], X, cfg["y"])
+    Xs = np.random.default_rng(4).random((1536, d))
+    mu, v = ag.mean_and_var(post, ag.RowVecs(Xs))
+    mu_r, v_r = ref.post_mean_and_var(pr, Xs)
+    assert np.allclose(mu, mu_r, rtol=1e-7, atol=1e-8) and np.allclose(v, v_r, rtol=1e-6, atol=1e-9)
