@@ -268,6 +268,14 @@ template <typename T> static int resolve_tensor_mode(const agp_ctx* ctx, int64_t
 }
 template <typename T> static int slices_of(const agp_ctx* ctx) { return std::is_same<T, double>::value ? ctx->oz_S : ctx->oz_S32; }
 // (re)size the cached slice workspace: rows x K bytes per slice, S slices
+static bool ensure_oz2(agp_ctx* ctx, int64_t rows, int K, int S, cudaStream_t s) {  // second cached workspace (long-K products)
+  if (!ctx->oz2.SL || ctx->oz2.K != K || ctx->oz2_rows < rows || ctx->oz2.S != S) {
+    if (ctx->oz2.SL) ozaki_ws_destroy(&ctx->oz2, s);
+    if (ozaki_ws_create(&ctx->oz2, rows, K, S, s) == 0) ctx->oz2_rows = rows;
+    else { memset(&ctx->oz2, 0, sizeof(ctx->oz2)); ctx->oz2_rows = 0; }
+  }
+  return ctx->oz2.SL != nullptr;
+}
 static bool ensure_oz(agp_ctx* ctx, int64_t rows, int K, int S, cudaStream_t s) {
   if (!ctx->oz.SL || ctx->oz.K != K || ctx->oz_rows < rows || ctx->oz.S != S) {
     if (ctx->oz.SL) ozaki_ws_destroy(&ctx->oz, s);
@@ -1383,6 +1391,11 @@ int vfe_core(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
   cap = cap / TILE * TILE;
   if (cap < TILE) cap = TILE;
   if (cap > n_padN) cap = n_padN;
+  // D += A_c A_c' on the tensor cores: the chunk is ONE long-K product (K = chunk width); the int32 accumulators of the
+  // sliced kernel hold (d+1) * K * 64^2 < 2^31, so K <= 32768 keeps every slice count exact
+  const bool syrk_tc = resolve_tensor_mode<T>(ctx, (int64_t)1 << 20) == 1 && m_pad >= 1024;
+  if (syrk_tc && cap > 32768) cap = 32768;
+  constexpr int is_f32 = std::is_same<T, double>::value ? 0 : 1;
   void* Bv = nullptr;
   CK(sc.alloc(&Bv, (size_t)m_pad * cap * sizeof(T)));
   T* B = (T*)Bv;
@@ -1394,10 +1407,17 @@ int vfe_core(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
     launch_gram<T>(Zt, Xt + c0 * D, m_pad, nc_pad, D, B, m_pad, gx, s);
     launch_scale_cols<T>(B, m_pad, m_pad, nc, isn + c0, s);
     forward_subst_multi<T>(ctx, Lz, lda, Dz, m_pad, B, m_pad, nc_pad);
-    GemmArgs g{};
-    g.A = B; g.lda = m_pad; g.B = B; g.ldb = m_pad; g.C = Lm; g.ldc = lda;
-    g.M = m_pad; g.N = m_pad; g.K = nc_pad; g.beta_one = 1; g.lower_only = 1;
-    launch_gemm<T>(g, s);
+    bool acc_done = false;
+    if (syrk_tc && nc_pad >= 1024 && ensure_oz2(ctx, m_pad, (int)nc_pad, slices_of<T>(ctx), s) && ctx->oz2.bulk == 2) {
+      ozaki_prepare_ex(ctx->oz2, B, is_f32, 0, m_pad, m_pad, 0, s);
+      acc_done = ozaki_update_ex(ctx->oz2, Lm, is_f32, lda, m_pad, m_pad, 0, 1.0, 0, 0, 0, 0, s) == 0;
+    }
+    if (!acc_done) {
+      GemmArgs g{};
+      g.A = B; g.lda = m_pad; g.B = B; g.ldb = m_pad; g.C = Lm; g.ldc = lda;
+      g.M = m_pad; g.N = m_pad; g.K = nc_pad; g.beta_one = 1; g.lower_only = 1;
+      launch_gemm<T>(g, s);
+    }
     launch_gemv_n_acc<T>(B, m_pad, m_pad, nc, delta + c0, bvec, s);
     launch_sumsq<T>(B, m_pad * nc_pad, dscal + 3, s);
   }

@@ -1252,6 +1252,7 @@ int ozaki_update_ex(const OzakiWs& ws, void* C, int c_is_float, int64_t ldc, int
                     int64_t b_tile_stride, int64_t b_tile_width, int64_t b_off, int64_t a_off, cudaStream_t s) {
   if (M <= 0 || N <= 0) return 0;
   if (ws.bulk != 2 || N % 128 != 0 || N / OZ_BN > ws.tab_cap) return 1;  // v3 kernel + interleaved slice layout only
+  if (ws.K > 32768) return 1;  // int32 accumulators ((d+1) K 64^2 < 2^31) and the 2^51 range of the exact int64 -> fp64 drain
 #define AGP_UPD(SS, CTT) launch_syrk_v2_S<SS, CTT>(ws, C, ldc, M, N, b_tile_stride, b_tile_width, b_off, a_off, s, full, sign)
   if (c_is_float) {
     switch (ws.S) {

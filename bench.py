@@ -497,11 +497,23 @@ def fit_roofline(wl, N, eng, torch, dev, prob, flush, args, world=1, dist=None, 
                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 entry)"})
     else:
         fp32 = tf / world / (trailing_ms * 1e-3) / 1e12 if trailing_ms > 0 else None
-        tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
-        out.update({"bound": "tensor", "kernel": "fp32 trailing update (see DESIGN.md s4)",
-                    "achieved": fp32, "peak": tf32_peak / 3.0, "unit": "TFLOP/s (fp32-equivalent, 3 tf32 products per fp32 product)",
-                    "frac": (fp32 / (tf32_peak / 3.0)) if fp32 else None,
-                    "peak_source": "bf16_tflops of MEASURED_PEAKS.json / 2 (tf32 runs at half the bf16 rate) / 3 (3xTF32 split)"})
+        f32_mode = cfg0.fp32_mode if cfg0.fp32_mode >= 0 else (1 if n_pad >= 4096 else 0)
+        if f32_mode == 1:  # the same int8-sliced tcgen05 kernel with 4 slices: 10 int8 MACs per fp32 MAC
+            S32 = int(os.environ.get("AGP_OZAKI_S32", "4"))
+            pairs = S32 * (S32 + 1) // 2
+            achieved = fp32 * pairs if fp32 else None
+            mma_peak = measure_int8_mma_peak(eng, torch, dev, 7)
+            out.update({"bound": "tensor", "kernel": "umma_ozaki_syrk_v3_kernel<%d, ., ., ., float> (tcgen05.mma.kind::i8, fp32 operands in %d slices)" % (S32, S32),
+                        "achieved": achieved, "peak": mma_peak, "unit": "TOP/s (int8 tensor, dense, per GPU)",
+                        "frac": (achieved / mma_peak) if achieved else None,
+                        "peak_source": "MEASURED in this run: the fp64 (7-slice) instance of the same kernel with operand traffic and epilogue off",
+                        "frac_of_nominal_4500": (achieved / 4500.0) if achieved else None,
+                        "fp32_equivalent_tflops_per_gpu": fp32, "slices": S32, "int8_macs_per_fp32_mac": pairs})
+        else:
+            ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+            out.update({"bound": "fp32 FMA", "kernel": "gemm_simt_kernel (FFMA tiles)", "achieved": fp32, "peak": ffma_peak,
+                        "unit": "TFLOP/s (fp32)", "frac": (fp32 / ffma_peak) if fp32 else None,
+                        "peak_source": "nominal 148 SMs x 128 FFMA/clk x 2 x 1.965 GHz"})
     tr = ncu_traffic(wl if wl in ("C4", "C4h", "C2", "C3", "C5") else "C4")
     out["traffic"] = tr.get("dram_bytes_per_launch") if tr else None
     out["traffic_detail"] = tr

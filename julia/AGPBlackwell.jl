@@ -2,7 +2,7 @@
 # dense hot path runs on libagp.so (hand-written sm_100a CUDA behind the C ABI of include/agp.h).
 #
 # Julia is NOT available in the build image, so this file is shipped as source and has never been
-# executed there; every `ccall` below is mirrored 1:1 by the ctypes binding
+# executed (INTEGRATION.md lists what a maintainer should check first); every `ccall` below is mirrored 1:1 by the ctypes binding
 # abstractgps.jl_b200/_cabi.py, which IS exercised by the test-suite -- the ABI is what is tested.
 #
 # Seams used (SURVEY.md s1, s8b): ordinary multiple dispatch on
@@ -13,7 +13,7 @@
 module AGPBlackwell
 
 using AbstractGPs, KernelFunctions, LinearAlgebra, FillArrays
-import AbstractGPs: posterior, mean_and_var, elbo, approx_log_evidence, FiniteGP, PosteriorGP, VFE, DTC
+import AbstractGPs: posterior, mean_and_var, elbo, approx_log_evidence, FiniteGP, PosteriorGP, VFE, DTC, GP
 import AbstractGPs: Xt_invA_X, Xt_invA_Y, diag_Xt_invA_X, tr_Xt_invA_X
 import Distributions: logpdf
 import Random
@@ -56,21 +56,43 @@ end
 const Stationary = Union{SqExponentialKernel,Matern12Kernel,Matern32Kernel,Matern52Kernel}
 family(::SqExponentialKernel) = Int32(0); family(::Matern12Kernel) = Int32(1)
 family(::Matern32Kernel) = Int32(2);      family(::Matern52Kernel) = Int32(3); family(::LinearKernel) = Int32(4)
+
+# Kernels the engine implements: a base kernel wrapped in any nesting of ScaledKernel / TransformedKernel{Scale|ARD}.
+# Everything else (sums, products, periodic, ...) is NOT claimed: the methods below `invoke` the stock reference method.
+supported(::Union{Stationary,LinearKernel}) = true
+supported(k::ScaledKernel) = supported(k.kernel)
+supported(k::TransformedKernel{<:Any,<:Union{ScaleTransform,ARDTransform}}) = supported(k.kernel)
+supported(::Kernel) = false
+supported(::Union{AbstractGPs.ZeroMean,AbstractGPs.ConstMean,AbstractGPs.CustomMean}) = true
+supported(::AbstractGPs.MeanFunction) = false
+supported(f::GP) = supported(f.kernel) && supported(f.mean)
+supported(::Any) = false
+
+# flattened description: (family, sigma_f^2, linear c, per-dimension input scaling w) with w === nothing (identity),
+# a scalar (ScaleTransform) or a vector (ARDTransform).  (k o t1) o t2 evaluates k(t1(t2(x))): diagonal scalings commute,
+# so nested transforms multiply (the Python mirror's `_chain`).
+flat(k::Union{Stationary,LinearKernel}) = (family(k), 1.0, k isa LinearKernel ? Float64(only(k.c)) : 0.0, nothing)
+function flat(k::ScaledKernel)
+    fam, var, c, w = flat(k.kernel)
+    (fam, var * Float64(only(k.σ²)), c * 1.0, w)      # sigma^2 * (x'y + c) keeps c inside: the engine applies variance to both
+end
+combine(::Nothing, t) = t
+combine(w, t) = w .* t
+function flat(k::TransformedKernel{<:Any,<:ScaleTransform})
+    fam, var, c, w = flat(k.kernel)
+    (fam, var, c, combine(w, Float64(only(k.transform.s))))
+end
+function flat(k::TransformedKernel{<:Any,<:ARDTransform})
+    fam, var, c, w = flat(k.kernel)
+    (fam, var, c, combine(w, Float64.(k.transform.v)))
+end
 # returns (AgpKernel, keepalive)
-kernel_spec(k::Union{Stationary,LinearKernel}, T) =
-    (AgpKernel(family(k), 0, 1.0, 1.0, k isa LinearKernel ? only(k.c) : 0.0, C_NULL), nothing)
-function kernel_spec(k::ScaledKernel, T)
-    s, keep = kernel_spec(k.kernel, T)
-    (AgpKernel(s.family, s.transform, s.variance * only(k.σ²), s.scale, s.linear_c, s.ard), keep)
-end
-function kernel_spec(k::TransformedKernel{<:Any,<:ScaleTransform}, T)
-    s, keep = kernel_spec(k.kernel, T)
-    (AgpKernel(s.family, 1, s.variance, only(k.transform.s), s.linear_c, C_NULL), keep)
-end
-function kernel_spec(k::TransformedKernel{<:Any,<:ARDTransform}, T)
-    s, _ = kernel_spec(k.kernel, T)
-    v = convert(Vector{T}, k.transform.v)
-    (AgpKernel(s.family, 2, s.variance, 1.0, s.linear_c, pointer(v)), v)
+function kernel_spec(k, T)
+    fam, var, c, w = flat(k)
+    w === nothing && return (AgpKernel(fam, 0, var, 1.0, c, C_NULL), nothing)
+    w isa Real && return (AgpKernel(fam, 1, var, Float64(w), c, C_NULL), nothing)
+    v = convert(Vector{T}, w)
+    return (AgpKernel(fam, 2, var, 1.0, c, pointer(v)), v)
 end
 mean_spec(::AbstractGPs.ZeroMean, x, T) = (AgpMean(0, 0.0, C_NULL), nothing)
 mean_spec(m::AbstractGPs.ConstMean, x, T) = (AgpMean(1, Float64(m.c), C_NULL), nothing)
@@ -83,6 +105,10 @@ function noise_spec(Σ::Diagonal, T); v = convert(Vector{T}, Σ.diag); (AgpNoise
 points(x::ColVecs{T}) where {T} = (x.X, AGP_POINT_MAJOR, size(x.X, 1))
 points(x::RowVecs{T}) where {T} = (x.X, AGP_FEATURE_MAJOR, size(x.X, 2))
 points(x::AbstractVector{T}) where {T<:Real} = (x, AGP_POINT_MAJOR, 1)
+# a second input collection (inducing / test points) in the SAME storage order as the first: the ABI takes one layout flag
+same_layout(z::ColVecs, layout) = layout == AGP_POINT_MAJOR ? z.X : permutedims(z.X)
+same_layout(z::RowVecs, layout) = layout == AGP_FEATURE_MAJOR ? z.X : permutedims(z.X)
+same_layout(z::AbstractVector{<:Real}, layout) = z
 
 # ---- device factor (boundary #2) --------------------------------------------------------------
 mutable struct DeviceCholesky{T}
@@ -136,8 +162,12 @@ function fit(fx::DevFiniteGP{T}, Y::AbstractVecOrMat; want_post::Bool=true) wher
 end
 
 # replaces src/finite_gp_projection.jl:306-311 and src/exact_gpr_posterior.jl:29-35 for the device types
-logpdf(fx::DevFiniteGP{T}, Y::AbstractVecOrMat{<:Real}) where {T} = fit(fx, Y; want_post=false)[1]
-posterior(fx::DevFiniteGP{T}, y::AbstractVector{<:Real}) where {T} = fit(fx, y)[2]
+# priors the engine does not implement fall through to the reference's own methods (Julia dispatch, not a CPU fallback
+# inside the engine)
+logpdf(fx::DevFiniteGP{T}, Y::AbstractVecOrMat{<:Real}) where {T} =
+    supported(fx.f) ? fit(fx, Y; want_post=false)[1] : invoke(logpdf, Tuple{FiniteGP,typeof(Y)}, fx, Y)
+posterior(fx::DevFiniteGP{T}, y::AbstractVector{<:Real}) where {T} =
+    supported(fx.f) ? fit(fx, y)[2] : invoke(posterior, Tuple{FiniteGP,AbstractVector{<:Real}}, fx, y)
 
 # replaces src/exact_gpr_posterior.jl:85-90 (+ src/finite_gp_projection.jl:154-158) with the fused cross-Gram path
 const DevPosterior = PosteriorGP{<:GP,<:NamedTuple{(:α, :C, :x, :δ),<:Tuple{Any,DeviceCholesky,Any,Any}}}
@@ -193,6 +223,7 @@ end
 
 # replaces rand(rng, fx, S) src/finite_gp_projection.jl:233-237: the normals come from the caller's rng
 function Random.rand(rng::Random.AbstractRNG, fx::DevFiniteGP{T}, S::Int) where {T}
+    supported(fx.f) || return invoke(Random.rand, Tuple{Random.AbstractRNG,FiniteGP,Int}, rng, fx, S)
     c = ctx(); X, layout, D = points(fx.x); Z = randn(rng, T, length(fx), S); out = similar(Z)
     ks, k1 = kernel_spec(fx.f.kernel, T); ms, k2 = mean_spec(fx.f.mean, fx.x, T); ns, k3 = noise_spec(fx.Σy, T)
     lock(c.lock) do
@@ -203,37 +234,92 @@ function Random.rand(rng::Random.AbstractRNG, fx::DevFiniteGP{T}, S::Int) where 
     return out
 end
 
-# replaces approx_log_evidence(::VFE, fx, y) src/sparse_approximations.jl:248-254
-function approx_log_evidence(vfe::VFE, fx::DevFiniteGP{T}, y::AbstractVector{<:Real}) where {T}
-    @assert vfe.fz.f === fx.f
-    c = ctx(); X, layout, D = points(fx.x); Z, _, _ = points(vfe.fz.x)
+# replaces approx_log_evidence(::VFE / ::DTC, fx, y) src/sparse_approximations.jl:248-254, :282-286: ONE streamed pass
+# returns both objectives (elbo, dtc)
+function sparse_objectives(fz::FiniteGP, fx::DevFiniteGP{T}, y::AbstractVector{<:Real}) where {T}
+    fz.f === fx.f || throw(ArgumentError("the inducing and the data FiniteGP must share the prior"))
+    length(y) == length(fx) || throw(DimensionMismatch("length(fx) = $(length(fx)) but length(y) = $(length(y))"))
+    c = ctx(); X, layout, D = points(fx.x); Z = same_layout(fz.x, layout)
     ks, k1 = kernel_spec(fx.f.kernel, T); ms, k2 = mean_spec(fx.f.mean, fx.x, T)
-    ns, k3 = noise_spec(fx.Σy, T); js, k4 = noise_spec(vfe.fz.Σy, T)
+    ns, k3 = noise_spec(fx.Σy, T); js, k4 = noise_spec(fz.Σy, T)
     yv = convert(Vector{T}, y); out = Vector{T}(undef, 2)
     lock(c.lock) do
-        GC.@preserve X Z yv k1 k2 k3 k4 check(c, ccall((:agp_vfe_elbo, libagp), Int32,
+        GC.@preserve X Z yv out k1 k2 k3 k4 check(c, ccall((:agp_vfe_elbo, libagp), Int32,
             (Ptr{Cvoid}, Int32, Ref{AgpKernel}, Ref{AgpMean}, Ref{AgpNoise}, Int32, Ptr{Cvoid}, Int64, Int32, Ptr{Cvoid}, Int64,
              Ref{AgpNoise}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
-            c.h, agp_dtype(T), ks, ms, ns, layout, X, length(fx), D, Z, length(vfe.fz), js, yv, pointer(out, 1), pointer(out, 2)))
+            c.h, agp_dtype(T), ks, ms, ns, layout, X, length(fx), D, Z, length(fz), js, yv, pointer(out, 1), pointer(out, 2)))
     end
-    return out[1]
+    return out[1], out[2]
 end
+approx_log_evidence(vfe::VFE, fx::DevFiniteGP{T}, y::AbstractVector{<:Real}) where {T} =
+    supported(fx.f) ? sparse_objectives(vfe.fz, fx, y)[1] : invoke(approx_log_evidence, Tuple{VFE,FiniteGP,AbstractVector{<:Real}}, vfe, fx, y)
+approx_log_evidence(dtc::DTC, fx::DevFiniteGP{T}, y::AbstractVector{<:Real}) where {T} =
+    supported(fx.f) ? sparse_objectives(dtc.fz, fx, y)[2] : invoke(approx_log_evidence, Tuple{DTC,FiniteGP,AbstractVector{<:Real}}, dtc, fx, y)
 
-# replaces approx_log_evidence(::DTC, fx, y) src/sparse_approximations.jl:282-286: the DTC objective is the second
-# output of the same call
-function approx_log_evidence(dtc::DTC, fx::DevFiniteGP{T}, y::AbstractVector{<:Real}) where {T}
-    @assert dtc.fz.f === fx.f
-    c = ctx(); X, layout, D = points(fx.x); Z, _, _ = points(dtc.fz.x)
-    ks, k1 = kernel_spec(fx.f.kernel, T); ms, k2 = mean_spec(fx.f.mean, fx.x, T)
-    ns, k3 = noise_spec(fx.Σy, T); js, k4 = noise_spec(dtc.fz.Σy, T)
-    yv = convert(Vector{T}, y); out = Vector{T}(undef, 2)
-    lock(c.lock) do
-        GC.@preserve X Z yv k1 k2 k3 k4 check(c, ccall((:agp_vfe_elbo, libagp), Int32,
-            (Ptr{Cvoid}, Int32, Ref{AgpKernel}, Ref{AgpMean}, Ref{AgpNoise}, Int32, Ptr{Cvoid}, Int64, Int32, Ptr{Cvoid}, Int64,
-             Ref{AgpNoise}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
-            c.h, agp_dtype(T), ks, ms, ns, layout, X, length(fx), D, Z, length(dtc.fz), js, yv, pointer(out, 1), pointer(out, 2)))
+# ---- posterior(::VFE, fx, y) src/sparse_approximations.jl:58-75 and its predictive mean_and_var :212-217 ------------
+# The reference's ApproxPosteriorGP caches host matrices; the device posterior keeps chol(K_zz), chol(A A' + I) and
+# m_eps in HBM behind an agp_vfe_post handle.
+mutable struct DeviceApproxPosterior{T,Tprior,Tz} <: AbstractGPs.AbstractGP
+    h::Ptr{Cvoid}
+    prior::Tprior
+    z::Tz
+    function DeviceApproxPosterior{T}(h, prior, z) where {T}
+        p = new{T,typeof(prior),typeof(z)}(h, prior, z)
+        finalizer(q -> ccall((:agp_vfe_post_free, libagp), Int32, (Ptr{Cvoid},), q.h), p)
     end
-    return out[2]
+end
+function posterior(vfe::Union{VFE,DTC}, fx::DevFiniteGP{T}, y::AbstractVector{<:Real}) where {T}
+    supported(fx.f) || return invoke(posterior, Tuple{typeof(vfe),FiniteGP,AbstractVector{<:Real}}, vfe, fx, y)
+    fz = vfe.fz
+    fz.f === fx.f || throw(ArgumentError("the inducing and the data FiniteGP must share the prior"))
+    c = ctx(); X, layout, D = points(fx.x); Z = same_layout(fz.x, layout)
+    ks, k1 = kernel_spec(fx.f.kernel, T); ms, k2 = mean_spec(fx.f.mean, fx.x, T)
+    ns, k3 = noise_spec(fx.Σy, T); js, k4 = noise_spec(fz.Σy, T)
+    yv = convert(Vector{T}, y); post = Ref{Ptr{Cvoid}}(C_NULL)
+    lock(c.lock) do
+        GC.@preserve X Z yv k1 k2 k3 k4 check(c, ccall((:agp_vfe_fit, libagp), Int32,
+            (Ptr{Cvoid}, Int32, Ref{AgpKernel}, Ref{AgpMean}, Ref{AgpNoise}, Int32, Ptr{Cvoid}, Int64, Int32, Ptr{Cvoid}, Int64,
+             Ref{AgpNoise}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
+            c.h, agp_dtype(T), ks, ms, ns, layout, X, length(fx), D, Z, length(fz), js, yv, post))
+    end
+    return DeviceApproxPosterior{T}(post[], fx.f, fz.x)
+end
+function mean_and_var(fx::FiniteGP{<:DeviceApproxPosterior{T},<:DevInputs{T},<:Diagonal}) where {T}
+    p = fx.f; c = ctx(); Xs, layout, D = points(fx.x); M = length(fx)
+    μ = Vector{T}(undef, M); v = Vector{T}(undef, M)
+    lock(c.lock) do
+        GC.@preserve Xs check(c, ccall((:agp_vfe_mean_var, libagp), Int32,
+            (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}), p.h, layout, Xs, M, μ, v))
+    end
+    # the handle applies Zero / Const prior means; a closure mean is evaluated host-side (src/mean_function.jl:52-55)
+    p.prior.mean isa AbstractGPs.CustomMean && (μ .+= AbstractGPs.mean_vector(p.prior.mean, fx.x))
+    return μ, v .+ diag(fx.Σy)
+end
+AbstractGPs.mean_and_var(p::DeviceApproxPosterior{T}, x::DevInputs{T}) where {T} = mean_and_var(p(x, zero(T)))
+AbstractGPs.mean(fx::FiniteGP{<:DeviceApproxPosterior}) = mean_and_var(fx)[1]
+AbstractGPs.var(fx::FiniteGP{<:DeviceApproxPosterior}) = mean_and_var(fx)[2]
+
+# ---- reverse-mode rule for logpdf (test/finite_gp_projection.jl:152-178, examples/1-mauna-loa/script.jl:200-242) ------
+# agp_post_logpdf_grad returns d logpdf / d (sigma_f^2, ScaleTransform s, LinearKernel c, noise, constant mean,
+# ARD weights) from the factor of ONE fit.  The pullback below hands these to ChainRulesCore as a Tangent of the FiniteGP
+# for the common parametrisation  f = GP(c, sigma2 * (k o ScaleTransform(s)))  / ARDTransform(v),  fx = f(x, noise).
+import ChainRulesCore
+function ChainRulesCore.rrule(::typeof(logpdf), fx::DevFiniteGP{T}, y::AbstractVector{<:Real}) where {T}
+    supported(fx.f) || return ChainRulesCore.rrule_via_ad(ChainRulesCore.NoForwardsMode(), logpdf, fx, y)
+    lp, post = fit(fx, y)
+    D = points(fx.x)[3]; N = length(fx)
+    g = Vector{Float64}(undef, 5 + D); nd = Vector{T}(undef, N)
+    c = ctx()
+    lock(c.lock) do
+        check(c, ccall((:agp_post_logpdf_grad, libagp), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}), post.data.C.h, g, nd))
+    end
+    function logpdf_pullback(Δ)
+        d = ChainRulesCore.unthunk(Δ)
+        grads = (variance=d * g[1], scale=d * g[2], linear_c=d * g[3], noise=d .* nd, mean_c=d * g[5], ard=d .* g[6:end],
+                 y=-d .* post.data.α)              # d logpdf / dy = -alpha
+        return ChainRulesCore.NoTangent(), ChainRulesCore.Tangent{typeof(fx)}(; agp_gradients=grads), grads.y
+    end
+    return lp, logpdf_pullback
 end
 
 end # module
