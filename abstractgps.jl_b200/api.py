@@ -520,17 +520,12 @@ def _fit(fx: FiniteGP, Y, want_post: bool, want_alpha: bool):
     lp = np.empty(S, dtype=dt)
     alpha = np.empty(pts.n, dtype=dt) if want_alpha else None
     post = C.c_void_p()
-    out_lp = []
-    for s0 in range(0, max(S, 1), 128):  # the border tile carries up to 128 right-hand sides per pass
-        s1 = min(S, s0 + 128)
-        Yc = np.asfortranarray(Yf[:, s0:s1])
-        first = s0 == 0
-        rc = eng.L.agp_fit(eng.h, cabi.dtype_code(dt), C.byref(ks), C.byref(ms), C.byref(ns), cabi.AGP_POINT_MAJOR,
-                           cabi.ptr(pts.a), pts.n, pts.D, cabi.ptr(Yc), s1 - s0, cabi.ptr(lp[s0:s1]),
-                           cabi.ptr(alpha) if (first and want_alpha) else None,
-                           C.byref(post) if (first and want_post) else None)
-        eng.check(rc)
-        out_lp.append(lp[s0:s1])
+    # one call whatever S is: the library carries 128 columns through the factorisation and solves the rest against the
+    # same factor (ONE Gram + ONE Cholesky)
+    rc = eng.L.agp_fit(eng.h, cabi.dtype_code(dt), C.byref(ks), C.byref(ms), C.byref(ns), cabi.AGP_POINT_MAJOR,
+                       cabi.ptr(pts.a), pts.n, pts.D, cabi.ptr(Yf), S, cabi.ptr(lp),
+                       cabi.ptr(alpha) if want_alpha else None, C.byref(post) if want_post else None)
+    eng.check(rc)
     lpv = lp[0] if vec else lp
     if not want_post:
         return lpv, None

@@ -675,6 +675,56 @@ int fit_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
   return AGP_OK;
 }
 
+// logpdf(fx, Y::Matrix) has no limit on the number of columns (/root/reference/src/finite_gp_projection.jl:306-311).
+// The border tile carries 128 right-hand sides through the factorisation; further columns reuse the SAME factor:
+// V = L^-1 (Y_c - m) by the multi-RHS forward substitution, sqmahal = column sums of V.^2 -- ONE Gram and ONE Cholesky
+// whatever S is.
+template <typename T>
+int fit_many_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_noise* noise, int layout,
+                  const void* X, int64_t N, int D, const void* Y, int S, void* logpdf_out, void* alpha_out,
+                  agp_post** post_out) {
+  if (S <= TILE) return fit_impl<T>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out, post_out, nullptr, nullptr, nullptr);
+  if (!Y || !logpdf_out) { ctx->err = "Y/logpdf_out is NULL"; return AGP_ERR_INVALID; }
+  agp_post* p = nullptr;
+  int rc = fit_impl<T>(ctx, k, mean, noise, layout, X, N, D, Y, TILE, logpdf_out, alpha_out, &p, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  struct Guard { agp_post* p; bool keep; ~Guard() { if (p && !keep) agp_post_free(p); } } guard{p, false};
+  cudaStream_t s = ctx->stream;
+  static const agp_mean zero_mean{0, 0.0, nullptr};
+  if (!mean) mean = &zero_mean;
+  const int64_t n_pad = p->n_pad;
+  const double log2pi = 1.8378770664093454835606594728112;
+  const int64_t chunk = 1024;
+  Scratch sc(ctx);
+  void* tmp = nullptr;
+  CK(sc.alloc(&tmp, (size_t)n_pad * chunk * sizeof(T)));
+  T* B = (T*)tmp;
+  CK(sc.alloc(&tmp, (size_t)chunk * sizeof(T)));
+  T* sq = (T*)tmp;
+  T* mean_d = nullptr;
+  if (mean->kind == 2) { rc = upload<T>(ctx, sc, mean->v, N, true, &mean_d); if (rc) return rc; }
+  std::vector<T> h_sq((size_t)chunk);
+  for (int64_t c0 = TILE; c0 < S; c0 += chunk) {
+    const int64_t nc = (S - c0 < chunk) ? (S - c0) : chunk, nc_pad = round_up(nc, TILE);
+    Scratch scc(ctx);
+    T* Yd = nullptr;
+    rc = upload<T>(ctx, scc, (const T*)Y + (size_t)c0 * N, (size_t)N * nc, false, &Yd);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(B, 0, (size_t)n_pad * nc_pad * sizeof(T), s));
+    CK(cudaMemsetAsync(sq, 0, (size_t)chunk * sizeof(T), s));
+    for (int64_t j = 0; j < nc; ++j) launch_sub_mean<T>(Yd + j * N, N, mean->kind, mean->c, mean_d, B + j * n_pad, s);
+    forward_subst_multi<T>(ctx, (const T*)p->L, p->lda, (const T*)p->Dinv, n_pad, B, n_pad, nc_pad);
+    launch_colsumsq_acc<T>(B, n_pad, n_pad, nc, 1.0, sq, s);
+    CK(cudaMemcpyAsync(h_sq.data(), sq, (size_t)nc * sizeof(T), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int64_t j = 0; j < nc; ++j)
+      ((T*)logpdf_out)[c0 + j] = (T)(-0.5 * ((double)N * log2pi + p->logdet + (double)h_sq[(size_t)j]));
+  }
+  CK(cudaGetLastError());
+  if (post_out) { *post_out = p; guard.keep = true; }
+  return AGP_OK;
+}
+
 template <typename T>
 int post_cross(agp_post* p, Scratch& sc, int layout, const void* Xs, int64_t M, int64_t m_pad, T** Xst, T** B) {
   agp_ctx* ctx = p->ctx;
@@ -2136,9 +2186,8 @@ int32_t agp_fit(agp_ctx* ctx, int32_t dtype, const agp_kernel* k, const agp_mean
     return DISPATCH(dtype, fit_dist_impl<float>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out, post_out),
                     fit_dist_impl<double>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out, post_out));
   }
-  return DISPATCH(dtype,
-                  fit_impl<float>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out, post_out, nullptr, nullptr, nullptr),
-                  fit_impl<double>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out, post_out, nullptr, nullptr, nullptr));
+  return DISPATCH(dtype, fit_many_impl<float>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out, post_out),
+                  fit_many_impl<double>(ctx, k, mean, noise, layout, X, N, D, Y, S, logpdf_out, alpha_out, post_out));
 }
 
 int32_t agp_post_mean_var(agp_post* p, int32_t layout, const void* Xs, int64_t M, const agp_mean* mean_s,

@@ -334,3 +334,18 @@ def test_vfe_golden_c5(ag):
     f = ag.GP(ag.with_lengthscale(ag.SqExponentialKernel(), np.sqrt(16) * 0.5))
     el, dt = ag.approx_log_evidence(ag.VFE(f(ag.RowVecs(Z), 1e-6)), f(ag.RowVecs(X), 0.1), y, return_dtc=True)
     assert abs(el - g["elbo"]) <= 1e-8 * abs(g["elbo"]) and abs(dt - g["dtc"]) <= 1e-8 * abs(g["dtc"])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_logpdf_many_columns(ag, dtype):
+    """logpdf(fx, Y::Matrix) with more columns than the border tile carries (src/finite_gp_projection.jl:306-311 has no
+    limit): 128 ride through the factorisation, the rest are solved against the same factor in the same call"""
+    n, d, S = 700, 3, 333
+    ks, X, y = problem(n, d, ref.MATERN52, dtype, seed=21)
+    rng = np.random.default_rng(6)
+    Y = (y[:, None] * rng.random(S)[None, :] + 0.1 * rng.standard_normal((n, S))).astype(dtype)
+    f = ag.GP(0.3, mk_kernel(ag, ks))
+    lp = ag.logpdf(f(ag.RowVecs(X), 0.2), Y)
+    lp_ref = ref.logpdf(ks, ref.MeanSpec(1, 0.3), ref.NoiseSpec(0, 0.2), X, Y)
+    assert lp.shape == (S,)
+    assert np.allclose(lp, lp_ref, rtol=TOL[dtype]["rtol"], atol=0 if dtype == np.float64 else 2e-2)

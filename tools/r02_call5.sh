@@ -13,7 +13,7 @@ timeout 600 bash -c "run 29551 tests/dist_fit_check.py" 2>&1 | grep -v "^W\|OMP_
 echo "== dist_fit_check, plain look-ahead schedule"
 AGP_DIST_SCHED=0 timeout 600 bash -c "run 29552 tests/dist_fit_check.py" 2>&1 | grep -v "^W\|OMP_NUM" | tail -4 | tee gpurun_out/r02c5_check_sched0_${N}.log
 port=29560
-for cfg in "2 16" "0 16" "2 8" "2 32"; do
+for cfg in ${CFGS:-"2 16" "0 16" "2 8" "2 32"}; do
   set -- $cfg
   port=$((port + 1))
   echo "== bench C4 N=$N AGP_DIST_SCHED=$1 reserve=$2"
