@@ -50,6 +50,7 @@ struct agp_ctx {
   int64_t oz_rows = 0, oz2_rows = 0;
   cudaStream_t stream_comm = nullptr;  // panel broadcasts of the pipelined distributed schedule
   int oz_S = 7;
+  int oz_chunk = 16;        // bounded-CTA size (tiles) of the rest updates that run beside a higher-priority stream; 0 = persistent
   int oz_S32 = 4;          // slices of the fp32 operands (4 x 7 bits >= the 24-bit significand)
 };
 
@@ -421,7 +422,9 @@ void cholesky_inplace(agp_ctx* ctx, T* L, int64_t lda, int64_t n_pad, int64_t ro
     if (cols_trail > next_cols) {
       const int64_t r0 = t0 + next_cols;
       cudaStreamWaitEvent(s2, e_panel, 0);
+      if (oz) oz->chunk_tiles = ctx->oz_chunk;  // the panel chain on the (higher-priority) main stream gets SMs between CTAs
       trailing_update<T>(ctx, L, lda, r0, r0, kc0, K, rows_total - r0, n_pad - r0, s2, oz, t0);
+      if (oz) oz->chunk_tiles = 0;
       cudaEventRecord(e_rest, s2);
       rest_pending = true;
       last_rest_full = true;
@@ -1789,7 +1792,11 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
       if (!oz_b) dist_sched = 0;
     }
   }
-  if (dist_sched == 2 && !ctx->stream_comm) CK(cudaStreamCreateWithFlags(&ctx->stream_comm, cudaStreamNonBlocking));
+  if (dist_sched == 2 && !ctx->stream_comm) {
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    CK(cudaStreamCreateWithPriority(&ctx->stream_comm, cudaStreamNonBlocking, prio_hi));
+  }
 
   // ---- Gram: only the local outer blocks, lower part, + border rows
   for (int lj = 0; lj < nloc; ++lj) {
@@ -1847,6 +1854,9 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
     if (e2) reserve_sms = atoi(e2);
     if (reserve_sms < 0 || reserve_sms > 64) reserve_sms = 16;
   }
+  // pipelined schedule: 1 = the owner of the next panel runs its rest update AFTER that panel's factorisation; 0 = at once
+  // (bounded CTAs + stream priorities let the factorisation through)
+  const bool dist_defer = env_int64("AGP_DIST_DEFER", 1) != 0;
   int nsm_dev = 148;
   cudaDeviceGetAttribute(&nsm_dev, cudaDevAttrMultiProcessorCount, ctx->device);
   struct DeferredRest { bool on; int kk; T* Pk; int lo, hi; bool use_oz; cudaEvent_t e_rest; };
@@ -1876,10 +1886,10 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
     struct Deferred { bool on; int kk; T* Pk; int lo, hi; bool use_oz; const OzakiWs* ws; cudaEvent_t e_prep; } dfr{false, 0, nullptr, 0, 0, false, nullptr, nullptr};
     auto issue_rest = [&](int kk, T* Pk, int lo, int hi, bool use_oz, const OzakiWs* ws) {
       e_rest[(size_t)kk] = ev();
-      if (ws) ws->max_ctas = nsm_dev - reserve_sms;
+      if (ws) { ws->max_ctas = nsm_dev - reserve_sms; ws->chunk_tiles = ctx->oz_chunk; }
       oz_cur = ws;
       trailing(kk, Pk, lo, hi, use_oz, s2);
-      if (ws) ws->max_ctas = 0;
+      if (ws) { ws->max_ctas = 0; ws->chunk_tiles = 0; }
       cudaEventRecord(e_rest[(size_t)kk], s2);
     };
     for (int kk = 0; kk < nto; ++kk) {
@@ -1937,7 +1947,7 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
         trailing(kk, Pk, lj_first, lj_first + 1, use_oz, s);
         lj_bulk = lj_first + 1;
       }
-      if (next_is_mine) {
+      if (next_is_mine && dist_defer) {
         dfr = Deferred{true, kk, Pk, lj_bulk, nloc, use_oz, use_oz ? ws_k : nullptr, e_prep};
       } else {
         cudaStreamWaitEvent(s2, e_prep, 0);
@@ -2102,9 +2112,15 @@ int32_t agp_init(agp_ctx** out, int32_t device, const agp_config* cfg) {
   ctx->oz_S32 = env_int("AGP_OZAKI_S32", 4);
   if (ctx->oz_S32 < 3 || ctx->oz_S32 > 5) ctx->oz_S32 = 4;
   if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
-  if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
-  if (cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
+  // priorities: the panel chain (main stream), the strip inverses and the panel broadcasts go first; the bulk trailing
+  // updates (stream2, bounded CTAs) fill whatever SMs are left -- block scheduling honours stream priority
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
+  if (cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
+  if (cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete ctx; return AGP_ERR_CUDA; }
+  ctx->oz_chunk = env_int("AGP_OZAKI_CHUNK", 16);
+  if (ctx->oz_chunk < 0 || ctx->oz_chunk > 4096) ctx->oz_chunk = 16;
   cudaEventCreateWithFlags(&ctx->ev_s3, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_fac, cudaEventDisableTiming);
   for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);

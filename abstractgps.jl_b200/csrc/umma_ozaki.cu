@@ -750,7 +750,15 @@ __device__ __forceinline__ double oz_combine(const uint32_t (&r)[S][8], int i) {
 }
 
 template <int S, int CL, int NEPI, int GE, typename CT>
-__global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v3_kernel(OzTileArgs a, int64_t ntiles, int nbi, int nbj) {
+__global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v3_kernel(OzTileArgs a, int64_t ntiles, int nbi, int nbj,
+                                                                                int tpc) {
+  // tpc = 0: persistent, CTA b walks slots b, b + grid, ...   tpc > 0: BOUNDED CTAs -- CTA b owns the tpc consecutive slots
+  // [b * tpc, (b + 1) * tpc) and exits; the grid is ceil(ntiles / tpc).  Bounded CTAs hand their SM back every ~0.1 ms, so
+  // kernels of a higher-priority stream (the panel chain, the NCCL broadcast) are scheduled between them instead of
+  // waiting for the whole update.
+  const int64_t t_begin = tpc ? (int64_t)blockIdx.x * tpc : (int64_t)blockIdx.x;
+  const int64_t t_end = tpc ? ((t_begin + tpc < ntiles) ? t_begin + tpc : ntiles) : ntiles;
+  const int64_t t_step = tpc ? 1 : (int64_t)gridDim.x;
   constexpr int A_BYTES = OZ_BM * V2_KB, B_BYTES = OZ_BN * V2_KB;
   constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
   constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
@@ -783,7 +791,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v3_kernel(O
     uint32_t it = 0;
     const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
     const int64_t rb_bytes = (int64_t)num_kb * S * 4096;  // bytes of one 128-row block (all k blocks, all slices)
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (int64_t t = t_begin; t < t_end; t += t_step) {
       int bi, bj;
       int64_t brow64;
       if (!v2_decode<GE>(a, t, nbi, nbj, bi, bj, brow64)) continue;
@@ -818,7 +826,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v3_kernel(O
     constexpr uint64_t DESC_HI = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);  // LBO, SBO, version
     const uint32_t stage0_lo = (smem_u32(base) & 0x3FFFF) >> 4;
     uint32_t it = 0, lt = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (int64_t t = t_begin; t < t_end; t += t_step) {
       {
         int bi_, bj_;
         int64_t br_;
@@ -860,7 +868,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v3_kernel(O
     const int c0 = (NEPI == 4) ? 0 : ((warp - 2) >> 2) * CB;      // warps 2-5: columns [0, CB), warps 6-9: [CB, 2 CB)
     const bool pair32 = (a.epi == 1);
     uint32_t lt = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (int64_t t = t_begin; t < t_end; t += t_step) {
       int bi, bj;
       int64_t brow64;
       if (!v2_decode<GE>(a, t, nbi, nbj, bi, bj, brow64)) continue;
@@ -980,7 +988,7 @@ void launch_v2_variant(const OzakiWs& ws, const OzTileArgs& a, int64_t ntiles, i
 
 
 template <int S, int CL, int NEPI, int GE, typename CT = double>
-void launch_v3_variant(const OzTileArgs& a, int64_t ntiles, int nbi, int nbj, int cap, size_t smem, cudaStream_t s) {
+void launch_v3_variant(const OzTileArgs& a, int64_t ntiles, int nbi, int nbj, int cap, size_t smem, cudaStream_t s, int tpc = 0) {
   static int max_clusters[64] = {0};  // per device; 0 = not queried yet
   static uint64_t configured = 0;
   constexpr unsigned THREADS = 64 + 32 * NEPI;
@@ -1006,9 +1014,11 @@ void launch_v3_variant(const OzTileArgs& a, int64_t ntiles, int nbi, int nbj, in
   int64_t grid = (int64_t)max_clusters[dev & 63] * CL;
   if (grid > cap) grid = cap / CL * CL;
   if (grid > ntiles) grid = ntiles / CL * CL;  // the slot count is even when CL = 2 is selected
+  if (CL > 1) tpc = 0;  // CTA pairs walk the slots in lockstep: persistent form only
+  if (tpc > 0) grid = (ntiles + tpc - 1) / tpc;
   if (grid <= 0) return;
   lc.gridDim = dim3((unsigned)grid);
-  cudaLaunchKernelEx(&lc, umma_ozaki_syrk_v3_kernel<S, CL, NEPI, GE, CT>, a, ntiles, nbi, nbj);
+  cudaLaunchKernelEx(&lc, umma_ozaki_syrk_v3_kernel<S, CL, NEPI, GE, CT>, a, ntiles, nbi, nbj, tpc);
 }
 
 template <int S, typename CT = double>
@@ -1112,17 +1122,17 @@ void launch_syrk_v2_S(const OzakiWs& ws, void* C, int64_t ldc, int64_t M, int64_
     const int ew = (f && atoi(f) == 4) ? 4 : 8;
     const bool cl2 = want_cl == 2 && (!a.strip_start || ge) && ntiles >= 2;
     if constexpr (std::is_same<CT, double>::value && S >= 5) {
-      if (ge && cl2 && ew == 8) launch_v3_variant<S, 2, 8, 1>(a, ntiles, nbi, nbj, cap, smem, s);
-      else if (ge && cl2) launch_v3_variant<S, 2, 4, 1>(a, ntiles, nbi, nbj, cap, smem, s);
-      else if (ge && ew == 8) launch_v3_variant<S, 1, 8, 1>(a, ntiles, nbi, nbj, cap, smem, s);
-      else if (ge) launch_v3_variant<S, 1, 4, 1>(a, ntiles, nbi, nbj, cap, smem, s);
-      else if (cl2 && ew == 8) launch_v3_variant<S, 2, 8, 0>(a, ntiles, nbi, nbj, cap, smem, s);
-      else if (cl2) launch_v3_variant<S, 2, 4, 0>(a, ntiles, nbi, nbj, cap, smem, s);
-      else if (ew == 8) launch_v3_variant<S, 1, 8, 0>(a, ntiles, nbi, nbj, cap, smem, s);
-      else launch_v3_variant<S, 1, 4, 0>(a, ntiles, nbi, nbj, cap, smem, s);
+      if (ge && cl2 && ew == 8) launch_v3_variant<S, 2, 8, 1>(a, ntiles, nbi, nbj, cap, smem, s, ws.chunk_tiles);
+      else if (ge && cl2) launch_v3_variant<S, 2, 4, 1>(a, ntiles, nbi, nbj, cap, smem, s, ws.chunk_tiles);
+      else if (ge && ew == 8) launch_v3_variant<S, 1, 8, 1>(a, ntiles, nbi, nbj, cap, smem, s, ws.chunk_tiles);
+      else if (ge) launch_v3_variant<S, 1, 4, 1>(a, ntiles, nbi, nbj, cap, smem, s, ws.chunk_tiles);
+      else if (cl2 && ew == 8) launch_v3_variant<S, 2, 8, 0>(a, ntiles, nbi, nbj, cap, smem, s, ws.chunk_tiles);
+      else if (cl2) launch_v3_variant<S, 2, 4, 0>(a, ntiles, nbi, nbj, cap, smem, s, ws.chunk_tiles);
+      else if (ew == 8) launch_v3_variant<S, 1, 8, 0>(a, ntiles, nbi, nbj, cap, smem, s, ws.chunk_tiles);
+      else launch_v3_variant<S, 1, 4, 0>(a, ntiles, nbi, nbj, cap, smem, s, ws.chunk_tiles);
     } else {  // fp32 output and / or short (3-, 4-slice) splits: the two main variants only
-      if (cl2) launch_v3_variant<S, 2, 8, 0, CT>(a, ntiles, nbi, nbj, cap, smem, s);
-      else launch_v3_variant<S, 1, 8, 0, CT>(a, ntiles, nbi, nbj, cap, smem, s);
+      if (cl2) launch_v3_variant<S, 2, 8, 0, CT>(a, ntiles, nbi, nbj, cap, smem, s, ws.chunk_tiles);
+      else launch_v3_variant<S, 1, 8, 0, CT>(a, ntiles, nbi, nbj, cap, smem, s, ws.chunk_tiles);
     }
     agp_count_launch();
     return;

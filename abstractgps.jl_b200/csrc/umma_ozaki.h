@@ -19,6 +19,7 @@ struct OzakiWs {
   int32_t* tab_bimin;  // consecutive calls (main / side stream) alternate slots
   int tab_cap;
   mutable int tab_slot;
+  mutable int chunk_tiles;  // v3 kernel: > 0 -> bounded CTAs of this many consecutive tiles (see the kernel), 0 -> persistent
   mutable int max_ctas;  // persistent (v2) kernel: cap on the grid, 0 = one CTA per SM.  The distributed schedule leaves
                          // a few SMs to the NCCL broadcast that overlaps the update.
 };

@@ -556,6 +556,12 @@ def run_ours(args, wl, n_full):
     if rank == 0:
         sampler.start()
     t_dev, wall_dev, launches = timed(prob, torch, flush, True, args.steps, args.warmup, dist)
+    if args.quick:  # development runs (schedule sweeps): device-resident timing only, no e2e / parity / roofline / CPU arm
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps({"quick": True, "n_gpus": world, "workload": wl, "value": t_dev["total"], "unit": "ms",
+                              "phases_ms": t_dev, "result": float(prob.lp[0]), "steps": args.steps}))
+        return
     t_e2e, wall_e2e, _ = timed(prob, torch, flush, False, args.steps, args.warmup, dist)
     clocks = sampler.stop() if rank == 0 else None
     lp_val = float(prob.lp[0])
@@ -632,6 +638,7 @@ def main():
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=None, help="override N of the workload (development / shard-sized runs)")
     ap.add_argument("--no-c2", action="store_true", help="skip the secondary C2 measurement on the N=1 C4 line")
+    ap.add_argument("--quick", action="store_true", help="development: device-resident timing only (not a bench line)")
     args = ap.parse_args()
     if args.impl == "ours":
         args.warmup = max(args.warmup, 3)

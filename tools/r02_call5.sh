@@ -10,10 +10,22 @@ run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-
 export -f run; export N
 echo "== dist_fit_check, pipelined schedule (default)"
 timeout 600 bash -c "run 29551 tests/dist_fit_check.py" 2>&1 | grep -v "^W\|OMP_NUM" | tail -12 | tee gpurun_out/r02c5_check_sched2_${N}.log
+if [ "${CHECK_PLAIN:-1}" = "1" ]; then
 echo "== dist_fit_check, plain look-ahead schedule"
 AGP_DIST_SCHED=0 timeout 600 bash -c "run 29552 tests/dist_fit_check.py" 2>&1 | grep -v "^W\|OMP_NUM" | tail -4 | tee gpurun_out/r02c5_check_sched0_${N}.log
+fi
+# quick schedule sweep: "sched reserve defer chunk"
+IFS=";" read -ra SWEEP <<< "${SWEEP:-}"
+port=29580
+for cfg in "${SWEEP[@]}"; do
+  set -- $cfg
+  port=$((port + 1))
+  echo "== quick C4 N=$N sched=$1 reserve=$2 defer=$3 chunk=$4"
+  AGP_DIST_SCHED=$1 AGP_DIST_RESERVE_SMS=$2 AGP_DIST_DEFER=$3 AGP_OZAKI_CHUNK=$4 timeout 600 bash -c "run $port bench.py --gpus $N --steps 3 --warmup 3 --quick" 2>/dev/null | tail -1 | cut -c1-400
+done
 port=29560
-for cfg in ${CFGS:-"2 16" "0 16" "2 8" "2 32"}; do
+IFS=";" read -ra CFG_LIST <<< "${CFGS:-2 16;0 16;2 8;2 32}"
+for cfg in "${CFG_LIST[@]}"; do
   set -- $cfg
   port=$((port + 1))
   echo "== bench C4 N=$N AGP_DIST_SCHED=$1 reserve=$2"
