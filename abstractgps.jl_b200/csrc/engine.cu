@@ -2022,20 +2022,30 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
   for (int sI = 0; sI < S; ++sI) launch_sumsq<T>(rwork + (size_t)sI * n_pad, n_pad, dscal + nt + sI, s);
   if (R > 1) CKN(ncclAllReduce(dscal, dscal, (size_t)(nt + TILE), ncclDouble, ncclSum, ctx->nccl, s));
   // ---- distributed backward substitution for column 0: alpha = L^-T v.  The owner of an outer block holds its G diagonal
-  // blocks and every tile between them, so it resolves the whole block locally (G dependent steps) and ONE broadcast per
-  // outer block ships G*128 values (128 collectives at C4, was 512); the other ranks then apply the block in one launch.
-  for (int io = nto - 1; io >= 0; --io) {
-    const int owner = io % R, i_lo = io * G;
-    if (owner == me) {
-      for (int i = i_lo + G - 1; i >= i_lo; --i) {
-        T* a_i = alpha + (int64_t)i * TILE;
-        launch_bwd_diag<T>(Dinv + ((int64_t)(io / R) * G + (i % G)) * TILE * TILE, rwork + (int64_t)i * TILE, a_i, s);
-        if (i > 0) launch_bwd_update_local<T>(L, lda, i, a_i, rwork, nloc * G, me, R, G, s);
+  // blocks and every tile between them, so it resolves the whole block in ONE single-CTA kernel; ONE broadcast per outer
+  // block ships G*128 values (128 collectives at C4).  The critical chain per block is
+  //   [alpha of block io+1 arrives] -> update of block io only (G CTAs) -> block solve -> broadcast;
+  // the bulk update of the other local columns with block io+1's alpha runs behind the broadcast on the owner and before it
+  // on the other ranks (who would otherwise idle in the collective).
+  {
+    int pending = -1;  // outer block whose alpha has been received but not yet applied to (all of) the local columns
+    for (int io = nto - 1; io >= 0; --io) {
+      const int owner = io % R, i_lo = io * G;
+      const int64_t p_lo = (int64_t)(pending >= 0 ? pending : 0) * G;
+      T* a_pend = alpha + p_lo * TILE;
+      if (owner == me) {
+        if (pending >= 0)  // own block first
+          launch_bwd_update_local_multi<T>(L, lda, (int)p_lo, G, a_pend, rwork, nloc * G, me, R, G, i_lo, (int64_t)i_lo + G, s);
+        launch_bwd_block_solve<T>(L + (int64_t)io * W + (int64_t)(io / R) * W * lda, lda, Dinv + (int64_t)(io / R) * G * TILE * TILE,
+                                  rwork + (int64_t)i_lo * TILE, alpha + (int64_t)i_lo * TILE, G, s);
+      } else if (pending >= 0) {
+        launch_bwd_update_local_multi<T>(L, lda, (int)p_lo, G, a_pend, rwork, nloc * G, me, R, G, 0, p_lo, s);
       }
+      if (R > 1) CKN(ncclBroadcast(alpha + (int64_t)i_lo * TILE, alpha + (int64_t)i_lo * TILE, (size_t)G * TILE, NcclType<T>::v, owner, ctx->nccl, s));
+      if (owner == me && pending >= 0)
+        launch_bwd_update_local_multi<T>(L, lda, (int)p_lo, G, a_pend, rwork, nloc * G, me, R, G, 0, i_lo, s);
+      pending = io;
     }
-    if (R > 1) CKN(ncclBroadcast(alpha + (int64_t)i_lo * TILE, alpha + (int64_t)i_lo * TILE, (size_t)G * TILE, NcclType<T>::v, owner, ctx->nccl, s));
-    if (owner != me && i_lo > 0)
-      launch_bwd_update_local_multi<T>(L, lda, i_lo, G, alpha + (int64_t)i_lo * TILE, rwork, nloc * G, me, R, G, s);
   }
   launch_finalize_logpdf<T>(dscal, nt, dscal + nt, S, N, lp_d, dscal + nt + TILE, s);
   CK(cudaEventRecord(ctx->ev[4], s));

@@ -80,7 +80,10 @@ template <typename T> void launch_bwd_diag(const T* Dinv_i, const T* r_i, T* alp
 template <typename T> void launch_bwd_update_local(const T* Lloc, int64_t lda, int i_blk, const T* alpha_i, T* r, int nloc,
                                                    int rank, int nranks, int G, cudaStream_t s);
 template <typename T> void launch_bwd_update_local_multi(const T* Lloc, int64_t lda, int i_lo, int Gn, const T* alpha_lo, T* r,
-                                                         int nloc, int rank, int nranks, int G, cudaStream_t s);
+                                                         int nloc, int rank, int nranks, int G, int64_t j_min, int64_t j_max,
+                                                         cudaStream_t s);
+template <typename T> void launch_bwd_block_solve(const T* Lblk, int64_t lda, const T* Dinv_blk, const T* r_blk, T* alpha_blk,
+                                                  int Gn, cudaStream_t s);
 template <typename T> void launch_finalize_logpdf(const double* logdet_part, int nblk, const double* sq, int S,
                                                   int64_t n, T* out, double* logdet_out, cudaStream_t s);
 // mu[j] = mean_j + sum_i B[i + j*ldb] * alpha[i]

@@ -222,11 +222,11 @@ __global__ void __launch_bounds__(256) bwd_update_local_kernel(const T* __restri
 template <typename T>
 __global__ void __launch_bounds__(256) bwd_update_local_multi_kernel(const T* __restrict__ Lloc, int64_t lda, int i_lo, int Gn,
                                                                       const T* __restrict__ alpha_lo, T* __restrict__ r,
-                                                                      int rank, int nranks, int G) {
+                                                                      int rank, int nranks, int G, int64_t j_min, int64_t j_max) {
   __shared__ T ak[8 * TB];
   const int lj = blockIdx.x;
   const int64_t j = ((int64_t)(lj / G) * nranks + rank) * G + (lj % G);
-  if (j >= i_lo) return;
+  if (j >= i_lo || j < j_min || j >= j_max) return;
   const int tid = threadIdx.x, o = tid >> 1, h = tid & 1;
   for (int q = tid; q < Gn * TB; q += 256) ak[q] = alpha_lo[q];
   __syncthreads();
@@ -613,13 +613,46 @@ void launch_bwd_update_local(const T* Lloc, int64_t lda, int i_blk, const T* alp
 }
 template <typename T>
 void launch_bwd_update_local_multi(const T* Lloc, int64_t lda, int i_lo, int Gn, const T* alpha_lo, T* r, int nloc, int rank,
-                                   int nranks, int G, cudaStream_t s) {
-  if (nloc <= 0 || Gn <= 0) return;
-  bwd_update_local_multi_kernel<T><<<nloc, 256, 0, s>>>(Lloc, lda, i_lo, Gn, alpha_lo, r, rank, nranks, G);
+                                   int nranks, int G, int64_t j_min, int64_t j_max, cudaStream_t s) {
+  if (nloc <= 0 || Gn <= 0 || j_max <= j_min) return;
+  bwd_update_local_multi_kernel<T><<<nloc, 256, 0, s>>>(Lloc, lda, i_lo, Gn, alpha_lo, r, rank, nranks, G, j_min, j_max);
   agp_count_launch();
 }
-template void launch_bwd_update_local_multi<float>(const float*, int64_t, int, int, const float*, float*, int, int, int, int, cudaStream_t);
-template void launch_bwd_update_local_multi<double>(const double*, int64_t, int, int, const double*, double*, int, int, int, int, cudaStream_t);
+template void launch_bwd_update_local_multi<float>(const float*, int64_t, int, int, const float*, float*, int, int, int, int, int64_t, int64_t, cudaStream_t);
+template void launch_bwd_update_local_multi<double>(const double*, int64_t, int, int, const double*, double*, int, int, int, int, int64_t, int64_t, cudaStream_t);
+
+// one outer block of the distributed backward substitution resolved by ONE CTA on its owner: for g = Gn-1 .. 0
+//   alpha_g = inv(L_gg)' r_g,   r_g' -= L(g, g')' alpha_g  (g' < g)
+// Lblk points at the block's diagonal element in the owner's local storage; r_blk / alpha_blk are its Gn*128 entries.
+template <typename T>
+__global__ void __launch_bounds__(256) bwd_block_solve_kernel(const T* __restrict__ Lblk, int64_t lda, const T* __restrict__ Dinv_blk,
+                                                               const T* __restrict__ r_blk, T* __restrict__ alpha_blk, int Gn) {
+  __shared__ T rs[8 * TB];
+  __shared__ T as[TB];
+  const int tid = threadIdx.x, o = tid >> 1, h = tid & 1;
+  for (int q = tid; q < Gn * TB; q += 256) rs[q] = r_blk[q];
+  __syncthreads();
+  for (int g = Gn - 1; g >= 0; --g) {
+    double acc = col_dot_half<T>(Dinv_blk + (int64_t)g * TB * TB + o * TB, rs + g * TB, h);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (h == 0) { as[o] = (T)acc; alpha_blk[g * TB + o] = (T)acc; }
+    __syncthreads();
+    for (int gp = 0; gp < g; ++gp) {
+      const T* tile = Lblk + (int64_t)g * TB + ((int64_t)gp * TB + o) * lda;
+      double a2 = col_dot_half<T>(tile, as, h);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+      if (h == 0) rs[gp * TB + o] -= (T)a2;
+    }
+    __syncthreads();
+  }
+}
+template <typename T>
+void launch_bwd_block_solve(const T* Lblk, int64_t lda, const T* Dinv_blk, const T* r_blk, T* alpha_blk, int Gn, cudaStream_t s) {
+  bwd_block_solve_kernel<T><<<1, 256, 0, s>>>(Lblk, lda, Dinv_blk, r_blk, alpha_blk, Gn);
+  agp_count_launch();
+}
+template void launch_bwd_block_solve<float>(const float*, int64_t, const float*, const float*, float*, int, cudaStream_t);
+template void launch_bwd_block_solve<double>(const double*, int64_t, const double*, const double*, double*, int, cudaStream_t);
 
 // explicit instantiations
 template void launch_border_init_cols<float>(float*, int64_t, int64_t, int64_t, int64_t, int64_t, const float*, int64_t, int, int, double, const float*, cudaStream_t);
