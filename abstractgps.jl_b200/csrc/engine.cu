@@ -571,6 +571,12 @@ int fit_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
   prof_begin(ctx);
   CK(cudaEventRecord(ctx->ev[0], s));
 
+  // the factor is allocated FIRST: the stream-ordered pool then hands back the block the previous fit freed, before the small
+  // staging buffers below can split it (a split forces a fresh multi-GB allocation from the OS: 0.1-0.6 s, seen as a
+  // sporadic e2e-only slowdown in round 2, tools/dist1_probe.py)
+  void* Lv = nullptr;
+  CK(cudaMallocAsync(&Lv, (size_t)lda * n_pad * sizeof(T), s));
+  struct BufGuard { void* p; cudaStream_t s; ~BufGuard() { if (p) cudaFreeAsync(p, s); } } lguard{Lv, s};  // error returns
   // ---- H2D
   T *ard_d = nullptr, *mean_d = nullptr, *noise_d = nullptr, *Yd = nullptr, *Xt = nullptr;
   if (k->transform == AGP_T_ARD) { rc = upload<T>(ctx, sc, k->ard, D, true, &ard_d); if (rc) return rc; }
@@ -583,14 +589,16 @@ int fit_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
   CK(cudaEventRecord(ctx->ev[1], s));
 
   // ---- buffers
-  void *Lv = nullptr, *Dinvv = nullptr, *alphav = nullptr;
-  CK(cudaMallocAsync(&Lv, (size_t)lda * n_pad * sizeof(T), s));
+  void *Dinvv = nullptr, *alphav = nullptr;
+  lguard.p = nullptr;  // ownership passes to the handle / scratch lists below
   CK(cudaMallocAsync(&Dinvv, (size_t)nblk * TILE * TILE * sizeof(T), s));
   CK(cudaMallocAsync(&alphav, (size_t)n_pad * sizeof(T), s));
   T* L = (T*)Lv; T* Dinv = (T*)Dinvv; T* alpha = (T*)alphav;
   agp_post* post = nullptr;
+  struct PostGuard { agp_post* p; ~PostGuard() { if (p) agp_post_free(p); } } pguard{nullptr};  // early error returns
   if (keep) {
     post = new agp_post();
+    pguard.p = post;
     post->ctx = ctx; post->dtype = sizeof(T) == 8 ? AGP_F64 : AGP_F32;
     post->n = N; post->n_pad = n_pad; post->lda = lda; post->D = D;
     post->L = Lv; post->Dinv = Dinvv; post->Xt = Xt; post->alpha = alphav;
@@ -670,9 +678,9 @@ int fit_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
     char b[128];
     snprintf(b, sizeof(b), "matrix is not positive definite; Cholesky failed at pivot %d", h_info);
     ctx->err = b;
-    if (post) { agp_post_free(post); }
-    return AGP_ERR_NOT_POSDEF;
+    return AGP_ERR_NOT_POSDEF;  // the guard releases the handle
   }
+  pguard.p = nullptr;
   if (post) { post->logdet = h_logdet; *post_out = post; }
   if (L_keep) { *L_keep = L; *lda_out = lda; }
   return AGP_OK;
@@ -1723,6 +1731,12 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
   const int fp64_mode = resolve_fp64_mode(ctx, n_pad);
   prof_begin(ctx);
   CK(cudaEventRecord(ctx->ev[0], s));
+  // big buffers FIRST (the local block columns, then the packed panels): the pool returns the blocks the previous fit freed
+  // before the small staging buffers can split them (see fit_impl)
+  void *Lv = nullptr, *Dv = nullptr, *Pv = nullptr;
+  CK(cudaMallocAsync(&Lv, (size_t)lda * (nloc > 0 ? nloc : 1) * W * sizeof(T), s));
+  struct BufGuard { void* p; cudaStream_t s; ~BufGuard() { if (p) cudaFreeAsync(p, s); } } lguard{Lv, s};
+  CK(sc.alloc(&Pv, (size_t)3 * lda * W * sizeof(T)));
   T *ard_d = nullptr, *mean_d = nullptr, *noise_d = nullptr, *Yd = nullptr, *Xt = nullptr;
   if (k->transform == AGP_T_ARD) { rc = upload<T>(ctx, sc, k->ard, D, true, &ard_d); if (rc) return rc; }
   if (mean->kind == 2) { rc = upload<T>(ctx, sc, mean->v, N, true, &mean_d); if (rc) return rc; }
@@ -1733,8 +1747,7 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
   void* tmp = nullptr;
   // the factor and its inverse diagonal blocks outlive the call when a posterior handle is requested
   agp_post* post = nullptr;
-  void *Lv = nullptr, *Dv = nullptr;
-  CK(cudaMallocAsync(&Lv, (size_t)lda * (nloc > 0 ? nloc : 1) * W * sizeof(T), s));
+  lguard.p = nullptr;  // ownership passes to the handle / scratch list below
   CK(cudaMallocAsync(&Dv, (size_t)(nloc > 0 ? nloc : 1) * G * TILE * TILE * sizeof(T), s));
   if (keep) {
     post = new agp_post();
@@ -1752,8 +1765,7 @@ int fit_dist_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
   struct PostGuard { agp_post* p; ~PostGuard() { if (p) agp_post_free(p); } } guard{post};  // freed on every error return
   T* L = (T*)Lv;
   T* Dinv = (T*)Dv;  // inverse diagonal blocks of the LOCAL 128-blocks
-  CK(sc.alloc(&tmp, (size_t)3 * lda * W * sizeof(T)));
-  T* P[3] = {(T*)tmp, (T*)tmp + lda * W, (T*)tmp + 2 * lda * W};  // packed panels (rows_below x W, ld = rows_below): two in
+  T* P[3] = {(T*)Pv, (T*)Pv + lda * W, (T*)Pv + 2 * lda * W};  // packed panels (rows_below x W, ld = rows_below): two in
                                                                    // flight in the default schedule, three in the pipelined one
   CK(sc.alloc(&tmp, (size_t)(nt + TILE + 4) * sizeof(double)));
   double* dscal = (double*)tmp;  // [0..nt) logdet parts, [nt..nt+TILE) sqmahal, [nt+TILE] logdet
@@ -2114,7 +2126,7 @@ int32_t agp_init(agp_ctx** out, int32_t device, const agp_config* cfg) {
   if (ctx->cfg.tile_nb % TILE) ctx->cfg.tile_nb = 0;
   ctx->cfg.fp64_mode = env_int("AGP_FP64_MODE", cfg ? ctx->cfg.fp64_mode : -1);            // -1 = auto
   ctx->cfg.fp32_mode = env_int("AGP_FP32_MODE", cfg ? ctx->cfg.fp32_mode : -1);            // -1 = auto
-  ctx->cfg.lookahead = env_int("AGP_LOOKAHEAD", cfg ? ctx->cfg.lookahead : 1);
+  ctx->cfg.lookahead = env_int("AGP_LOOKAHEAD", cfg ? ctx->cfg.lookahead : 2);  // 2: depth-2 look-ahead on the DMMA path (validated in round 2: C2 3.49 -> 3.27 ms)
   ctx->cfg.use_graph = env_int("AGP_GRAPH", ctx->cfg.use_graph);
   ctx->profile = env_int("AGP_PROFILE", cfg ? cfg->profile_kernels : 0);
   ctx->oz_S = env_int("AGP_OZAKI_S", (cfg && cfg->ozaki_slices) ? cfg->ozaki_slices : 7);

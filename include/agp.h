@@ -78,7 +78,8 @@ typedef struct {
                             1 = int8-sliced (Ozaki) trailing update on tcgen05.mma.kind::i8 */
   int32_t fp32_mode;     /* -1 auto (tcgen05 from n_pad >= 4096), 0 = FFMA tile kernels, 1 = int8-sliced trailing update /
                             triangular solves on tcgen05.mma.kind::i8 (4 seven-bit slices cover the fp32 significand) */
-  int32_t lookahead;     /* 0/1: overlap the next panel with the bulk of the trailing update */
+  int32_t lookahead;     /* 0 off, 1: overlap the next panel with the bulk of the trailing update, 2 (default): additionally
+                            split the bulk so that the chain waits only for the panel-after-next block (DMMA path) */
   int32_t use_graph;     /* reserved */
   int32_t ozaki_slices;  /* 5..8 seven-bit slices of the tcgen05 fp64 path; 0 -> 7 (~2^-49 of the row scale) */
   int32_t profile_kernels; /* 1: CUDA events around every trailing-update launch (agp_last_timings[7]); default 0 */

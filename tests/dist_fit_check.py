@@ -60,9 +60,9 @@ def main():
             eng.check(eng.L.agp_post_factor_export(post, cabi.ptr(U)))
             good_p &= bool(np.allclose(U, pr["U"], rtol=1e-7 if dtype == np.float64 else 1e-2, atol=1e-9 if dtype == np.float64 else 2e-3))
         eng.L.agp_post_free(post)
-        if rank == 0:
-            print("n=%d %s fam=%d: logpdf %s ref %s  ok=%s  posterior(mean_and_var, logdet, U) ok=%s"
-                  % (n, np.dtype(dtype).name, fam, lp, lp_ref, good, good_p), flush=True)
+        if rank == 0 or not (good and good_p):
+            print("[rank %d] n=%d %s fam=%d: logpdf %s ref %s  ok=%s  posterior(mean_and_var, logdet, U) ok=%s  max|dmu|=%.3g max|dvar|=%.3g"
+                  % (rank, n, np.dtype(dtype).name, fam, lp, lp_ref, good, good_p, np.abs(mu - mu_r).max(), np.abs(var - var_r).max()), flush=True)
         ok &= bool(good) and bool(good_p)
     # a case large enough for the tcgen05 trailing update with the block-cyclic strip table (n_pad >= 8192, W = 512)
     if os.environ.get("DIST_CHECK_LARGE", "1") == "1":
@@ -91,8 +91,8 @@ def main():
         mu_r, var_r = ref.post_mean_and_var(pr, Xs)
         good &= np.allclose(mu, mu_r, rtol=1e-6, atol=1e-7) and np.allclose(var, var_r, rtol=1e-6, atol=1e-8)
         eng.L.agp_post_free(post)
-        if rank == 0:
-            print("large n=%d (tcgen05 + strip table): logpdf %r ref %r ok=%s" % (n, lp[0], lp_ref, bool(good)), flush=True)
+        if rank == 0 or not good:
+            print("[rank %d] large n=%d (tcgen05 + strip table): logpdf %r ref %r ok=%s" % (rank, n, lp[0], lp_ref, bool(good)), flush=True)
         ok &= bool(good)
     # VFE elbo with the data dimension sharded over the ranks (one all-reduce): must match the oracle
     for dtype in (np.float64, np.float32):
@@ -115,8 +115,8 @@ def main():
         el = ref.elbo(ksr, ref.MeanSpec(), ref.NoiseSpec(0, 0.1), X.astype(np.float64), yv.astype(np.float64),
                       Z.astype(np.float64), ref.NoiseSpec(0, js.s))
         good = abs(out[0] - el) <= (1e-8 if dtype == np.float64 else 2e-3) * abs(el)
-        if rank == 0:
-            print("vfe %s: elbo %r ref %r ok=%s" % (np.dtype(dtype).name, out[0], el, good), flush=True)
+        if rank == 0 or not good:
+            print("[rank %d] vfe %s: elbo %r ref %r ok=%s" % (rank, np.dtype(dtype).name, out[0], el, good), flush=True)
         ok &= bool(good)
     # non-PD must surface on every rank, not hang
     n = 200
@@ -129,6 +129,8 @@ def main():
     lp = np.zeros(1)
     rc = eng.L.agp_fit(eng.h, cabi.AGP_F64, C.byref(ks), None, C.byref(ns), cabi.AGP_POINT_MAJOR, cabi.ptr(X), n, 1,
                        cabi.ptr(Y), 1, cabi.ptr(lp), None, None)
+    if rc != cabi.AGP_ERR_NOT_POSDEF:
+        print("[rank %d] non-PD case returned %d instead of AGP_ERR_NOT_POSDEF" % (rank, rc), flush=True)
     ok &= (rc == cabi.AGP_ERR_NOT_POSDEF)
     import torch
     import torch.distributed as dist

@@ -9,7 +9,7 @@ mkdir -p gpurun_out
 run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
 export -f run; export N
 echo "== dist_fit_check, pipelined schedule (default)"
-timeout 600 bash -c "run 29551 tests/dist_fit_check.py" 2>&1 | grep -v "^W\|OMP_NUM" | tail -12 | tee gpurun_out/r02c5_check_sched2_${N}.log
+timeout 600 bash -c "run 29551 tests/dist_fit_check.py" 2>&1 | grep -v "^W\|OMP_NUM\|^\*\*\*" | tail -40 | tee gpurun_out/r02c5_check_sched2_${N}.log
 if [ "${CHECK_PLAIN:-1}" = "1" ]; then
 echo "== dist_fit_check, plain look-ahead schedule"
 AGP_DIST_SCHED=0 timeout 600 bash -c "run 29552 tests/dist_fit_check.py" 2>&1 | grep -v "^W\|OMP_NUM" | tail -4 | tee gpurun_out/r02c5_check_sched0_${N}.log
