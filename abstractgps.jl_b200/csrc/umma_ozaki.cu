@@ -478,227 +478,6 @@ __device__ __forceinline__ bool v2_decode(const OzTileArgs& a, int64_t t, int nb
   return ok;
 }
 
-// CL = CTAs per cluster (1 or 2).  CL = 2: the two CTAs of a cluster take slots 2u and 2u + 1 of the enumeration --
-// the same 128-row tile bi and the two 64-column strips of one 128-column block -- so they read the SAME A slices;
-// each CTA fetches half of every 4 KB A chunk and multicasts it to both (28 KB instead of 43 KB per K chunk and SM
-// from L2).  Validity of the two slots is identical (row bi owns an even number of strips, N is a multiple of 128),
-// so both CTAs run the same sequence of tiles and K chunks in lockstep.
-// NEPI = epilogue warps (4 or 8).  8: two warps per TMEM lane quarter, 32 of the tile's 64 columns each -- the drain
-// (tcgen05.ld + int->fp64 + Horner) is 12-15 % of the kernel and is issue / latency bound per warp, not TMEM bound.
-template <int S, int CL, int NEPI, int GE>
-__global__ void __launch_bounds__(64 + 32 * NEPI, 1) umma_ozaki_syrk_v2_kernel(const __grid_constant__ CUtensorMap tmapA,
-                                                                    const __grid_constant__ CUtensorMap tmapB, OzTileArgs a,
-                                                                    int64_t ntiles, int nbi, int nbj) {
-  constexpr int A_BYTES = OZ_BM * V2_KB, B_BYTES = OZ_BN * V2_KB;
-  constexpr int STAGE_BYTES = S * (A_BYTES + B_BYTES);
-  constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
-  __shared__ uint32_t tmem_base_s;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
-  auto a_tile = [&](int st, int sl) { return base + st * STAGE_BYTES + sl * A_BYTES; };
-  auto b_tile = [&](int st, int sl) { return base + st * STAGE_BYTES + S * A_BYTES + sl * B_BYTES; };
-
-  if (warp == 0 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
-    mbar_init(&tmem_full_bar, 1);
-    mbar_init(&tmem_empty_bar, NEPI);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if constexpr (CL > 1) cluster_sync_all();  // every CTA's barriers exist before a peer's copy / commit can hit them
-  const uint32_t tmem_base = tmem_base_s;
-  const int num_kb = a.K / V2_KB;
-  constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1);
-
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        int bi, bj;
-        int64_t brow64;
-        if (!v2_decode<GE>(a, t, nbi, nbj, bi, bj, brow64)) continue;
-        const int arow = (int)(bi * OZ_BM + a.a_off), brow = (int)brow64;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int st = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty_bar[st], ph ^ 1);
-          if (a.epi == 5) { mbar_arrive(&full_bar[st]); continue; }  // PROBE 5: MMA-only loop, no operand traffic
-          mbar_expect_tx(&full_bar[st], STAGE_BYTES);
-          if (a.SLb) {  // contiguous 4 KB / 2 KB chunks already in the UMMA smem layout: 1-D bulk copies
-            const int64_t nrb = a.m_alloc >> 7, nkb = a.K >> 5;
-#pragma unroll 1
-            for (int sl = 0; sl < S; ++sl) {
-              const int8_t* ca = a.SLb + (((int64_t)sl * nrb + (arow >> 7)) * nkb + kb) * 4096;
-              const int8_t* cb = a.SLb + (((int64_t)sl * nrb + (brow >> 7)) * nkb + kb) * 4096 + (brow & 64) * 32;
-              if constexpr (CL > 1) {  // rows [64 r, 64 r + 64) of the A chunk are contiguous (8-row groups of 256 B)
-                constexpr int PART = A_BYTES / CL;
-                const uint32_t r = cluster_ctarank();
-                bulk_load_mc(a_tile(st, sl) + r * PART, ca + r * PART, PART, &full_bar[st], CL_MASK);
-              } else {
-                bulk_load(a_tile(st, sl), ca, A_BYTES, &full_bar[st]);
-              }
-              bulk_load(b_tile(st, sl), cb, B_BYTES, &full_bar[st]);
-            }
-          } else {
-#pragma unroll 1
-            for (int sl = 0; sl < S; ++sl) {
-              const int rbase = (int)(sl * a.m_alloc);
-              tma_load_2d(a_tile(st, sl), &tmapA, kb * V2_KB, rbase + arow, &full_bar[st]);
-              tma_load_2d(b_tile(st, sl), &tmapB, kb * V2_KB, rbase + brow, &full_bar[st]);
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_base = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
-      uint32_t it = 0, lt = 0;
-      for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        {
-          int bi_, bj_;
-          int64_t br_;
-          if (!v2_decode<GE>(a, t, nbi, nbj, bi_, bj_, br_)) continue;
-        }
-        mbar_wait(&tmem_empty_bar, (lt & 1) ^ 1);  // epilogue has drained the previous tile's accumulators
-        tc_fence_after();
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int st = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full_bar[st], ph);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(a_tile(st, 0)), b0 = smem_u32(b_tile(st, 0));
-#pragma unroll 1
-          for (int sl = (a.epi == 6 ? S : 0); sl < S; ++sl) {  // PROBE 6: operand traffic only, no MMAs
-            const int Ns = (S - sl) * OZ_BN;
-            const uint64_t adesc = a.SLb ? umma_desc_nosw(a0 + sl * A_BYTES) : umma_desc_sw32(a0 + sl * A_BYTES);
-            for (int c = 0; c < Ns; c += 256) {
-              const int nchunk = (Ns - c < 256) ? (Ns - c) : 256;
-              const uint64_t bdesc = a.SLb ? umma_desc_nosw(b0 + c * V2_KB) : umma_desc_sw32(b0 + c * V2_KB);
-              const uint32_t idesc = idesc_base | ((uint32_t)(nchunk >> 3) << 17);
-              umma_i8(tmem_base + (uint32_t)(sl * OZ_BN + c), adesc, bdesc, idesc, (kb == 0 && sl == 0) ? 0u : 1u);
-            }
-          }
-          if constexpr (CL > 1) umma_commit_mc(&empty_bar[st], CL_MASK);
-          else umma_commit(&empty_bar[st]);
-        }
-        umma_commit(&tmem_full_bar);
-        ++lt;
-      }
-    }
-  } else {
-    const int quarter = warp & 3;
-    constexpr int CB = OZ_BN * 4 / NEPI;                          // columns drained by one epilogue warp
-    const int c0 = (NEPI == 4) ? 0 : ((warp - 2) >> 2) * CB;      // warps 2-5: columns [0, CB), warps 6-9: [CB, 2 CB)
-    uint32_t lt = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      int bi, bj;
-      int64_t brow64;
-      if (!v2_decode<GE>(a, t, nbi, nbj, bi, bj, brow64)) continue;
-      const int64_t m0 = (int64_t)bi * OZ_BM, n0 = (int64_t)bj * OZ_BN + c0;
-      brow64 += c0;
-      const int64_t row = m0 + 32 * quarter + lane;
-      const bool row_ok = row < a.M;
-      const double rs = row_ok ? a.rscale[row + a.a_off] * (1.0 / 4096.0) : 0.0;
-      double* crow = (double*)a.C + row;
-      mbar_wait(&tmem_full_bar, lt & 1);
-      tc_fence_after();
-      // (1) drain TMEM: Horner-combine the S int32 accumulators of all 64 columns into registers, 8 columns per
-      //     trip (all S loads of a trip in flight before one wait), then hand the accumulators back to the MMA
-      //     warp -- the C read-modify-write below overlaps the next tile's MMAs.
-      double v[CB];
-      if (a.epi >= 3 && a.epi != 7) {  // PROBE: no drain at all (3, 4, 5, 6) -- results are garbage, timing only
-#pragma unroll
-        for (int i = 0; i < CB; ++i) v[i] = 0.0;
-      } else {
-#pragma unroll
-      for (int c8 = 0; c8 < CB; c8 += 8) {
-        uint32_t r[S][8];
-#pragma unroll
-        for (int d = 0; d < S; ++d)
-          tmem_ld8_nowait(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(d * OZ_BN + c0 + c8), r[d]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (a.epi == 7) {  // PROBE 7: TMEM reads only, one int op per value, one conversion per element
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint32_t x = r[0][i];
-#pragma unroll
-            for (int d = 1; d < S; ++d) x ^= r[d][i];
-            v[c8 + i] = __hiloint2double(0x43300000, (int)x);
-          }
-        } else if (a.epi == 1) {
-          // adjacent diagonals combined exactly in int32 first: |ACC_d| <= (d+1) * K * 64 * 64, so for K <= 512
-          // t_j = 128 * ACC_2j + ACC_2j+1 stays below 2^31 up to S = 8.  4 int->fp64 conversions and 4 fp64 ops
-          // per element instead of 7 and 6 (S = 7): the drain is bound by the fp64 pipe, not by tcgen05.ld.
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            double acc;
-            if constexpr (S & 1) {
-              acc = (double)(int)r[S - 1][i];
-              acc = fma(acc, 1.0 / 128.0, (double)((int)r[S - 3][i] * 128 + (int)r[S - 2][i]));
-#pragma unroll
-              for (int d = S - 5; d >= 0; d -= 2)
-                acc = fma(acc, 1.0 / 16384.0, (double)((int)r[d][i] * 128 + (int)r[d + 1][i]));
-            } else {
-              acc = (double)((int)r[S - 2][i] * 128 + (int)r[S - 1][i]);
-#pragma unroll
-              for (int d = S - 4; d >= 0; d -= 2)
-                acc = fma(acc, 1.0 / 16384.0, (double)((int)r[d][i] * 128 + (int)r[d + 1][i]));
-            }
-            v[c8 + i] = acc * (1.0 / 128.0);
-          }
-        } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          double acc = (double)(int)r[S - 1][i];
-#pragma unroll
-          for (int d = S - 2; d >= 0; --d) acc = fma(acc, 1.0 / 128.0, (double)(int)r[d][i]);
-          v[c8 + i] = acc;
-        }
-        }
-      }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar);
-      // (2) C -= scale_i * scale_j * v, streamed (.cs) so the int8 slices stay resident in L2
-      if (row_ok && a.epi != 2 && a.epi != 3 && a.epi != 5 && a.epi != 6) {  // PROBE 2/3/5/6: no C read-modify-write
-#pragma unroll
-        for (int c = 0; c < CB; c += 16) {
-          double cv[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int64_t col = n0 + c + i;
-            cv[i] = (col < a.N) ? ld_cs(crow + col * a.ldc) : 0.0;
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int64_t col = n0 + c + i;
-            if (col < a.N) st_cs(crow + col * a.ldc, fma(-v[c + i] * rs, a.rscale[brow64 + c + i], cv[i]));
-          }
-        }
-      }
-      ++lt;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while a peer can still copy into it / arrive on its barriers
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-  }
-}
-
-
 // ---------------------------------------------------------------------------------------------
 // v3: same algorithm and tile walk as v2, restructured after the round-2 probe (profiles/r02_call1_*): the v2 main loop
 // ran at the SAME speed with its operand traffic switched off -- it was bound by the single issuing thread (~38 SASS
@@ -956,37 +735,6 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// launch of an experimental variant (cluster size CL, NEPI epilogue warps) through cudaLaunchKernelEx; the persistent
-// grid must be fully co-resident, so with clusters it is capped by cudaOccupancyMaxActiveClusters
-template <int S, int CL, int NEPI, int GE>
-void launch_v2_variant(const OzakiWs& ws, const OzTileArgs& a, int64_t ntiles, int nbi, int nbj, int cap, size_t smem,
-                       cudaStream_t s) {
-  static int max_clusters = -1;
-  constexpr unsigned THREADS = 64 + 32 * NEPI;
-  cudaLaunchConfig_t lc{};
-  lc.blockDim = dim3(THREADS); lc.dynamicSmemBytes = smem; lc.stream = s;
-  cudaLaunchAttribute la[1];
-  la[0].id = cudaLaunchAttributeClusterDimension;
-  la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
-  lc.attrs = la; lc.numAttrs = 1;
-  if (max_clusters < 0) {
-    cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S, CL, NEPI, GE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lc.gridDim = dim3((unsigned)(cap / CL * CL));
-    max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, umma_ozaki_syrk_v2_kernel<S, CL, NEPI, GE>, &lc) != cudaSuccess) {
-      max_clusters = 0;
-      cudaGetLastError();
-    }
-  }
-  int64_t grid = (int64_t)max_clusters * CL;
-  if (grid > cap) grid = cap / CL * CL;
-  if (grid > ntiles) grid = ntiles / CL * CL;  // the closed-form slot count is even
-  if (grid <= 0) return;
-  lc.gridDim = dim3((unsigned)grid);
-  cudaLaunchKernelEx(&lc, umma_ozaki_syrk_v2_kernel<S, CL, NEPI, GE>, ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
-}
-
-
 template <int S, int CL, int NEPI, int GE, typename CT = double>
 void launch_v3_variant(const OzTileArgs& a, int64_t ntiles, int nbi, int nbj, int cap, size_t smem, cudaStream_t s, int tpc = 0) {
   static int max_clusters[64] = {0};  // per device; 0 = not queried yet
@@ -1030,8 +778,6 @@ void launch_syrk_v2_S(const OzakiWs& ws, void* C, int64_t ldc, int64_t M, int64_
   static uint64_t configured = 0;  // per-device bit: the attribute is per device (one ctx per GPU in one process)
   static int nsm = 148;
   if (agp_first_use_on_device(&configured)) {
-    if constexpr (S >= 5 && std::is_same<CT, double>::value)
-      cudaFuncSetAttribute(umma_ozaki_syrk_v2_kernel<S, 1, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -1060,7 +806,7 @@ void launch_syrk_v2_S(const OzakiWs& ws, void* C, int64_t ldc, int64_t M, int64_
     // AGP_OZAKI_EPI=0 restores the plain Horner drain, >= 2 are the timing-only variants of tools/ozaki_probe.py.
     const char* e = getenv("AGP_OZAKI_EPI");
     a.epi = e ? atoi(e) : 1;
-    if (a.epi == 1 && (ws.K > 512 || (S != 7 && ws.bulk != 2))) a.epi = 0;  // the int32 pair bound needs K <= 512 (v2: validated for S = 7 only)
+    if (a.epi == 1 && ws.K > 512) a.epi = 0;  // the int32 pair bound needs K <= 512
   }
   const int nbi = (int)((M + OZ_BM - 1) / OZ_BM), nbj = (int)(N / OZ_BN);
   int64_t ntiles = 0;
@@ -1117,7 +863,7 @@ void launch_syrk_v2_S(const OzakiWs& ws, void* C, int64_t ldc, int64_t M, int64_
   if (ntiles <= 0) return;
   const int cap = (ws.max_ctas > 0 && ws.max_ctas < nsm) ? ws.max_ctas : nsm;
   const bool ge = want_ge && a.strip_start;
-  if (ws.bulk == 2) {  // v3 kernel (default): 8 epilogue warps unless AGP_OZAKI_EPIWARPS=4; CTA pairs with AGP_OZAKI_CLUSTER=2
+  {  // 8 epilogue warps unless AGP_OZAKI_EPIWARPS=4; CTA pairs with AGP_OZAKI_CLUSTER=2
     const char* f = getenv("AGP_OZAKI_EPIWARPS");
     const int ew = (f && atoi(f) == 4) ? 4 : 8;
     const bool cl2 = want_cl == 2 && (!a.strip_start || ge) && ntiles >= 2;
@@ -1135,34 +881,13 @@ void launch_syrk_v2_S(const OzakiWs& ws, void* C, int64_t ldc, int64_t M, int64_
       else launch_v3_variant<S, 1, 8, 0, CT>(a, ntiles, nbi, nbj, cap, smem, s, ws.chunk_tiles);
     }
     agp_count_launch();
-    return;
-  }
-  if constexpr (!(S >= 5 && std::is_same<CT, double>::value)) return;  // the round-1 kernels exist for fp64, S >= 5 only
-  else {
-  if (want_cl == 2 || want_ew == 8 || ge) {
-    // CTA pairs need slots 2u, 2u + 1 on the same row tile: the closed-form order and the grouped table order give that
-    const bool cl2 = want_cl == 2 && a.SLb && (!a.strip_start || ge) && ntiles >= 2;
-    if (ge && cl2 && want_ew == 8) launch_v2_variant<S, 2, 8, 1>(ws, a, ntiles, nbi, nbj, cap, smem, s);
-    else if (ge && cl2) launch_v2_variant<S, 2, 4, 1>(ws, a, ntiles, nbi, nbj, cap, smem, s);
-    else if (ge && want_ew == 8) launch_v2_variant<S, 1, 8, 1>(ws, a, ntiles, nbi, nbj, cap, smem, s);
-    else if (ge) launch_v2_variant<S, 1, 4, 1>(ws, a, ntiles, nbi, nbj, cap, smem, s);
-    else if (cl2 && want_ew == 8) launch_v2_variant<S, 2, 8, 0>(ws, a, ntiles, nbi, nbj, cap, smem, s);
-    else if (cl2) launch_v2_variant<S, 2, 4, 0>(ws, a, ntiles, nbi, nbj, cap, smem, s);
-    else if (want_ew == 8) launch_v2_variant<S, 1, 8, 0>(ws, a, ntiles, nbi, nbj, cap, smem, s);
-    else launch_v2_variant<S, 1, 4, 0>(ws, a, ntiles, nbi, nbj, cap, smem, s);
-    agp_count_launch();
-    return;
-  }
-  const int grid = (int)(ntiles < cap ? ntiles : cap);
-  umma_ozaki_syrk_v2_kernel<S, 1, 4, 0><<<grid, 192, smem, s>>>(ws.tmapA32, ws.tmapB32, a, ntiles, nbi, nbj);
-  agp_count_launch();
   }
 }
 
 template <int S>
 void launch_syrk_S(const OzakiWs& ws, double* C, int64_t ldc, int64_t M, int64_t N, int lower_only, int64_t b_tile_stride,
                    int64_t b_tile_width, int64_t b_off, int64_t a_off, cudaStream_t s) {
-  if ((ws.use_v2 || ws.bulk) && lower_only && N % 128 == 0 && N >= 128 && N / OZ_BN <= ws.tab_cap) {
+  if (ws.bulk == 2 && lower_only && N % 128 == 0 && N >= 128 && N / OZ_BN <= ws.tab_cap) {
     launch_syrk_v2_S<S>(ws, C, ldc, M, N, b_tile_stride, b_tile_width, b_off, a_off, s);
     return;
   }
@@ -1201,19 +926,8 @@ int ozaki_ws_create(OzakiWs* ws, int64_t max_rows, int K, int S, cudaStream_t s)
   CUresult r = enc(&ws->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ws->SL, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return 4;
-  cuuint32_t boxA[2] = {(cuuint32_t)V2_KB, (cuuint32_t)OZ_BM}, boxB[2] = {(cuuint32_t)V2_KB, (cuuint32_t)OZ_BN};
-  r = enc(&ws->tmapA32, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ws->SL, gdim, gstr, boxA, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-          CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return 4;
-  r = enc(&ws->tmapB32, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ws->SL, gdim, gstr, boxB, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-          CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return 4;
-  const char* v = getenv("AGP_OZAKI_V2");
-  ws->use_v2 = v ? atoi(v) : 1;
-  const char* b = getenv("AGP_OZAKI_BULK");
-  ws->bulk = (ws->use_v2 && (b ? atoi(b) : 1)) ? 1 : 0;
-  const char* kv = getenv("AGP_OZAKI_KERNEL");  // 3 (default): v3 kernel + [row block][k block][slice] layout; 2: the round-1 kernel
-  if (ws->bulk == 1 && !(kv && atoi(kv) == 2)) ws->bulk = 2;
+  ws->bulk = 2;  // [row block][k block][slice] layout of the persistent kernel; the debug entry clears it for generic shapes
+  { const char* ct = getenv("AGP_OZAKI_CHUNK_TEST"); ws->chunk_tiles = ct ? atoi(ct) : 0; }  // tests: bounded CTAs everywhere
   return 0;
 }
 

@@ -12,9 +12,8 @@ struct OzakiWs {
   int K;            // panel width (bytes per slice row), multiple of 64
   int S;            // number of 7-bit slices (5..8)
   CUtensorMap tmap; // 2-D uint8 tensor (K, S*m_alloc), box 64 B x 64 rows, 64-byte swizzle (v1 kernel)
-  CUtensorMap tmapA32, tmapB32;  // same tensor, 32 B x 128 / 64 rows, 32-byte swizzle (persistent v2 kernel)
-  int use_v2;
-  int bulk;   // 1: slices are stored in the blocked UMMA layout and fetched with 1-D bulk copies (v2 kernel only)
+  int bulk;   // 2: slices in the blocked UMMA layout [row block][k block][slice] fetched with 1-D bulk copies (persistent kernel);
+              // 0: row-major slices behind the tensor map (non-persistent kernel, generic shapes)
   int64_t* tab_start;  // device tables of the block-cyclic tile enumeration (v2), two slots of tab_cap+1 entries:
   int32_t* tab_bimin;  // consecutive calls (main / side stream) alternate slots
   int tab_cap;

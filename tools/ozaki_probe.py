@@ -159,17 +159,6 @@ def cluster_part():
             save()
     os.environ["AGP_OZAKI_CLUSTER"] = "1"
     os.environ.pop("AGP_OZAKI_EPIWARPS", None)
-    # the round-1 kernel on the same problem, for the record
-    os.environ["AGP_OZAKI_KERNEL"] = "2"
-    for epi in (1, 3, 5, 6):
-        t = syrk(epi, M)
-        d = {"ms": t, "syrk_ms": t - fixed, "fp64_equiv_tflops": flops / ((t - fixed) * 1e-3) / 1e12}
-        if epi == 1:
-            _, got = sample()
-            d["max_rel_diff_vs_default"] = float(max(np.max(np.abs(r - w) / sc) for r, w, sc in zip(got, base, scale)))
-        res["kernel_v2_epi%d" % epi] = d
-        save()
-    os.environ.pop("AGP_OZAKI_KERNEL", None)
 
 
 run_cluster_last = os.environ.get("PROBE_CLUSTER") == "1"
