@@ -42,3 +42,15 @@ except Exception as e:
     print("parse failed", e)
 PY
 done
+if [ "${RUN_C5:-0}" = "1" ]; then
+  echo "== bench C5 (VFE, N = 10^6, M = 8192, fp32) on $N GPUs"
+  timeout 900 bash -c "run 29599 bench.py --gpus $N --workload C5 --steps 3 --warmup 3" 2>/dev/null | tail -1 > gpurun_out/r02c5_bench_c5_${N}gpu.json
+  python - "$N" <<'PY'
+import json, sys
+try:
+    d = json.loads(open("gpurun_out/r02c5_bench_c5_%sgpu.json" % sys.argv[1]).read().strip().splitlines()[-1])
+    print("C5 value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "phases", {k: round(v, 1) for k, v in d["phases_ms"].items()}, "elbo", d["result"], "parity", d["parity"], "roofline", {k: d["roofline"].get(k) for k in ("achieved", "peak", "frac")})
+except Exception as e:
+    print("parse failed", e)
+PY
+fi
