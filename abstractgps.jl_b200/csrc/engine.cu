@@ -736,6 +736,19 @@ int fit_many_impl(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const
   return AGP_OK;
 }
 
+// rows [c0, c0 + mc) of a feature-major point set (M x D column-major, host or device per the context's memspace) gathered
+// into a contiguous mc x D feature-major DEVICE block: chunked prediction over RowVecs inputs larger than one chunk
+template <typename T>
+int gather_feature_major_chunk(agp_ctx* ctx, Scratch& sc, const void* Xs, int64_t M, int D, int64_t c0, int64_t mc, T** out) {
+  void* d = nullptr;
+  CK(sc.alloc(&d, (size_t)mc * D * sizeof(T)));
+  const cudaMemcpyKind kind = ctx->memspace == AGP_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  CK(cudaMemcpy2DAsync(d, (size_t)mc * sizeof(T), (const T*)Xs + c0, (size_t)M * sizeof(T), (size_t)mc * sizeof(T), (size_t)D, kind,
+                       ctx->stream));
+  *out = (T*)d;
+  return AGP_OK;
+}
+
 template <typename T>
 int post_cross(agp_post* p, Scratch& sc, int layout, const void* Xs, int64_t M, int64_t m_pad, T** Xst, T** B) {
   agp_ctx* ctx = p->ctx;
@@ -761,6 +774,7 @@ int post_mean_var_impl(agp_post* p, int layout, const void* Xs, int64_t M, const
   CK(cudaEventRecord(ctx->ev[0], s));
   // chunk the test points so that the N x Mc cross-Gram stays <= ~4 GB
   int64_t cap = (int64_t)(4.0e9 / ((double)p->n_pad * sizeof(T)));
+  { const int64_t c_env = env_int64("AGP_PREDICT_CHUNK", 0); if (c_env > 0) cap = c_env; }  // tests: force small chunks
   cap = cap / TILE * TILE;
   if (cap < TILE) cap = TILE;
   agp_mean mz{p->mean_kind, p->mean_c, nullptr};
@@ -771,15 +785,23 @@ int post_mean_var_impl(agp_post* p, int layout, const void* Xs, int64_t M, const
     Scratch sc(ctx);
     const char* xs_c = (const char*)Xs;
     const void* xs_chunk = nullptr;
-    std::vector<char> stage;
+    const int saved_memspace = ctx->memspace;
     if (layout == AGP_POINT_MAJOR) {
       xs_chunk = xs_c + (size_t)c0 * p->D * sizeof(T);
-    } else {
-      if (c0 == 0 && mc == M) xs_chunk = Xs;
-      else { ctx->err = "feature-major test sets larger than one chunk are unsupported"; return AGP_ERR_UNSUPPORTED; }
+    } else if (c0 == 0 && mc == M) {
+      xs_chunk = Xs;
+    } else {  // RowVecs test set larger than one chunk: gather the chunk's rows on the device
+      T* g = nullptr;
+      int grc = gather_feature_major_chunk<T>(ctx, sc, Xs, M, p->D, c0, mc, &g);
+      if (grc) return grc;
+      xs_chunk = g;
+      ctx->memspace = AGP_MEM_DEVICE;  // the gathered block is a device pointer (inputs only; outputs use the override below)
     }
     T *Xst = nullptr, *B = nullptr;
     int rc = post_cross<T>(p, sc, layout, xs_chunk, mc, m_pad, &Xst, &B);
+    const bool out_dev_saved = ctx->out_dev_override;
+    if (ctx->memspace != saved_memspace) { ctx->memspace = saved_memspace; }
+    (void)out_dev_saved;
     if (rc) return rc;
     T *mean_d = nullptr, *noise_d = nullptr;
     if (mean_s->kind == 2) { rc = upload<T>(ctx, sc, (const T*)mean_s->v + c0, mc, true, &mean_d); if (rc) return rc; }
@@ -1538,19 +1560,25 @@ int vfe_mean_var_impl(agp_vfe_post* p, int layout, const void* Xs, int64_t Ms, v
   CK(cudaSetDevice(ctx->device));
   if (Ms <= 0) return AGP_OK;
   int64_t cap = (int64_t)(2.0e9 / ((double)p->m_pad * sizeof(T)));
+  { const int64_t c_env = env_int64("AGP_PREDICT_CHUNK", 0); if (c_env > 0) cap = c_env; }
   cap = cap / TILE * TILE;
   if (cap < TILE) cap = TILE;
   for (int64_t c0 = 0; c0 < Ms; c0 += cap) {
     const int64_t mc = (Ms - c0 < cap) ? (Ms - c0) : cap;
     const int64_t c_pad = round_up(mc, TILE);
     Scratch sc(ctx);
-    if (layout != AGP_POINT_MAJOR && !(c0 == 0 && mc == Ms)) {
-      ctx->err = "feature-major test sets larger than one chunk are unsupported";
-      return AGP_ERR_UNSUPPORTED;
-    }
     const void* xs_chunk = (layout == AGP_POINT_MAJOR) ? (const void*)((const char*)Xs + (size_t)c0 * p->D * sizeof(T)) : Xs;
+    const int saved_memspace = ctx->memspace;
+    if (layout != AGP_POINT_MAJOR && !(c0 == 0 && mc == Ms)) {  // RowVecs test set larger than one chunk
+      T* g = nullptr;
+      int grc = gather_feature_major_chunk<T>(ctx, sc, Xs, Ms, p->D, c0, mc, &g);
+      if (grc) return grc;
+      xs_chunk = g;
+      ctx->memspace = AGP_MEM_DEVICE;
+    }
     T* Xst = nullptr;
     int rc = prep_points<T>(ctx, sc, &p->k, (const T*)p->ard, layout, xs_chunk, mc, c_pad, p->D, &Xst, false);
+    ctx->memspace = saved_memspace;
     if (rc) return rc;
     void* tmp = nullptr;
     CK(sc.alloc(&tmp, (size_t)p->m_pad * c_pad * sizeof(T)));

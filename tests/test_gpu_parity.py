@@ -349,3 +349,40 @@ def test_logpdf_many_columns(ag, dtype):
     lp_ref = ref.logpdf(ks, ref.MeanSpec(1, 0.3), ref.NoiseSpec(0, 0.2), X, Y)
     assert lp.shape == (S,)
     assert np.allclose(lp, lp_ref, rtol=TOL[dtype]["rtol"], atol=0 if dtype == np.float64 else 2e-2)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_chunked_prediction_rowvecs_and_colvecs(ag, dtype, monkeypatch):
+    """test sets larger than one prediction chunk in BOTH storage orders (RowVecs = feature-major needs a strided gather per
+    chunk): forced 256-column chunks must reproduce the single-chunk result exactly, for the exact and the VFE posterior"""
+    n, d, M = 400, 3, 700
+    ks, X, y = problem(n, d, ref.MATERN32, dtype, seed=9)
+    Xs = np.random.default_rng(2).random((M, d)).astype(dtype)
+    f = ag.GP(0.1, mk_kernel(ag, ks))
+    post = ag.posterior(f(ag.RowVecs(X), 0.1), y)
+    vp = ag.posterior(ag.VFE(f(ag.RowVecs(X[:60].copy()), 1e-4)), f(ag.RowVecs(X), 0.1), y)
+    eng = ag.engine()
+    import ctypes as C
+    from agp_b200 import _cabi as cabi
+
+    def raw_mean_var(handle_call, layout, arr):
+        mu, var = np.zeros(M, dtype=dtype), np.zeros(M, dtype=dtype)
+        eng.check(handle_call(layout, cabi.ptr(arr), mu, var))
+        return mu, var
+
+    def exact(layout, arr, mu, var):
+        return eng.L.agp_post_mean_var(post.data.C.h, layout, arr, M, None, None, cabi.ptr(mu), cabi.ptr(var))
+
+    def vfe(layout, arr, mu, var):
+        return eng.L.agp_vfe_mean_var(vp.h, layout, arr, M, cabi.ptr(mu), cabi.ptr(var))
+    pm = np.ascontiguousarray(Xs)            # point-major: [M, d] C-order
+    fm = np.asfortranarray(Xs)               # feature-major: M x d column-major
+    for call in (exact, vfe):
+        base = raw_mean_var(call, cabi.AGP_POINT_MAJOR, pm)
+        monkeypatch.setenv("AGP_PREDICT_CHUNK", "256")
+        got_pm = raw_mean_var(call, cabi.AGP_POINT_MAJOR, pm)
+        got_fm = raw_mean_var(call, cabi.AGP_FEATURE_MAJOR, fm)
+        monkeypatch.delenv("AGP_PREDICT_CHUNK")
+        for got in (got_pm, got_fm):
+            tol = dict(rtol=1e-12, atol=1e-13) if dtype == np.float64 else dict(rtol=1e-5, atol=1e-6)
+            assert np.allclose(got[0], base[0], **tol) and np.allclose(got[1], base[1], **tol)
