@@ -94,6 +94,31 @@ def main():
         if rank == 0 or not good:
             print("[rank %d] large n=%d (tcgen05 + strip table): logpdf %r ref %r ok=%s" % (rank, n, lp[0], lp_ref, bool(good)), flush=True)
         ok &= bool(good)
+    # repeated fits at sizes where every rank owns few outer blocks (n_pad = a small multiple of 512 x ranks): steps are short,
+    # so any missing dependency between the main-stream chain and the side-stream rest updates shows up as a wrong logpdf
+    # (or a non-PD exit); the result must be identical from run to run
+    if os.environ.get("DIST_CHECK_LARGE", "1") == "1":
+        for n in (8192, 6144, 12288):
+            d = 8
+            cfg = ref.make_config("C4", n=n)
+            X = np.ascontiguousarray(cfg["X"][:, :d])
+            yv = np.asfortranarray(cfg["y"].reshape(-1, 1))
+            ksr = ref.KernelSpec(ref.SE, 1.0, ref.T_SCALE, scale=1.0 / (0.5 * np.sqrt(d)))
+            ks = cabi.agp_kernel()
+            ks.family, ks.transform, ks.variance, ks.scale = 0, 1, 1.0, ksr.scale
+            ns = cabi.agp_noise()
+            ns.kind, ns.s = 0, 0.1
+            lp_ref = ref.logpdf(ksr, ref.MeanSpec(), ref.NoiseSpec(0, 0.1), X, yv[:, 0])
+            vals = []
+            for rep in range(4):
+                lp = np.zeros(1)
+                rc = eng.L.agp_fit(eng.h, cabi.AGP_F64, C.byref(ks), None, C.byref(ns), cabi.AGP_POINT_MAJOR, cabi.ptr(X), n, d,
+                                   cabi.ptr(yv), 1, cabi.ptr(lp), None, None)
+                vals.append((rc, float(lp[0])))
+            good = all(rc == 0 and abs(v - lp_ref) <= 1e-8 * abs(lp_ref) for rc, v in vals) and len({v for _, v in vals}) == 1
+            if rank == 0 or not good:
+                print("[rank %d] repeat n=%d: %s ref %r ok=%s" % (rank, n, vals, lp_ref, good), flush=True)
+            ok &= bool(good)
     # VFE elbo with the data dimension sharded over the ranks (one all-reduce): must match the oracle
     for dtype in (np.float64, np.float32):
         n, m, d = 3000, 200, 4
