@@ -18,7 +18,8 @@ def main():
     eng = init_distributed_engine()
     rank = getattr(eng, "rank", 0)
     ok = True
-    for (n, d, dtype, fam) in [(300, 3, np.float64, ref.SE), (1537, 8, np.float64, ref.MATERN32), (1000, 4, np.float32, ref.SE),
+    only_stress = os.environ.get("DIST_CHECK_ONLY_STRESS") == "1"
+    for (n, d, dtype, fam) in [] if only_stress else [(300, 3, np.float64, ref.SE), (1537, 8, np.float64, ref.MATERN32), (1000, 4, np.float32, ref.SE),
                                (128, 2, np.float64, ref.SE), (2100, 6, np.float64, ref.MATERN52)]:
         rng = np.random.default_rng(n)
         X = rng.random((n, d)).astype(dtype)
@@ -65,7 +66,7 @@ def main():
                   % (rank, n, np.dtype(dtype).name, fam, lp, lp_ref, good, good_p, np.abs(mu - mu_r).max(), np.abs(var - var_r).max()), flush=True)
         ok &= bool(good) and bool(good_p)
     # a case large enough for the tcgen05 trailing update with the block-cyclic strip table (n_pad >= 8192, W = 512)
-    if os.environ.get("DIST_CHECK_LARGE", "1") == "1":
+    if os.environ.get("DIST_CHECK_LARGE", "1") == "1" and not only_stress:
         n, d = 8704, 8
         cfg = ref.make_config("C4", n=n)
         X = np.ascontiguousarray(cfg["X"][:, :d])
@@ -98,7 +99,10 @@ def main():
     # so any missing dependency between the main-stream chain and the side-stream rest updates shows up as a wrong logpdf
     # (or a non-PD exit); the result must be identical from run to run
     if os.environ.get("DIST_CHECK_LARGE", "1") == "1":
-        for n in (8192, 6144, 12288):
+        sizes = (8192, 6144, 12288)
+        if os.environ.get("DIST_CHECK_SIZES"):
+            sizes = tuple(int(v) for v in os.environ["DIST_CHECK_SIZES"].split(","))
+        for n in sizes:
             d = 8
             cfg = ref.make_config("C4", n=n)
             X = np.ascontiguousarray(cfg["X"][:, :d])
@@ -115,12 +119,14 @@ def main():
                 rc = eng.L.agp_fit(eng.h, cabi.AGP_F64, C.byref(ks), None, C.byref(ns), cabi.AGP_POINT_MAJOR, cabi.ptr(X), n, d,
                                    cabi.ptr(yv), 1, cabi.ptr(lp), None, None)
                 vals.append((rc, float(lp[0])))
-            good = all(rc == 0 and abs(v - lp_ref) <= 1e-8 * abs(lp_ref) for rc, v in vals) and len({v for _, v in vals}) == 1
+            # (the sqmahal reduction uses floating-point atomics: the last bits may differ from run to run)
+            good = all(rc == 0 and abs(v - lp_ref) <= 1e-8 * abs(lp_ref) for rc, v in vals) and \
+                max(v for _, v in vals) - min(v for _, v in vals) <= 1e-11 * abs(lp_ref)
             if rank == 0 or not good:
                 print("[rank %d] repeat n=%d: %s ref %r ok=%s" % (rank, n, vals, lp_ref, good), flush=True)
             ok &= bool(good)
     # VFE elbo with the data dimension sharded over the ranks (one all-reduce): must match the oracle
-    for dtype in (np.float64, np.float32):
+    for dtype in () if only_stress else (np.float64, np.float32):
         n, m, d = 3000, 200, 4
         rng = np.random.default_rng(5)
         X = rng.random((n, d)).astype(dtype)

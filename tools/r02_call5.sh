@@ -9,7 +9,11 @@ mkdir -p gpurun_out
 run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
 export -f run; export N
 echo "== dist_fit_check, pipelined schedule (default)"
-timeout 600 bash -c "run 29551 tests/dist_fit_check.py" 2>&1 | grep -v "^W\|OMP_NUM\|^\*\*\*" | tail -40 | tee gpurun_out/r02c5_check_sched2_${N}.log
+timeout 600 bash -c "run 29551 tests/dist_fit_check.py" > gpurun_out/r02c5_check_sched2_${N}.full.log 2>&1
+grep "^\[rank\|DIST_" gpurun_out/r02c5_check_sched2_${N}.full.log | cut -c1-330 | tee gpurun_out/r02c5_check_sched2_${N}.log
+echo "== dist_fit_check stress with forced 512-wide tcgen05 panels at small n (few blocks per rank)"
+AGP_NB=512 AGP_FP64_MODE=1 DIST_CHECK_ONLY_STRESS=1 DIST_CHECK_SIZES=${STRESS_SIZES:-2048,2560,3072,4096,5120} timeout 600 bash -c "run 29553 tests/dist_fit_check.py" > gpurun_out/r02c5_check_stress_${N}.full.log 2>&1
+grep "^\[rank\|DIST_" gpurun_out/r02c5_check_stress_${N}.full.log | cut -c1-330 | tee gpurun_out/r02c5_check_stress_${N}.log
 if [ "${CHECK_PLAIN:-1}" = "1" ]; then
 echo "== dist_fit_check, plain look-ahead schedule"
 AGP_DIST_SCHED=0 timeout 600 bash -c "run 29552 tests/dist_fit_check.py" 2>&1 | grep -v "^W\|OMP_NUM" | tail -4 | tee gpurun_out/r02c5_check_sched0_${N}.log
@@ -26,6 +30,7 @@ done
 port=29560
 IFS=";" read -ra CFG_LIST <<< "${CFGS:-2 16;0 16;2 8;2 32}"
 for cfg in "${CFG_LIST[@]}"; do
+  [ "${RUN_BENCH:-1}" = "1" ] || break
   set -- $cfg
   port=$((port + 1))
   echo "== bench C4 N=$N AGP_DIST_SCHED=$1 reserve=$2"
