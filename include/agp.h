@@ -205,6 +205,9 @@ int32_t agp_vfe_post_rand(agp_vfe_post* p, int32_t layout, const void* Xs, int64
                           const void* Z, int32_t S, void* out);
 int32_t agp_vfe_post_free(agp_vfe_post* p);
 
+/* Device-pointer entry points (AGP_MEM_DEVICE and the agp_debug_* hooks): the library runs on its OWN non-blocking streams
+ * and returns after synchronising them, so results are complete on return -- but the CALLER must make sure the device
+ * buffers it passes in are complete (synchronise the stream that produced them) before the call. */
 /* ---- test hook for the tcgen05 int8-sliced fp64 trailing update (csrc/umma_ozaki.cu): DEVICE pointers;
  * C (M x N, ldc, fp64) -= P P' (lower tiles when lower_only), P = M x K fp64 (lda), S in 5..8 slices. */
 int32_t agp_debug_ozaki_syrk(agp_ctx* ctx, void* C_dev, int64_t ldc, const void* P_dev, int64_t lda, int64_t M,

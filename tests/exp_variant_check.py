@@ -32,6 +32,7 @@ def main():
             else:
                 os.environ.pop(k_, None)
         Cc = C0.clone()
+        torch.cuda.synchronize()  # the library works on its OWN stream: device inputs must be complete before the call
         eng.check(eng.L.agp_debug_ozaki_syrk(eng.h, C.c_void_p(Cc.data_ptr()), M, C.c_void_p(Pc.data_ptr()), M, M, N, K, S, 1))
         torch.cuda.synchronize()
         outs.append(Cc.cpu().numpy())

@@ -24,6 +24,7 @@ def _run(ag, M, N, K, S, lower, seed=0, integer=False):
     C0 = Cm.clone()
     Pc = P.t().contiguous()      # storage of the column-major M x K matrix
     Cc = Cm.t().contiguous()     # storage of the column-major (M+5) x N matrix
+    torch.cuda.synchronize()  # the library works on its own stream: device inputs must be complete before the call
     rc = eng.L.agp_debug_ozaki_syrk(eng.h, C.c_void_p(Cc.data_ptr()), ldc, C.c_void_p(Pc.data_ptr()), lda, M, N, K, S, int(lower))
     eng.check(rc)
     got = Cc.t()[:M, :N]
@@ -93,6 +94,7 @@ def test_ozaki_general_product(ag, M, N, K, S, cdt, adt, bdt, akm, bkm, sign):
     # storage: row-contiguous operand = col-major M x K = tensor [K, M]; k-major = tensor [M, K]
     Ast = A.contiguous() if akm else A.t().contiguous()
     Bst = B.contiguous() if bkm else B.t().contiguous()
+    torch.cuda.synchronize()
     rc = eng.L.agp_debug_ozaki_gemm(eng.h, C.c_void_p(Cst.data_ptr()), int(cdt == "f32"), M + 3, C.c_void_p(Ast.data_ptr()),
                                     int(adt == "f32"), akm, K if akm else M, M, C.c_void_p(Bst.data_ptr()), int(bdt == "f32"), bkm,
                                     K if bkm else N, N, K, S, sign)
@@ -119,6 +121,7 @@ def test_ozaki_fp32_syrk_lower(ag, N, K, S):
     C0 = torch.rand((N, M), generator=g, device="cuda", dtype=torch.float32)
     Cst = C0.clone()
     Pst = P.t().contiguous()
+    torch.cuda.synchronize()
     eng.check(eng.L.agp_debug_ozaki_gemm(eng.h, C.c_void_p(Cst.data_ptr()), 1, M, C.c_void_p(Pst.data_ptr()), 1, 0, M, M, None, 0, 0, 0,
                                          N, K, S, -1.0))
     want = C0.t().double() - P.double() @ P.double()[:N].t()

@@ -93,6 +93,7 @@ def test_strip_table_enumeration_matches_fp64(ag, R, me, kk, nto, W):
     Cst = torch.rand((ncols, ldc), generator=g, device="cuda", dtype=torch.float64)           # storage of col-major ldc x ncols
     C0 = Cst.clone()
     b_off = (loc[0] - (kk + 1)) * W
+    torch.cuda.synchronize()  # the library works on its own stream: device inputs must be complete before the call
     rc = eng.L.agp_debug_ozaki_syrk_map(eng.h, C.c_void_p(Cst.data_ptr()), ldc, C.c_void_p(P.data_ptr()), rows_below,
                                         rows_below, rows_below, ncols, K, S, R * W, W, b_off, 0)
     eng.check(rc)
