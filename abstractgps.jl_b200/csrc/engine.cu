@@ -1456,7 +1456,9 @@ int vfe_core(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
     if (ard_d) { sc.release(ard_d); vp->ard = ard_d; }
     vp->mean_kind = mean->kind == 2 ? 0 : mean->kind; vp->mean_c = mean->c;
   }
-  auto fail = [&](int code) { if (vp) agp_vfe_post_free(vp); return code; };
+  // every early return (CK / CKN failures, non-PD) releases the half-built handle and its buffers
+  struct VfeGuard { agp_vfe_post* p; ~VfeGuard() { if (p) agp_vfe_post_free(p); } } vguard{vp};
+  auto fail = [&](int code) { return code; };
 
   // (1) chol(K_zz + jitter)
   GramParams gz{};
@@ -1549,6 +1551,7 @@ int vfe_core(agp_ctx* ctx, const agp_kernel* k, const agp_mean* mean, const agp_
   T e = (T)elbo, dd = (T)dtc;
   if (elbo_out) memcpy(elbo_out, &e, sizeof(T));
   if (dtc_out) memcpy(dtc_out, &dd, sizeof(T));
+  vguard.p = nullptr;
   if (keep) *post_out = vp;
   return AGP_OK;
 }
