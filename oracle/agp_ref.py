@@ -13,7 +13,14 @@ be run here.  The oracle is instead pinned (tests/test_oracle.py) against
 independent implementations: scipy.stats.multivariate_normal.logpdf (mirror
 of test/finite_gp_projection.jl:143), naive inv/det formulas, and the
 relations the reference's own tests assert (collapse-on-data, sequential ==
-batch, VFE(z=x) == exact, elbo <= logpdf, operator identities).
+batch, VFE(z=x) == exact, elbo <= logpdf, operator identities); and
+(tests/test_oracle_independent_pins.py) against scikit-learn's
+GaussianProcessRegressor -- kernel matrices, log marginal likelihood, alpha,
+predictive mean / std for RBF, Matern 1/2, 3/2, 5/2 and DotProduct -- and
+against 60-digit mpmath arithmetic for logpdf, alpha, the DTC objective and the
+Titsias bound.  Its two distance formulations ("direct", what the CUDA kernel
+computes, and "gemm", what Distances.jl executes in the reference) are bounded
+against each other in tests/test_oracle.py.
 
 Kernel formulas are those of KernelFunctions.jl (un-vendored dependency,
 compat "0.9, 0.10", Project.toml:26), restated from its documented closed
