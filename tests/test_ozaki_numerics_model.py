@@ -118,3 +118,104 @@ def test_umma_noswizzle_chunk_layout_halves():
             assert (o < 2048) == (row < 64)
             seen.add(o)
     assert seen == set(range(4096))
+
+
+# ---- the v3 drain (round 2): exact int64 words + magic-number conversion + ONE rounding --------------------------------
+MAGIC = 0x4338000000000000        # bit pattern of 2^52 + 2^51
+MAGIC_D = 6755399441055744.0      # 2^52 + 2^51
+
+
+def i64_to_f64_exact(x):
+    """the device's i64_to_f64_exact: as_double(x + MAGIC) - (2^52 + 2^51), exact for |x| < 2^51"""
+    bits = (np.asarray(x, dtype=np.int64) + np.int64(MAGIC)).astype(np.int64)
+    return bits.view(np.float64) - MAGIC_D
+
+
+def oz_combine(acc, pair32):
+    """oz_combine<S, PAIR32> of csrc/umma_ozaki.cu on a [S, ...] int64 array of accumulators: value = sum_d acc_d 128^(3-d)"""
+    S = acc.shape[0]
+    a = acc.astype(np.int64)
+    if S <= 4:
+        h = a[0].copy()
+        for d in range(1, S):
+            h = h * 128 + a[d]
+        for _ in range(S, 4):
+            h = h * 128
+        return i64_to_f64_exact(h)
+    if pair32:
+        a32 = acc.astype(np.int32)
+        t = lambda d: (a32[d] * np.int32(128) + a32[d + 1]).astype(np.int64)   # int32 arithmetic, wraps like the device
+        h = t(0) * 16384 + t(2)
+        if S == 5:
+            l = a[4]
+        elif S == 6:
+            l = t(4)
+        elif S == 7:
+            l = t(4) * 128 + a[6]
+        else:
+            l = t(4) * 16384 + t(6)
+    else:
+        h = ((a[0] * 128 + a[1]) * 128 + a[2]) * 128 + a[3]
+        l = a[4].copy()
+        for d in range(5, S):
+            l = l * 128 + a[d]
+    lo_scale = {5: 1.0 / 128, 6: 1.0 / 16384, 7: 1.0 / 2097152, 8: 1.0 / 268435456}[S]
+    hh, ll = i64_to_f64_exact(h), i64_to_f64_exact(l)
+    # fma(ll, lo_scale, hh): ll * lo_scale is exact (power of two), so the fma equals one correctly rounded addition
+    return (ll * lo_scale) + hh
+
+
+def test_magic_number_conversion_is_exact_below_2_pow_51():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.integers(-(2 ** 51) + 1, 2 ** 51 - 1, 10000), [0, 1, -1, 2 ** 51 - 1, -(2 ** 51) + 1, 2 ** 45 + 3]])
+    assert np.array_equal(i64_to_f64_exact(x), x.astype(np.float64))          # |x| < 2^53: the cast is exact too
+    assert all(Fraction(float(v)) == int(u) for u, v in zip(x[:200], i64_to_f64_exact(x[:200])))
+
+
+@pytest.mark.parametrize("S", [3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("K,pair32", [(512, True), (512, False), (4096, False), (32768, False)])
+def test_v3_drain_is_exact_up_to_one_rounding(S, K, pair32):
+    """worst-case-magnitude and random accumulators: the int64 words stay below 2^51 for K <= 32768 (the bound
+    ozaki_update_ex enforces), both integer paths agree, and the result equals the exact rational value rounded once"""
+    rng = np.random.default_rng(S * 100 + K % 97)
+    lim = np.array([(d + 1) * K * 4096 for d in range(S)], dtype=np.int64)
+    assert lim.max() < 2 ** 31
+    acc = np.stack([rng.integers(-lim[d], lim[d] + 1, 64) for d in range(S)])
+    acc[:, 0] = lim           # all accumulators at their positive bound
+    acc[:, 1] = -lim
+    # word bounds
+    a = acc.astype(object)
+    h = sum(a[d] * 128 ** (3 - d) for d in range(min(S, 4)))
+    assert max(abs(int(v)) for v in h) < 2 ** 51
+    if S > 4:
+        l = sum(a[d] * 128 ** (S - 1 - d) for d in range(4, S))
+        assert max(abs(int(v)) for v in l) < 2 ** 51
+    got = oz_combine(acc, pair32 and K <= 512)
+    for j in range(acc.shape[1]):
+        ex = sum(Fraction(int(acc[d, j]), 1) * Fraction(128) ** (3 - d) for d in range(S))
+        g = Fraction(float(got[j]))
+        assert abs(g - ex) <= abs(ex) * Fraction(1, 2 ** 53) + Fraction(1, 2 ** 80), (S, K, j)
+    if S > 4 and K <= 512:
+        assert np.array_equal(oz_combine(acc, True), oz_combine(acc, False))   # the pair form is exact for K <= 512
+
+
+@pytest.mark.parametrize("S,bits", [(3, 21), (4, 28)])
+def test_fp32_operands_are_covered_by_short_splits(S, bits):
+    """fp32 panels sliced into S 7-bit digits: 4 slices (28 bits) hold the 24-bit significand of every element with |x| >= 2^-4 of
+    the row scale exactly; the product with the d <= S-1 diagonals reproduces fp32-precision results"""
+    rng = np.random.default_rng(S)
+    m, K = 32, 512
+    P = (rng.standard_normal((m, K)) * np.exp(rng.uniform(-3, 3, (m, 1)))).astype(np.float32).astype(np.float64)
+    q, scale, resid = slice_rows(P, S)
+    assert np.abs(q).max() <= 64
+    assert np.abs(resid).max() <= 2.0 ** (-7 * S)
+    if S == 4:   # 4 slices resolve 2^-27 of the row scale 2^e: a 24-bit significand with |x| >= 2^(e-4) is held exactly
+        big = np.abs(P) >= scale[:, None] * 2.0 ** -4
+        assert np.all(resid[big] == 0.0)
+    acc = accumulators(q, q, S)
+    v = oz_combine(acc, False)                      # value * 128^3
+    got = v * (scale[:, None] * 2.0 ** -33) * scale[None, :]
+    want = P @ P.T
+    bound = (2.0 ** (-7 * S + 3)) * np.outer(scale, scale) * K + 1e-300
+    assert np.all(np.abs(got - want) <= bound)
+    assert np.all(np.abs(got - want) <= 2.0 ** (-bits + 6) * np.outer(scale, scale) * np.sqrt(K) * 8 + 1e-300)
