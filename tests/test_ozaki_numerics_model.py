@@ -219,3 +219,40 @@ def test_fp32_operands_are_covered_by_short_splits(S, bits):
     bound = (2.0 ** (-7 * S + 3)) * np.outer(scale, scale) * K + 1e-300
     assert np.all(np.abs(got - want) <= bound)
     assert np.all(np.abs(got - want) <= 2.0 ** (-bits + 6) * np.outer(scale, scale) * np.sqrt(K) * 8 + 1e-300)
+
+
+def test_v3_slice_layout_matches_the_producer_addressing():
+    """ozaki_slice_kernel (bulk == 2) writes byte (row, k, slice s) of the panel at
+         chunk = ((row >> 7) * (K >> 5) + (k >> 5)) * S + s,   offset = chunk * 4096 + core-matrix offset(row & 127, k & 31);
+    the v3 producer fetches, for a 128-row tile at `arow` and k block kb, ONE run of S * 4096 bytes (A slices 0..S-1 in
+    order) and for a 64-row strip at `brow` S pieces of 2048 bytes at stride 4096 -- both must see exactly their rows."""
+    S, K, rows = 7, 128, 512
+    nkb = K >> 5
+
+    def core(row, kbyte):
+        g, r8, h = (row & 127) >> 3, row & 7, (kbyte >> 4) & 1
+        return ((g * 2 + h) * 8 + r8) * 16 + (kbyte & 15)
+
+    buf = np.full(((rows >> 7) * nkb * S * 4096, 3), -1, dtype=np.int64)   # (row, k, slice) stored at every byte
+    for row in range(rows):
+        for k in range(K):
+            for s in range(S):
+                chunk = ((row >> 7) * nkb + (k >> 5)) * S + s
+                buf[chunk * 4096 + core(row, k & 31)] = (row, k, s)
+    assert (buf[:, 0] >= 0).all()                                        # every byte written exactly once (a bijection)
+    rb_bytes = nkb * S * 4096
+    for arow, kb in ((0, 0), (128, 3), (384, 1)):
+        a = buf[(arow >> 7) * rb_bytes + kb * S * 4096:][: S * 4096]
+        for sl in range(S):
+            tile = a[sl * 4096:(sl + 1) * 4096]
+            assert set(tile[:, 2]) == {sl} and set(tile[:, 0]) == set(range(arow, arow + 128))
+            assert set(tile[:, 1]) == set(range(kb * 32, kb * 32 + 32))
+            # inside the tile: the UMMA no-swizzle K-major core-matrix layout (SBO 256 B, LBO 128 B)
+            r, k = 77, kb * 32 + 21
+            assert tuple(tile[core(r, 21)]) == (arow + r, k, sl)
+    for brow, kb in ((0, 2), (64, 0), (192, 3), (448, 1)):
+        base = (brow >> 7) * rb_bytes + (brow & 64) * 32 + kb * S * 4096
+        for sl in range(S):
+            piece = buf[base + sl * 4096:][:2048]
+            assert set(piece[:, 2]) == {sl} and set(piece[:, 0]) == set(range(brow, brow + 64))
+            assert set(piece[:, 1]) == set(range(kb * 32, kb * 32 + 32))
