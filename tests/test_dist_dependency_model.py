@@ -12,10 +12,11 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import dist_dependency_model as m  # noqa: E402
 
 
+@pytest.mark.parametrize("use_oz", [True, False])  # tcgen05 path (updates read the slices) / DMMA-FFMA path (they read the panel)
 @pytest.mark.parametrize("defer", [True, False])
 @pytest.mark.parametrize("R,nto", [(2, 4), (2, 9), (3, 10), (4, 11), (8, 16), (8, 17), (8, 5), (8, 33)])
-def test_shipped_schedule_has_no_unordered_conflicts(R, nto, defer):
-    assert m.check(R, nto, split_first=True, defer=defer) == []
+def test_shipped_schedule_has_no_unordered_conflicts(R, nto, defer, use_oz):
+    assert m.check(R, nto, split_first=True, defer=defer, use_oz=use_oz) == []
 
 
 def test_model_detects_the_round2_race_without_the_first_piece_rule():

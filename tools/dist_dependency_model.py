@@ -20,8 +20,9 @@ from collections import defaultdict
 
 
 class Rank:
-    def __init__(self, me, R, nto, G, split_first, defer):
+    def __init__(self, me, R, nto, G, split_first, defer, use_oz=True):
         self.me, self.R, self.nto, self.G, self.split_first, self.defer = me, R, nto, G, split_first, defer
+        self.use_oz = use_oz   # False: DMMA / FFMA trailing updates read the packed panel itself, nothing is sliced
         self.ops = []            # (name, stream, reads, writes, waits[event ids], record event id or None)
         self.next_event = 0
 
@@ -49,14 +50,17 @@ class Rank:
             w = pending_waits.pop(stream, [])
             self.op(name, stream, reads, writes, w, record)
 
+        def operand(kk):  # what a trailing update of step kk reads
+            return [("ws", kk & 1)] if self.use_oz else [("P", kk % 3, g) for g in range(G)]
+
         def issue_rest(kk, cols):
             e_rest[kk] = self.ev()
             if self.split_first and kk + 2 < nto and (kk + 2) % R == me and cols:
                 e_first[kk] = self.ev()
-                emit("rest%d:first" % kk, "s2", reads=[("ws", kk & 1)], writes=[("col", cols[0])], record=e_first[kk])
-                emit("rest%d" % kk, "s2", reads=[("ws", kk & 1)], writes=[("col", j) for j in cols[1:]], record=e_rest[kk])
+                emit("rest%d:first" % kk, "s2", reads=operand(kk), writes=[("col", cols[0])], record=e_first[kk])
+                emit("rest%d" % kk, "s2", reads=operand(kk), writes=[("col", j) for j in cols[1:]], record=e_rest[kk])
             else:
-                emit("rest%d" % kk, "s2", reads=[("ws", kk & 1)], writes=[("col", j) for j in cols], record=e_rest[kk])
+                emit("rest%d" % kk, "s2", reads=operand(kk), writes=[("col", j) for j in cols], record=e_rest[kk])
 
         e_start = self.ev()
         emit("gram", "s", writes=[("col", j) for j in range(nto) if j % R == me], record=e_start)
@@ -94,13 +98,16 @@ class Rank:
             if kk >= 2:
                 wait("s", e_rest.get(kk - 2))
             e_prep = self.ev()
-            emit("prepare%d" % kk, "s", reads=[("P", b3, g) for g in range(G)], writes=[("ws", kk & 1)], record=e_prep)
+            if self.use_oz:
+                emit("prepare%d" % kk, "s", reads=[("P", b3, g) for g in range(G)], writes=[("ws", kk & 1)], record=e_prep)
+            else:
+                emit("mark_prep%d" % kk, "s", record=e_prep)
             cols = self.local_cols_after(kk)
             next_is_mine = (kk + 1) % R == me
             if next_is_mine:
                 if kk >= 1:
                     wait("s", e_first.get(kk - 1) if self.split_first else None)
-                emit("colupd%d" % kk, "s", reads=[("ws", kk & 1)], writes=[("col", kk + 1)])
+                emit("colupd%d" % kk, "s", reads=operand(kk), writes=[("col", kk + 1)])
                 cols = cols[1:]
             if next_is_mine and self.defer:
                 deferred = (kk, cols)
@@ -116,9 +123,9 @@ class Rank:
         return self.ops
 
 
-def check(R, nto, G=4, split_first=True, defer=True):
+def check(R, nto, G=4, split_first=True, defer=True, use_oz=True):
     """returns the list of unordered conflicting op pairs (rank, op a, op b, object); empty = schedule is race-free"""
-    ranks = [Rank(me, R, nto, G, split_first, defer) for me in range(R)]
+    ranks = [Rank(me, R, nto, G, split_first, defer, use_oz) for me in range(R)]
     progs = [r.program() for r in ranks]
     # node ids: (rank, index); edges: stream order, event record -> waiter, owner's send -> every peer's matching recv
     nodes = [(r, i) for r in range(R) for i in range(len(progs[r]))]
