@@ -1,21 +1,26 @@
-// umma_ozaki.cu -- K5 on the 5th-generation tensor cores: the fp64 trailing update
-//     C (m x n, lower tiles, fp64)  -=  P P'          (P = the factored outer panel, m x K, fp64)
-// executed as EXACT int8 x int8 -> int32 products on tcgen05.mma.kind::i8 with TMEM accumulators,
-// operands staged by TMA (cp.async.bulk.tensor, 64-byte swizzle), recombined in fp64 in the epilogue
-// (Ozaki-style error-free splitting).  Replaces the LAPACK potrf trailing update inside
-// cholesky(_symmetric(C)) (/root/reference/src/finite_gp_projection.jl:308) for fp64_mode = 1.
+// umma_ozaki.cu -- K5 on the 5th-generation tensor cores: the trailing update and every other large product of the path
+//     C (m x n, fp64 or fp32)  +=  sign * A B'      (trailing update: B = A = the factored outer panel, lower tiles, sign -1)
+// executed as EXACT int8 x int8 -> int32 products on tcgen05.mma.kind::i8 with TMEM accumulators, operands staged by TMA,
+// recombined exactly and rounded once in the epilogue (Ozaki-style error-free splitting).  Replaces the LAPACK potrf
+// trailing update inside cholesky(_symmetric(C)) (/root/reference/src/finite_gp_projection.jl:308,
+// /root/reference/src/exact_gpr_posterior.jl:31), the rank-512 updates of `C.U' \ X`
+// (/root/reference/src/util/common_covmat_ops.jl:54,90) and the A A' accumulation of the VFE bound
+// (/root/reference/src/sparse_approximations.jl:296-299).
 //
-// Splitting.  Row i of P is scaled by 2^-e_i (e_i: exponent of the row maximum) to |x| < 1 and cut into
+// Splitting.  Row i of an operand is scaled by 2^-e_i (e_i: exponent of the row maximum) to |x| < 1 and cut into
 // S signed 7-bit slices  x = sum_s q_s 2^-(7s-1),  q_s in [-64, 64]  -- every step exact in fp64.
-// Then  p_i . p_j = 2^(e_i+e_j) sum_d 2^(-7d-5) ACC_d[i,j],  ACC_d = sum_{s+t=d+1} q_s . q_t  (int32, exact);
-// diagonals d > S are dropped (relative 2^(-7S)).  S = 7 gives ~2^-49, S = 8 ~2^-56 of the row scale.
+// Then  a_i . b_j = 2^(e_i+e_j) sum_d 2^(-7d-5) ACC_d[i,j],  ACC_d = sum_{s+t=d+1} q_s . q_t  (int32, exact);
+// diagonals d > S are dropped (relative 2^(-7S)).  fp64: S = 7 (~2^-49 of the row scale; 5..8 selectable);
+// fp32: S = 4 (28 bits >= the 24-bit significand).
 //
-// Kernel (one CTA per 128 x 64 output tile, 192 threads):
-//   warp 0  TMA producer : per 64-byte k-block, S slices x (128 A rows + 64 B rows) -> smem (2 stages)
-//   warp 1  MMA issuer   : for A slice s one MMA against the STACK of B slices 1..S+1-s (they are
-//                          consecutive in smem, so N = (S+1-s)*64 and the products land in consecutive
-//                          TMEM column blocks d = s..S): S+ceil MMAs per 32-byte K chunk instead of S(S+1)/2
-//   warps 2-5 epilogue   : tcgen05.ld the S int32 accumulators, Horner-combine in fp64, scale, C -= ...
+// Two kernels:
+//  * umma_ozaki_syrk_kernel (v1): one CTA per 128 x 64 output tile, row-major slices behind a 2-D tensor map (64-byte
+//    swizzle), Horner drain.  Generic shapes (ragged N, full rectangles of the fp64 debug entry); not on the hot path.
+//  * umma_ozaki_syrk_v3_kernel: the production kernel -- persistent or bounded CTAs, warp-specialised (producer / MMA
+//    issuer / 4 or 8 epilogue warps), slices in the blocked UMMA layout fetched with bulk copies; see its own header
+//    further down.  (The round-1 persistent kernel "v2" was removed in round 2; the tile-walk helpers keep its prefix.)
+//   warp 1 issues, for A slice s, one MMA against the STACK of B slices 1..S+1-s (consecutive in smem, so N = (S+1-s)*64
+//   and the products land in consecutive TMEM column blocks d = s..S): S+3 MMAs per 32-byte K chunk instead of S(S+1)/2.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
