@@ -300,24 +300,56 @@ AbstractGPs.mean(fx::FiniteGP{<:DeviceApproxPosterior}) = mean_and_var(fx)[1]
 AbstractGPs.var(fx::FiniteGP{<:DeviceApproxPosterior}) = mean_and_var(fx)[2]
 
 # ---- reverse-mode rule for logpdf (test/finite_gp_projection.jl:152-178, examples/1-mauna-loa/script.jl:200-242) ------
-# agp_post_logpdf_grad returns d logpdf / d (sigma_f^2, ScaleTransform s, LinearKernel c, noise, constant mean,
-# ARD weights) from the factor of ONE fit.  The pullback below hands these to ChainRulesCore as a Tangent of the FiniteGP
-# for the common parametrisation  f = GP(c, sigma2 * (k o ScaleTransform(s)))  / ARDTransform(v),  fx = f(x, noise).
+# agp_post_logpdf_grad returns, from the factor of ONE fit, d logpdf / d (total sigma_f^2, total ScaleTransform factor,
+# LinearKernel c, scalar noise, constant mean, total ARD weights) and the per-point noise gradient.  `logpdf_and_gradient`
+# exposes them flat; the `rrule` maps them back onto the nested kernel structs (chain rule through the products the shim
+# forms in `flat`: sigma_f^2 = prod of the ScaledKernel factors, w = prod of the transform scalings).  Inputs x are treated
+# as constants (NoTangent); a CustomMean closure is not differentiated.
 import ChainRulesCore
-function ChainRulesCore.rrule(::typeof(logpdf), fx::DevFiniteGP{T}, y::AbstractVector{<:Real}) where {T}
-    supported(fx.f) || return ChainRulesCore.rrule_via_ad(ChainRulesCore.NoForwardsMode(), logpdf, fx, y)
+const CRC = ChainRulesCore
+
+function logpdf_and_gradient(fx::DevFiniteGP{T}, y::AbstractVector{<:Real}) where {T}
     lp, post = fit(fx, y)
     D = points(fx.x)[3]; N = length(fx)
     g = Vector{Float64}(undef, 5 + D); nd = Vector{T}(undef, N)
     c = ctx()
     lock(c.lock) do
-        check(c, ccall((:agp_post_logpdf_grad, libagp), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}), post.data.C.h, g, nd))
+        GC.@preserve g nd check(c, ccall((:agp_post_logpdf_grad, libagp), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}), post.data.C.h, g, nd))
     end
+    return lp, (variance=g[1], scale=g[2], linear_c=g[3], noise=g[4], mean_c=g[5], ard=g[6:end], noise_diag=nd, y=-post.data.α)
+end
+
+# tangent of a (nested) kernel: `tot` carries the flattened totals the gradients refer to
+kernel_tangent(k::Stationary, g, var, w) = CRC.NoTangent()
+kernel_tangent(k::LinearKernel, g, var, w) = CRC.Tangent{typeof(k)}(; c=[g.linear_c])
+function kernel_tangent(k::ScaledKernel, g, var, w)          # d/d sigma_i^2 = d/d var * var / sigma_i^2
+    CRC.Tangent{typeof(k)}(; kernel=kernel_tangent(k.kernel, g, var, w), σ²=[g.variance * var / only(k.σ²)])
+end
+function kernel_tangent(k::TransformedKernel{<:Any,<:ScaleTransform}, g, var, w)
+    s_i = only(k.transform.s)
+    ds = w isa Real ? g.scale * w / s_i : sum(g.ard .* w) / s_i      # scalar layer under vector totals: sum over dimensions
+    CRC.Tangent{typeof(k)}(; kernel=kernel_tangent(k.kernel, g, var, w), transform=CRC.Tangent{typeof(k.transform)}(; s=[ds]))
+end
+function kernel_tangent(k::TransformedKernel{<:Any,<:ARDTransform}, g, var, w)
+    dv = g.ard .* w ./ k.transform.v                                    # d/d v_i[d] = d/d w[d] * w[d] / v_i[d]
+    CRC.Tangent{typeof(k)}(; kernel=kernel_tangent(k.kernel, g, var, w), transform=CRC.Tangent{typeof(k.transform)}(; v=dv))
+end
+mean_tangent(m::AbstractGPs.ConstMean, g) = CRC.Tangent{typeof(m)}(; c=g.mean_c)
+mean_tangent(m, g) = CRC.NoTangent()
+noise_tangent(Σ::Diagonal{<:Any,<:Fill}, g) = CRC.Tangent{typeof(Σ)}(; diag=CRC.Tangent{typeof(Σ.diag)}(; value=g.noise))
+noise_tangent(Σ::Diagonal, g) = CRC.Tangent{typeof(Σ)}(; diag=collect(g.noise_diag))
+
+function CRC.rrule(::typeof(logpdf), fx::DevFiniteGP{T}, y::AbstractVector{<:Real}) where {T}
+    supported(fx.f) || return nothing                                     # no rule: AD differentiates the stock method
+    lp, g = logpdf_and_gradient(fx, y)
+    _, var, _, w = flat(fx.f.kernel)
+    w === nothing && (w = 1.0)
     function logpdf_pullback(Δ)
-        d = ChainRulesCore.unthunk(Δ)
-        grads = (variance=d * g[1], scale=d * g[2], linear_c=d * g[3], noise=d .* nd, mean_c=d * g[5], ard=d .* g[6:end],
-                 y=-d .* post.data.α)              # d logpdf / dy = -alpha
-        return ChainRulesCore.NoTangent(), ChainRulesCore.Tangent{typeof(fx)}(; agp_gradients=grads), grads.y
+        d = CRC.unthunk(Δ)
+        gs = map(v -> v isa Number ? d * v : d .* v, g)
+        f̄ = CRC.Tangent{typeof(fx.f)}(; mean=mean_tangent(fx.f.mean, gs), kernel=kernel_tangent(fx.f.kernel, gs, var, w))
+        f̄x = CRC.Tangent{typeof(fx)}(; f=f̄, x=CRC.NoTangent(), Σy=noise_tangent(fx.Σy, gs))
+        return CRC.NoTangent(), f̄x, gs.y
     end
     return lp, logpdf_pullback
 end
